@@ -1,0 +1,358 @@
+"""Generators for the BASELINE.json workloads as `ClusteredSDP`s.
+
+They restate the problem definitions of the reference's examples so that the
+oracle and the device library can be fed identical inputs without Julia:
+
+  maxcut          README.md:39-65           (config 2, dense constraint path)
+  polyopt         examples/PolyOpt.jl:7-30  (config 1)
+  delsarte        examples/Delsarte.jl:7-49 (config 3)
+  sphere_packing  examples/SpherePacking.jl:13-115 (config 5)
+
+and the pieces of src/basesandsamples.jl:28-99,146-169 and
+src/approximate_fekete.jl:25-50 they use.  Everything is evaluated with mpmath
+at prec+64 bits and rounded to `prec` bits on conversion to wire numbers
+(what convert_to_prec does, src/interface.jl:1078-1112).  Cluster / block /
+free-variable ORDER is this module's own (the reference orders them by `hash`,
+src/interface.jl:885,1032, which only relabels the problem).
+"""
+from __future__ import annotations
+
+import math
+from fractions import Fraction
+
+import numpy as np
+import mpmath
+from mpmath import mpf
+
+from . import wire
+from .sdp import ClusteredSDP, Cluster, PSDBlock, LowRankTerm
+
+
+# ---------------------------------------------------------------------------
+# bases and sample points (src/basesandsamples.jl)
+# ---------------------------------------------------------------------------
+def chebyshev_values(d, x):
+    """T_0..T_d at x  (basis_chebyshev, src/basesandsamples.jl:66-76)."""
+    v = [mpf(1)]
+    if d >= 1:
+        v.append(x)
+    for _ in range(2, d + 1):
+        v.append(2 * x * v[-1] - v[-2])
+    return v
+
+
+def gegenbauer_values(d, n, x):
+    """Gegenbauer polynomials in dimension n, normalised to 1 at 1 (src/basesandsamples.jl:86-96)."""
+    v = [mpf(1)]
+    if d >= 1:
+        v.append(x)
+    for l in range(2, d + 1):
+        v.append(mpf(2 * l + n - 4) / (l + n - 3) * x * v[-1] - mpf(l - 1) / (l + n - 3) * v[-2])
+    return v
+
+
+def laguerre_values(d, alpha, x):
+    """Generalised Laguerre L_0..L_d (src/basesandsamples.jl:28-38)."""
+    v = [mpf(1)]
+    if d >= 1:
+        v.append(1 + alpha - x)
+    for l in range(2, d + 1):
+        v.append(((2 * l - 1 + alpha - x) * v[-1] - (l + alpha - 1) * v[-2]) / l)
+    return v
+
+
+def laguerre_coefficients(d, alpha, scale):
+    """Coefficient lists (low degree first) of L_k^alpha(scale*x), k=0..d."""
+    polys = [[mpf(1)]]
+    if d >= 1:
+        polys.append([1 + alpha, -scale])
+    for l in range(2, d + 1):
+        a, b = polys[-1], polys[-2]
+        new = [mpf(0)] * (l + 1)
+        for i, c in enumerate(a):
+            new[i] += (2 * l - 1 + alpha) * c
+            new[i + 1] -= scale * c
+        for i, c in enumerate(b):
+            new[i] -= (l + alpha - 1) * c
+        polys.append([c / l for c in new])
+    return polys
+
+
+def sample_points_chebyshev(d, a=-1, b=1):
+    """d+1 Chebyshev points in [a,b] (src/basesandsamples.jl:162-169)."""
+    a, b = mpf(a), mpf(b)
+    return [(a + b) / 2 + (b - a) / 2 * mpmath.cospi(mpf(2 * k - 1) / (2 * (d + 1))) for k in range(1, d + 2)]
+
+
+def sample_points_rescaled_laguerre(d):
+    """(src/basesandsamples.jl:146-155)"""
+    const = -mpmath.sqrt(mpmath.pi) / (64 * (d + 1) * mpmath.log(3 - 2 * mpmath.sqrt(2)))
+    return [const * (-1 + 4 * k) ** 2 for k in range(d + 1)]
+
+
+def approximatefekete(V, samples, s=3):
+    """Orthogonalise the basis w.r.t. the samples (src/approximate_fekete.jl:6-22,51-80).
+
+    V[i][k] = basis_k(sample_i).  QR in Float64, basis change in high precision.
+    With as many samples as basis functions every point is kept; rows are
+    returned sorted by sample.  Returns (V', samples').
+    """
+    V = mpmath.matrix(V)
+    n = V.cols
+    assert V.rows == n, "only the square (univariate) case is needed for the configs"
+    for _ in range(s + 1):
+        F = np.array([[float(V[i, j]) for j in range(n)] for i in range(V.rows)])
+        R = np.linalg.qr(F, mode="r")
+        U = np.linalg.solve(R, np.eye(n))
+        Um = mpmath.matrix(n, n)
+        for i in range(n):
+            for j in range(i, n):
+                Um[i, j] = mpf(float(U[i, j]))
+        V = V * Um
+    order = sorted(range(len(samples)), key=lambda i: samples[i])
+    Vs = mpmath.matrix(V.rows, n)
+    for ii, i in enumerate(order):
+        for j in range(n):
+            Vs[ii, j] = V[i, j]
+    return Vs, [samples[i] for i in order]
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+def _w(values, prec):
+    return wire.to_wire(values, prec)
+
+
+def _rank1(r, s, p, lam, vec, prec):
+    return LowRankTerm(r, s, p, _w([lam], prec), _w([list(vec)], prec), _w([list(vec)], prec))
+
+
+class _Lazy:
+    """Dense constraint matrix produced on demand (keeps host memory bounded for n=300)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __array__(self, dtype=None, copy=None):
+        return self.fn()
+
+
+# ---------------------------------------------------------------------------
+# config 2: Goemans-Williamson MAX-CUT relaxation (README.md:39-65)
+# ---------------------------------------------------------------------------
+def laplacian_random(n, p=0.5, seed=0):
+    rng = np.random.default_rng(seed)
+    A = np.triu((rng.random((n, n)) < p).astype(np.int64), 1)
+    A = A + A.T
+    return np.diag(A.sum(axis=1)) - A
+
+
+def laplacian_complete(n):
+    return n * np.eye(n, dtype=np.int64) - np.ones((n, n), dtype=np.int64)
+
+
+def laplacian_cycle(n):
+    L = 2 * np.eye(n, dtype=np.int64)
+    for i in range(n):
+        L[i, (i + 1) % n] -= 1
+        L[(i + 1) % n, i] -= 1
+    return L
+
+
+def maxcut(L, prec=256):
+    """maximize <L/4, X> s.t. X_ii = 1, X PSD; every E_ii is passed as a dense matrix (dense path)."""
+    L = np.asarray(L)
+    n = L.shape[0]
+    with mpmath.workprec(prec + 64):
+        Cw = wire.wire_zeros((n, n), prec)
+        cache = {}
+        for i in range(n):
+            for j in range(n):
+                v = int(L[i, j])
+                if v == 0:
+                    continue
+                if v not in cache:
+                    cache[v] = _w(mpf(v) / 4, prec)[()]
+                Cw[i, j] = cache[v]
+        one = _w(1, prec)[()]
+        blk = PSDBlock(m=1, delta=n, high_rank=True, C=Cw, name="X")
+
+        def make(i):
+            def fn():
+                A = wire.wire_zeros((n, n), prec)
+                A[i, i] = one
+                return A
+            return fn
+
+        for i in range(n):
+            blk.dense[i] = _Lazy(make(i))
+        c = wire.wire_zeros((n,), prec)
+        c[:] = one
+        cl = Cluster(B=wire.wire_zeros((n, 0), prec), c=c, blocks=[blk])
+        return ClusteredSDP(prec=prec, maximize=True, constant=_w(0, prec), b=wire.wire_zeros((0,), prec),
+                            clusters=[cl], name=f"maxcut(n={n})")
+
+
+# ---------------------------------------------------------------------------
+# config 1: univariate polynomial minimisation (examples/PolyOpt.jl:7-30)
+# ---------------------------------------------------------------------------
+def polyopt(f, d, prec=256, name=None):
+    """maximize lambda s.t. f - lambda is a sum of squares of degree 2d.
+
+    `f` is a callable evaluating the polynomial (degree <= 2d) at an mpf.
+    Chebyshev basis T_0..T_d, 2d+1 Chebyshev sample points on [-1,1].
+    """
+    with mpmath.workprec(prec + 64):
+        samples = sample_points_chebyshev(2 * d, -1, 1)
+        P = len(samples)
+        blk = PSDBlock(m=1, delta=d + 1, high_rank=False, C=wire.wire_zeros((d + 1, d + 1), prec), name=("sos", 1))
+        for p, x in enumerate(samples):
+            blk.lowrank.append(_rank1(0, 0, p, 1, chebyshev_values(d, x), prec))
+        B = _w([[1]] * P, prec)
+        c = _w([f(x) for x in samples], prec)
+        cl = Cluster(B=B, c=c, blocks=[blk])
+        return ClusteredSDP(prec=prec, maximize=True, constant=_w(0, prec), b=_w([1], prec), clusters=[cl],
+                            name=name or f"polyopt(d={d})")
+
+
+def polyopt_random(d=20, seed=0, prec=256):
+    """Config 1: degree-2d polynomial with N(0,1) Chebyshev coefficients (seed) plus 2*T_2d."""
+    rng = np.random.default_rng(seed)
+    coef = [float(v) for v in rng.standard_normal(2 * d + 1)]
+    coef[2 * d] += 2.0
+
+    def f(x):
+        T = chebyshev_values(2 * d, x)
+        return mpmath.fsum(mpf(cf) * t for cf, t in zip(coef, T))
+
+    return polyopt(f, d, prec, name=f"polyopt_random(d={d},seed={seed})")
+
+
+# ---------------------------------------------------------------------------
+# config 3: Delsarte LP bound (examples/Delsarte.jl:7-49)
+# ---------------------------------------------------------------------------
+def delsarte(n, d, costheta, prec=256):
+    with mpmath.workprec(prec + 64):
+        ct = mpf(costheta.numerator) / costheta.denominator if isinstance(costheta, Fraction) else mpf(costheta)
+        samples = sample_points_chebyshev(2 * d, -1, ct)
+        V = [chebyshev_values(2 * d, x) for x in samples]
+        V, samples = approximatefekete(V, samples)
+        ns = len(samples)                 # 2d+1
+        P = ns + 1
+        blocks = []
+        # (:a, k), k = 1..2d : dense 1x1 blocks, coefficient gp[k](x) in constraint 1 and 1 in constraint 2
+        gp = [gegenbauer_values(2 * d, n, x) for x in samples]
+        for k in range(1, 2 * d + 1):
+            blk = PSDBlock(m=1, delta=1, high_rank=True, C=wire.wire_zeros((1, 1), prec), name=("a", k))
+            for p in range(ns):
+                blk.dense[p] = _w([[gp[p][k]]], prec)
+            blk.dense[ns] = _w([[1]], prec)
+            blocks.append(blk)
+        sos1 = PSDBlock(m=1, delta=d + 1, high_rank=False, C=wire.wire_zeros((d + 1, d + 1), prec), name=("SOS", 1))
+        sos2 = PSDBlock(m=1, delta=d, high_rank=False, C=wire.wire_zeros((d, d), prec), name=("SOS", 2))
+        for p, x in enumerate(samples):
+            sos1.lowrank.append(_rank1(0, 0, p, 1, [V[p, k] for k in range(d + 1)], prec))
+            sos2.lowrank.append(_rank1(0, 0, p, (1 + x) * (ct - x), [V[p, k] for k in range(d)], prec))
+        blocks += [sos1, sos2]
+        slack = PSDBlock(m=1, delta=1, high_rank=True, C=wire.wire_zeros((1, 1), prec), name="slack")
+        slack.dense[ns] = _w([[1]], prec)
+        blocks.append(slack)
+        B = _w([[0]] * ns + [[-1]], prec)
+        c = _w([-1] * P, prec)
+        cl = Cluster(B=B, c=c, blocks=blocks)
+        return ClusteredSDP(prec=prec, maximize=False, constant=_w(0, prec), b=_w([1], prec), clusters=[cl],
+                            name=f"delsarte(n={n},d={d})")
+
+
+# ---------------------------------------------------------------------------
+# config 5: N-radii sphere packing (examples/SpherePacking.jl:13-115)
+# ---------------------------------------------------------------------------
+def sphere_packing(n, d, r, prec=256):
+    with mpmath.workprec(prec + 64):
+        Nr = len(r)
+        r = [mpf(v.numerator) / v.denominator if isinstance(v, Fraction) else mpf(v) for v in r]
+        pairs = [(i, j) for i in range(Nr) for j in range(i + 1)]        # i >= j
+        T = len(pairs)
+        deg = 2 * d + 1
+        ns = deg + 1                                                     # samples per polynomial constraint
+        alpha = mpf(n) / 2 - 1
+        # free variables: (k,i,j) for k=0..2d+1, then M
+        fidx = {}
+        for (i, j) in pairs:
+            for k in range(deg + 1):
+                fidx[(k, i, j)] = len(fidx)
+        fidx["M"] = len(fidx)
+        N = len(fidx)
+
+        def vol(rad):
+            return mpmath.sqrt(mpmath.pi) ** n / mpmath.gamma(mpf(n) / 2 + 1) * rad ** n
+
+        # orthogonalised Laguerre basis on the rescaled Laguerre points (:50-54)
+        samples = sample_points_rescaled_laguerre(deg)
+        polys = laguerre_coefficients(deg, alpha, 2 * mpmath.pi)
+        maxc = [max(pl) for pl in polys]
+        V = [[mpmath.polyval(list(reversed(polys[k])), x) / maxc[k] for k in range(deg + 1)] for x in samples]
+        V, samples = approximatefekete(V, samples)
+        basis = lambda p, cnt: [V[p, k] for k in range(cnt)]
+        zeroB = lambda rows: [[mpf(0)] * N for _ in range(rows)]
+        clusters = []
+
+        # constraint 1 (:33-48): cluster PSD1, one block with Nr x Nr subblocks of size 1
+        blk = PSDBlock(m=Nr, delta=1, high_rank=False, C=wire.wire_zeros((Nr, Nr), prec), name="PSD1")
+        Bm, cv = zeroB(T), []
+        for p, (i, j) in enumerate(pairs):
+            cv.append(-mpmath.sqrt(vol(r[i]) * vol(r[j])))
+            Bm[p][fidx[(0, i, j)]] = mpf(-1)
+            if i != j:
+                blk.lowrank.append(_rank1(i, j, p, mpf(1) / 2, [1], prec))
+                blk.lowrank.append(_rank1(j, i, p, mpf(1) / 2, [1], prec))
+            else:
+                blk.lowrank.append(_rank1(i, i, p, 1, [1], prec))
+        clusters.append(Cluster(B=_w(Bm, prec), c=_w(cv, prec), blocks=[blk]))
+
+        # constraint 2 (:56-81): cluster SOS2, blocks SOS21 and SOS22 with Nr x Nr subblocks of size d+1
+        b21 = PSDBlock(m=Nr, delta=d + 1, high_rank=False, C=wire.wire_zeros((Nr * (d + 1),) * 2, prec), name="SOS21")
+        b22 = PSDBlock(m=Nr, delta=d + 1, high_rank=False, C=wire.wire_zeros((Nr * (d + 1),) * 2, prec), name="SOS22")
+        Bm = zeroB(T * ns)
+        row = 0
+        for (i, j) in pairs:
+            for p, x in enumerate(samples):
+                vec = basis(p, d + 1)
+                for k in range(deg + 1):
+                    Bm[row][fidx[(k, i, j)]] = (-2 if i != j else -1) * x ** k
+                for (a, b_) in ([(i, j), (j, i)] if i != j else [(i, i)]):
+                    b21.lowrank.append(_rank1(a, b_, row, 1, vec, prec))
+                    b22.lowrank.append(_rank1(a, b_, row, x, vec, prec))
+                row += 1
+        clusters.append(Cluster(B=_w(Bm, prec), c=_w([0] * (T * ns), prec), blocks=[b21, b22]))
+
+        # constraint 3 (:83-95): one cluster per pair, blocks SOS31 (1x1) and SOS32 (d+1)
+        fact = [mpmath.factorial(k) / mpmath.pi ** k for k in range(deg + 1)]
+        for (i, j) in pairs:
+            b31 = PSDBlock(m=1, delta=1, high_rank=False, C=wire.wire_zeros((1, 1), prec), name=("SOS31", i, j))
+            b32 = PSDBlock(m=1, delta=d + 1, high_rank=False, C=wire.wire_zeros((d + 1, d + 1), prec), name=("SOS32", i, j))
+            Bm = zeroB(ns)
+            for p, x in enumerate(samples):
+                Lv = laguerre_values(deg, alpha, mpmath.pi * x)
+                for k in range(deg + 1):
+                    Bm[p][fidx[(k, i, j)]] = fact[k] * Lv[k]
+                b31.lowrank.append(_rank1(0, 0, p, 1, basis(p, 1), prec))
+                b32.lowrank.append(_rank1(0, 0, p, x - (r[i] + r[j]) ** 2, basis(p, d + 1), prec))
+            clusters.append(Cluster(B=_w(Bm, prec), c=_w([0] * ns, prec), blocks=[b31, b32]))
+
+        # constraint 4 (:97-107): one cluster per radius, a dense 1x1 slack block
+        L0 = laguerre_values(deg, alpha, mpf(0))
+        for i in range(Nr):
+            sl = PSDBlock(m=1, delta=1, high_rank=True, C=wire.wire_zeros((1, 1), prec), name=("slack4", i))
+            sl.dense[0] = _w([[1]], prec)
+            Bm = zeroB(1)
+            for k in range(deg + 1):
+                Bm[0][fidx[(k, i, i)]] = fact[k] * L0[k]
+            Bm[0][fidx["M"]] = mpf(-1)
+            clusters.append(Cluster(B=_w(Bm, prec), c=_w([0], prec), blocks=[sl]))
+
+        bvec = [mpf(0)] * N
+        bvec[fidx["M"]] = mpf(1)
+        return ClusteredSDP(prec=prec, maximize=False, constant=_w(0, prec), b=_w(bvec, prec), clusters=clusters,
+                            name=f"sphere_packing(n={n},d={d},Nr={Nr})")
