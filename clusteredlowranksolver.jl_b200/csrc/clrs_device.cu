@@ -1,0 +1,737 @@
+// clrs_device.cu — host driver of the B200 hot path and the C ABI (include/clrs_b200.h).
+//
+// One handle = one SDP resident in HBM.  clrs_iterate runs one predictor-corrector
+// iteration of src/solver.jl:362-592 as a stream of kernels; every scalar decision
+// of the loop body (mu, beta_c, step lengths, the safe-step rule, objectives) is
+// taken ON the device by small scalar kernels, so the host synchronises once per
+// iteration, to read the report.  No CPU fallback exists in this file.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <tuple>
+#include <algorithm>
+#include <stdexcept>
+#include <cuda_runtime.h>
+#include "../../include/clrs_b200.h"
+#include "kernels.cuh"
+#include "gemm_tc.cuh"
+#include "wire_host.h"
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+static inline int grid_for(int64_t n, int bs = 256, int cap = 148 * 8) { int64_t g = (n + bs - 1) / bs; if (g < 1) g = 1; return (int)std::min<int64_t>(g, cap); }
+
+// scalar slots in device memory
+enum { SC_MU, SC_MUP, SC_MUC, SC_BETA, SC_BETAC, SC_ALPHAD, SC_ALPHAP, SC_D0, SC_D1, SC_D2, SC_D3, SC_DOBJ, SC_POBJ, SC_GAP,
+       SC_ERRP, SC_ERRp, SC_ERRd, SC_CX, SC_CY, SC_BY, SC_K, SC_ONE, SC_BETA_INF, SC_BETA_FEAS, SC_GAMMA, SC_OMEGA_P, SC_OMEGA_D,
+       SC_GAPTHR, SC_DERRTHR, SC_PERRTHR, SC_MAXGAP, SC_STEPTHR, SC_CONSTANT, SC_ZERO, SC_TMP, SC_COUNT };
+enum { FL_PDFEAS, FL_STOP, FL_STATUS, FL_COUNT };
+enum { INFO_MU, INFO_DOBJ, INFO_POBJ, INFO_GAP, INFO_ERRP, INFO_ERRp, INFO_ERRd, INFO_ALPHAD, INFO_ALPHAP, INFO_BETAC, INFO_COUNT };
+
+struct ScalarCfg { int correctoronly, safe_step, maximize; };
+
+// the scalar logic of the loop body, one thread
+template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, double* info, ScalarCfg cfg,
+                                           int nblocks, const int32_t* bn, const int64_t* boff, const mpn<NL>* M, const mpn<NL>* dM,
+                                           const double* lam, int which) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typedef mpn<NL> num;
+  if (phase == 0) {            // mu, mu_p  (src/solver.jl:369-380)
+    num mu; mp_div(mu, sc[SC_D0], sc[SC_K]); sc[SC_MU] = mu;
+    num mup; mp_zero(mup);
+    if (cfg.correctoronly) mup = mu; else if (!fl[FL_PDFEAS]) mp_mul(mup, sc[SC_BETA_INF], mu);
+    sc[SC_MUP] = mup;
+    info[INFO_MU] = mp_to_double(mu);
+    if (mp_cmp(mu, sc[SC_MAXGAP]) > 0) fl[FL_STOP] = CLRS_STOP_MAX_COMPLEMENTARY_GAP;
+  } else if (phase == 1) {     // beta, beta_c, mu_c with the STALE pd_feas, then the fresh errors/pd_feas (src/solver.jl:429-447)
+    num s, t, r, beta, betac;
+    mp_add(s, sc[SC_D0], sc[SC_D1]); mp_add(s, s, sc[SC_D2]); mp_add(s, s, sc[SC_D3]);
+    mp_mul(t, sc[SC_MU], sc[SC_K]); mp_div(r, s, t);
+    if (mp_cmp(r, sc[SC_ONE]) < 0) mp_mul(beta, r, r); else beta = r;
+    if (fl[FL_PDFEAS]) { betac = mp_cmp(sc[SC_BETA_FEAS], beta) > 0 ? sc[SC_BETA_FEAS] : beta; if (mp_cmp(betac, sc[SC_ONE]) > 0) betac = sc[SC_ONE]; }
+    else betac = mp_cmp(sc[SC_BETA_INF], beta) > 0 ? sc[SC_BETA_INF] : beta;
+    sc[SC_BETA] = beta; sc[SC_BETAC] = betac; num muc; mp_mul(muc, betac, sc[SC_MU]); sc[SC_MUC] = muc;
+    num de = mp_cmp_abs(sc[SC_ERRP], sc[SC_ERRp]) > 0 ? sc[SC_ERRP] : sc[SC_ERRp];
+    fl[FL_PDFEAS] = (mp_cmp(de, sc[SC_DERRTHR]) < 0) && (mp_cmp(sc[SC_ERRd], sc[SC_PERRTHR]) < 0);
+    info[INFO_BETAC] = mp_to_double(betac);
+    info[INFO_ERRP] = mp_to_double(sc[SC_ERRP]); info[INFO_ERRp] = mp_to_double(sc[SC_ERRp]); info[INFO_ERRd] = mp_to_double(sc[SC_ERRd]);
+  } else if (phase == 2) {     // step length from the per-block smallest eigenvalues (src/solver.jl:1684-1692)
+    num mn; bool have = false;
+    for (int b = 0; b < nblocks; b++) {
+      num ev;
+      if (bn[b] == 1) mp_div(ev, dM[boff[b]], M[boff[b]]);
+      else { num c; mp_from_double(ev, lam[b]); mp_from_double(c, 1e-5); mp_sub(ev, ev, c); }
+      if (!have || mp_cmp(ev, mn) < 0) { mn = ev; have = true; }
+    }
+    num ng = sc[SC_GAMMA]; ng.sign = -ng.sign; num alpha;
+    const bool unsafe_step = fl[FL_PDFEAS] && !cfg.safe_step;
+    if (mp_cmp(mn, ng) > 0 && !unsafe_step) alpha = sc[SC_ONE]; else mp_div(alpha, ng, mn);
+    sc[which] = alpha;
+  } else if (phase == 3) {     // threshold test and the safe-step rule (src/solver.jl:470-483)
+    num ad = sc[SC_ALPHAD], ap = sc[SC_ALPHAP];
+    info[INFO_ALPHAD] = mp_to_double(ad); info[INFO_ALPHAP] = mp_to_double(ap);
+    num mn = mp_cmp(ad, ap) < 0 ? ad : ap;
+    if (mp_cmp(mn, sc[SC_STEPTHR]) < 0) { fl[FL_STOP] = CLRS_STOP_STEP_TOO_SHORT; mp_zero(sc[SC_ALPHAD]); mp_zero(sc[SC_ALPHAP]); }
+    else if (fl[FL_PDFEAS] && cfg.safe_step) { sc[SC_ALPHAD] = mn; sc[SC_ALPHAP] = mn; }
+    if (fl[FL_STOP] == CLRS_STOP_MAX_COMPLEMENTARY_GAP) { mp_zero(sc[SC_ALPHAD]); mp_zero(sc[SC_ALPHAP]); }
+  } else if (phase == 4) {     // objectives and gap (src/solver.jl:792-847)
+    num d = sc[SC_CX]; if (!cfg.maximize) d.sign = -d.sign; mp_add(d, d, sc[SC_CONSTANT]);
+    num p; mp_add(p, sc[SC_CY], sc[SC_BY]); mp_add(p, p, sc[SC_CONSTANT]);
+    num a, b; mp_sub(a, d, p); a.sign = a.sign ? 1 : 0; mp_add(b, d, p); b.sign = b.sign ? 1 : 0;
+    if (mp_cmp(b, sc[SC_ONE]) < 0) b = sc[SC_ONE];
+    num g; mp_div(g, a, b);
+    sc[SC_DOBJ] = d; sc[SC_POBJ] = p; sc[SC_GAP] = g;
+    info[INFO_DOBJ + 10] = mp_to_double(d); info[INFO_POBJ + 10] = mp_to_double(p); info[INFO_GAP + 10] = mp_to_double(g);
+  } else if (phase == 5) {     // pd_feas from the current errors (initialisation, src/solver.jl:326-333)
+    num de = mp_cmp_abs(sc[SC_ERRP], sc[SC_ERRp]) > 0 ? sc[SC_ERRP] : sc[SC_ERRp];
+    fl[FL_PDFEAS] = (mp_cmp(de, sc[SC_DERRTHR]) < 0) && (mp_cmp(sc[SC_ERRd], sc[SC_PERRTHR]) < 0);
+    info[INFO_ERRP] = mp_to_double(sc[SC_ERRP]); info[INFO_ERRp] = mp_to_double(sc[SC_ERRp]); info[INFO_ERRd] = mp_to_double(sc[SC_ERRd]);
+  }
+}
+// small vector kernels
+template <int NL> __global__ void k_vec_rhs(int n, mpn<NL>* dx, const mpn<NL>* d, const mpn<NL>* tr) {   // dx = -d - tr
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return; mpn<NL> a = d[i], b = tr[i], r; a.sign = -a.sign; mp_sub(r, a, b); dx[i] = r;
+}
+template <int NL> __global__ void k_set_diag(int n, mpn<NL>* A, int ld, const mpn<NL>* v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return; A[(int64_t)i * ld + i] = *v;
+}
+// S[plist[a], plist[b]] += T[a,b] for b >= a
+template <int NL> __global__ void k_scatter_upper(int np, const int32_t* plist, const mpn<NL>* T, mpn<NL>* S, int ldS) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (idx >= (int64_t)np * np) return;
+  int a = (int)(idx / np), b = (int)(idx % np); if (b < a) return;
+  int p = plist[a], q = plist[b]; mpn<NL>* dst = S + (int64_t)min(p, q) * ldS + max(p, q);
+  mpn<NL> o = *dst, t = T[idx]; mp_add(o, o, t); *dst = o;
+}
+
+// ---------------------------------------------------------------------------
+struct SolverBase {
+  std::string err; clrs_options opt; int prec = 256;
+  virtual ~SolverBase() {}
+  virtual int set_option_num(int which, const void* w) = 0;
+  virtual int set_free(int N, const void* b, const void* constant, int maximize) = 0;
+  virtual int add_cluster(int j, int P, const void* B, const void* c) = 0;
+  virtual int add_block(int j, int l, int m, int delta, int high_rank, const void* C) = 0;
+  virtual int add_dense_term(int j, int l, int p, const void* A) = 0;
+  virtual int add_lowrank_term(int j, int l, int r, int s, int p, int rank, const void* lam, const void* vs, const void* ws) = 0;
+  virtual int finalize() = 0;
+  virtual int set_state(const void* x, const void* X, const void* y, const void* Y) = 0;
+  virtual int get_state(void* x, void* X, void* y, void* Y) = 0;
+  virtual int64_t matrix_count() const = 0;
+  virtual int iterate(clrs_iter_info* info) = 0;
+  virtual int get_objectives(void* d, void* p, void* g) = 0;
+  virtual int mp_gemm(int M, int N, int K, const void* A, const void* B, void* C, int path, double* ms) = 0;
+  virtual int mp_cholesky(int n, const void* A, void* L) = 0;
+  virtual int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) = 0;
+  size_t wire_size() const { return 16 + 8 * (size_t)((prec + 63) / 64); }
+};
+
+template <int NL> struct Solver : SolverBase {
+  typedef mpn<NL> num;
+  static constexpr int NS = I8Cfg<NL>::NS, NSP = I8Cfg<NL>::NSP;
+  cudaStream_t st = nullptr;
+  std::vector<void*> allocs;
+
+  template <class T> T* dalloc(size_t n) { void* p = nullptr; if (n == 0) n = 1; CK(cudaMalloc(&p, n * sizeof(T))); CK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); allocs.push_back(p); return (T*)p; }
+  template <class T> T* upload(const std::vector<T>& v) { T* p = dalloc<T>(v.size()); if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); return p; }
+  num* upload_wire(const void* w, size_t n) { std::vector<num> h(n); for (size_t i = 0; i < n; i++) wire_to_mpn(h[i], (const char*)w + i * wire_size()); return upload(h); }
+  void download_wire(void* w, const num* d, size_t n) { std::vector<num> h(n); CK(cudaMemcpyAsync(h.data(), d, n * sizeof(num), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); for (size_t i = 0; i < n; i++) mpn_to_wire((char*)w + i * wire_size(), h[i]); }
+
+  // ---- sliced panels -------------------------------------------------------
+  struct Sliced { int32_t* sl = nullptr; int32_t* E = nullptr; int nvec = 0, K = 0, K4 = 0; size_t cap_w = 0, cap_v = 0; };
+  void ensure(Sliced& s, int nvec, int K) {
+    int K4 = (K + 3) / 4; size_t need = (size_t)nvec * K4 * NSP;
+    if (need > s.cap_w || (size_t)nvec > s.cap_v) {
+      // grow-only, stream ordered
+      if (s.sl) CK(cudaFreeAsync(s.sl, st)); if (s.E) CK(cudaFreeAsync(s.E, st));
+      s.cap_w = std::max(need, s.cap_w); s.cap_v = std::max<size_t>(nvec, s.cap_v);
+      CK(cudaMallocAsync((void**)&s.sl, std::max<size_t>(s.cap_w, 4) * sizeof(int32_t), st));
+      CK(cudaMallocAsync((void**)&s.E, std::max<size_t>(s.cap_v, 1) * sizeof(int32_t), st));
+    }
+    s.nvec = nvec; s.K = K; s.K4 = K4;
+  }
+  std::vector<Sliced*> owned_sliced;
+  static VecView rows_view(const num* A, int lda, int M, int K) { VecView v; v.base = A; v.bstride = 0; v.vper = M > 0 ? M : 1; v.sv = lda; v.sk = 1; v.nvec = M; v.K = K; return v; }
+  static VecView cols_view(const num* B, int ldb, int K, int N) { VecView v; v.base = B; v.bstride = 0; v.vper = N > 0 ? N : 1; v.sv = 1; v.sk = ldb; v.nvec = N; v.K = K; return v; }
+  void split(Sliced& s, const VecView& v, bool kfast) {
+    ensure(s, v.nvec, v.K); if (v.nvec == 0 || v.K == 0) return;
+    k_vec_exp<NL><<<(v.nvec * 32 + 255) / 256, 256, 0, st>>>(v, s.E);
+    int64_t tot = (int64_t)v.nvec * s.K4;
+    k_split<NL><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0);
+  }
+  void split_rows(Sliced& s, const num* A, int lda, int M, int K) { split(s, rows_view(A, lda, M, K), true); }
+  void split_cols(Sliced& s, const num* B, int ldb, int K, int N) { split(s, cols_view(B, ldb, K, N), false); }
+
+  // C (M x N) = op(D, A*B);  A, B sliced with vector offsets a0, b0
+  void gemm(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0,
+            int batch = 1, int64_t a_bvec = 0, int64_t b_bvec = 0, int64_t c_bs = 0, int64_t d_bs = 0, int lower_only = 0) {
+    if (M == 0 || N == 0) return;
+    if (A.K4 != B.K4) throw CudaError("gemm: inner dimensions differ");
+    GemmArgs g; g.M = M; g.N = N; g.K4 = A.K4; g.batch = batch;
+    g.Asl = A.sl + (int64_t)a0 * A.K4 * NSP; g.EA = A.E + a0; g.a_bvec = a_bvec;
+    g.Bsl = B.sl + (int64_t)b0 * B.K4 * NSP; g.EB = B.E + b0; g.b_bvec = b_bvec;
+    g.C = C; g.ldc = ldc; g.c_bstride = c_bs; g.D = D; g.ldd = ldd; g.d_bstride = d_bs; g.mode = mode; g.lower_only = lower_only;
+    if (A.K4 == 0) {   // empty inner dimension: C = op(D, 0)
+      throw CudaError("gemm: K == 0 not supported");
+    }
+    dim3 grid((N + 15) / 16, (M + 15) / 16, batch);
+    k_gemm_dp4a<NL><<<grid, 256, 0, st>>>(g);
+    n_gemm_launch++;
+  }
+  long n_gemm_launch = 0;
+  Sliced tA, tB;    // scratch panels
+  // C = op(D, A*B) for plain matrices A (M x K, lda), B (K x N, ldb)
+  void mm(const num* A, int lda, const num* B, int ldb, int M, int N, int K, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0) {
+    split_rows(tA, A, lda, M, K); split_cols(tB, B, ldb, K, N); gemm(tA, 0, tB, 0, M, N, C, ldc, mode, D, ldd);
+  }
+
+  // ---- flat helpers ------------------------------------------------------------
+  void zero(num* a, int64_t n) { if (n) k_zero<NL><<<grid_for(n), 256, 0, st>>>(n, a); }
+  void copy(num* r, const num* a, int64_t n) { if (n) k_copy<NL><<<grid_for(n), 256, 0, st>>>(n, r, a); }
+  void addsub(num* r, const num* a, int sa, const num* b, int sb, int64_t n) { if (n) k_addsub<NL><<<grid_for(n), 256, 0, st>>>(n, r, a, sa, b, sb); }
+  num* partial = nullptr;
+  void reduce(const num* a, const num* b, int64_t n, num* out, int mode) {   // b == null: max-abs
+    if (n == 0) { if (mode == 0) zero(out, 1); return; }
+    int g = grid_for(n, 128, 256);
+    k_reduce_partial<NL><<<g, 128, 128 * sizeof(num), st>>>(n, a, b, partial);
+    k_reduce_final<NL><<<1, 128, 128 * sizeof(num), st>>>(g, partial, b ? 0 : 1, out, mode);
+  }
+
+  // ---- blocked Cholesky with explicit factor inverse -----------------------------------
+  // A (n x n, lower part read) -> L in place (strict upper zeroed); Minv = L^-1 (lower triangular, full n x n buffer)
+  num* chol_W = nullptr; size_t chol_W_cap = 0;
+  void chol(num* A, int lda, int n, num* Minv, int ldm, int code) {
+    if (n == 0) return;
+    for (int r = 0; r < n; r++) { (void)r; }
+    if (ldm == n) zero(Minv, (int64_t)n * n); else for (int r = 0; r < n; r++) zero(Minv + (int64_t)r * ldm, n);
+    for (int k0 = 0; k0 < n; k0 += 32) {
+      const int nb = std::min(32, n - k0), rem = n - k0 - nb;
+      k_potrf_diag<NL><<<1, 256, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code);
+      if (rem > 0) {
+        num* A21 = A + (int64_t)(k0 + nb) * lda + k0; num* A22 = A + (int64_t)(k0 + nb) * lda + k0 + nb;
+        split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);
+        gemm(tA, 0, tB, 0, rem, nb, A21, lda);                       // L21 = A21 * inv(L11)^T
+        split_rows(tA, A21, lda, rem, nb);
+        gemm(tA, 0, tA, 0, rem, rem, A22, lda, 1, A22, lda, 1, 0, 0, 0, 0, 1);   // A22 -= L21 L21^T (lower)
+      }
+    }
+    k_zero_upper<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, A, lda);
+    // rows of the inverse below the diagonal blocks: M[i,0:k0] = -inv(L_ii) * (L[i,0:k0] * M[0:k0,0:k0])
+    if (n > 32) {
+      size_t need = (size_t)32 * n; if (need > chol_W_cap) { chol_W = dalloc<num>(need); chol_W_cap = need; }
+      for (int k0 = 32; k0 < n; k0 += 32) {
+        const int nb = std::min(32, n - k0);
+        mm(A + (int64_t)k0 * lda, lda, Minv, ldm, nb, k0, k0, chol_W, k0);
+        mm(Minv + (int64_t)k0 * ldm + k0, ldm, chol_W, k0, nb, k0, nb, Minv + (int64_t)k0 * ldm, ldm, 3);
+      }
+    }
+  }
+
+  // ---- problem description -------------------------------------------------------------
+  struct HTerm { int r, s, p, k; num lam; std::vector<num> v, w; int colV = -1, rowW = -1; };
+  struct Block {
+    int j = 0, l = 0, m = 1, delta = 1, n = 1; bool high_rank = false; int64_t off = 0;   // offset in the flat block storage
+    std::vector<num> hC;
+    // dense
+    std::vector<int> dense_p; std::vector<std::vector<num>> dense_A;
+    int np = 0; int32_t* d_plist = nullptr; num* Aall = nullptr; Sliced AallB, AallV; num* T1 = nullptr; num* T2 = nullptr; num* Sd = nullptr; Sliced T1S, T2V;
+    // low rank
+    std::vector<HTerm> lr;
+    int nP = 0; int32_t* lr_plist = nullptr; int32_t* lr_tstart = nullptr; LRTermDev* lr_terms = nullptr; num* lr_lam = nullptr;
+    std::vector<int> u_r, ul_r; std::vector<num*> V, W; std::vector<Sliced> Vs, Ws;        // V_r: delta x u_r ; W_r: ul_r x delta
+    std::vector<num*> BX, BY, ZV; MatRef *d_BX = nullptr, *d_BY = nullptr, *d_ZV = nullptr, *d_W = nullptr;
+    num* part = nullptr; int umax = 0;
+    struct RS { int cnt = 0; int32_t* elist = nullptr; num* H = nullptr; Sliced Hs; num* G = nullptr; };
+    std::vector<RS> rs;                                                                     // index r*m+s, s <= r
+    // per-iteration cached panels
+    Sliced YS, XiS, MS;
+  };
+  struct Clu { int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; int off = 0; };
+  std::vector<Clu> cl; std::vector<Block*> blk;   // blk: all blocks in (j,l) order
+  int N = 0, Ptot = 0, Ksum = 0, maximize = 1; std::vector<num> hb; num hconst;
+  int64_t tot = 0;   // numbers in the flat block storage
+  // device state
+  num *X = nullptr, *Y = nullptr, *Cm = nullptr, *L = nullptr, *Minv = nullptr, *Xi = nullptr, *R = nullptr, *P = nullptr, *dX = nullptr, *dY = nullptr, *T1 = nullptr, *TXY = nullptr, *U = nullptr;
+  num *x = nullptr, *y = nullptr, *c = nullptr, *b = nullptr, *d = nullptr, *p = nullptr, *dx = nullptr, *dy = nullptr, *tr = nullptr, *Q = nullptr, *QMinv = nullptr, *tmpN = nullptr;
+  num* sc = nullptr; int* flags = nullptr; double* dinfo = nullptr; double* Td = nullptr; double* lamX = nullptr; double* lamY = nullptr; double* eigV = nullptr; EigTask* eigT = nullptr;
+  int64_t* d_boff = nullptr; int32_t* d_bn = nullptr; BlockTab bt;
+  num hopt[10]; bool hopt_set[10] = {false};
+  bool finalized = false; int iter = 1;
+  double h_gap = 1, h_derr = 1e300, h_perr = 1e300, h_dobj = 0, h_pobj = 0; int h_pdfeas = 0;
+  cudaEvent_t ev[24];
+
+  Solver(const clrs_options& o) {
+    opt = o; prec = o.prec;
+    int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError("no CUDA device: libclrs_b200 has no CPU fallback");
+    CK(cudaSetDevice(o.device)); cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, o.device));
+    if (pr.major < 10) throw CudaError("an sm_100 device is required");
+    CK(cudaStreamCreate(&st));
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
+    mp_zero(hconst);
+    double dv[10] = {o.beta_infeasible, o.beta_feasible, o.gamma, o.omega_p, o.omega_d, o.duality_gap_threshold, o.dual_error_threshold, o.primal_error_threshold, o.max_complementary_gap, o.step_length_threshold};
+    for (int i = 0; i < 10; i++) mp_from_double(hopt[i], dv[i]);
+    partial = dalloc<num>(256); sc = dalloc<num>(SC_COUNT); flags = dalloc<int>(FL_COUNT); dinfo = dalloc<double>(32);
+  }
+  ~Solver() {
+    cudaStreamSynchronize(st);
+    for (Sliced* s : owned_sliced) { if (s->sl) cudaFree(s->sl); if (s->E) cudaFree(s->E); }
+    if (tA.sl) cudaFree(tA.sl); if (tA.E) cudaFree(tA.E); if (tB.sl) cudaFree(tB.sl); if (tB.E) cudaFree(tB.E);
+    for (void* p : allocs) cudaFree(p);
+    for (auto& e : ev) cudaEventDestroy(e);
+    cudaStreamDestroy(st);
+  }
+  int set_option_num(int which, const void* w) override { if (which < 0 || which > 9) return CLRS_ERR_ARG; wire_to_mpn(hopt[which], w); return 0; }
+  int set_free(int N_, const void* b_, const void* constant, int maximize_) override {
+    N = N_; hb.resize(N); for (int i = 0; i < N; i++) wire_to_mpn(hb[i], (const char*)b_ + i * wire_size()); wire_to_mpn(hconst, constant); maximize = maximize_ != 0; return 0;
+  }
+  int add_cluster(int j, int P, const void* B, const void* c_) override {
+    if (j != (int)cl.size()) { err = "clusters must be added in order"; return CLRS_ERR_ARG; }
+    cl.emplace_back(); Clu& c0 = cl.back(); c0.P = P; c0.hB.resize((size_t)P * N); c0.hc.resize(P);
+    for (size_t i = 0; i < c0.hB.size(); i++) wire_to_mpn(c0.hB[i], (const char*)B + i * wire_size());
+    for (int i = 0; i < P; i++) wire_to_mpn(c0.hc[i], (const char*)c_ + i * wire_size());
+    return 0;
+  }
+  int add_block(int j, int l, int m, int delta, int high_rank, const void* C) override {
+    if (j >= (int)cl.size() || l != (int)cl[j].blocks.size()) { err = "blocks must be added in order"; return CLRS_ERR_ARG; }
+    if (high_rank && m != 1) { err = "dense blocks have one subblock"; return CLRS_ERR_ARG; }
+    cl[j].blocks.emplace_back(); Block& b0 = cl[j].blocks.back(); b0.j = j; b0.l = l; b0.m = m; b0.delta = delta; b0.n = m * delta; b0.high_rank = high_rank != 0;
+    b0.hC.resize((size_t)b0.n * b0.n); for (size_t i = 0; i < b0.hC.size(); i++) wire_to_mpn(b0.hC[i], (const char*)C + i * wire_size());
+    return 0;
+  }
+  int add_dense_term(int j, int l, int p_, const void* A) override {
+    Block& b0 = cl[j].blocks[l]; if (!b0.high_rank) { err = "dense term on a low-rank block"; return CLRS_ERR_ARG; }
+    b0.dense_p.push_back(p_); b0.dense_A.emplace_back((size_t)b0.n * b0.n); auto& v = b0.dense_A.back();
+    for (size_t i = 0; i < v.size(); i++) wire_to_mpn(v[i], (const char*)A + i * wire_size());
+    return 0;
+  }
+  int add_lowrank_term(int j, int l, int r, int s, int p_, int rank, const void* lam, const void* vs, const void* ws) override {
+    Block& b0 = cl[j].blocks[l]; if (b0.high_rank) { err = "low-rank term on a dense block"; return CLRS_ERR_ARG; }
+    for (int k = 0; k < rank; k++) { b0.lr.emplace_back(); HTerm& t = b0.lr.back(); t.r = r; t.s = s; t.p = p_; t.k = k;
+      wire_to_mpn(t.lam, (const char*)lam + k * wire_size()); t.v.resize(b0.delta); t.w.resize(b0.delta);
+      for (int a = 0; a < b0.delta; a++) { wire_to_mpn(t.v[a], (const char*)vs + ((size_t)k * b0.delta + a) * wire_size()); wire_to_mpn(t.w[a], (const char*)ws + ((size_t)k * b0.delta + a) * wire_size()); } }
+    return 0;
+  }
+  static bool same_vec(const std::vector<num>& a, const std::vector<num>& b) {
+    for (size_t i = 0; i < a.size(); i++) { if (a[i].sign != b[i].sign) return false; if (a[i].sign == 0) continue; if (a[i].exp != b[i].exp || memcmp(a[i].l, b[i].l, sizeof(a[i].l))) return false; }
+    return true;
+  }
+  Sliced& own(Sliced& s) { owned_sliced.push_back(&s); return s; }
+
+  // ---- finalize: build tables (precompute_matrices_bilinear_pairings, src/solver.jl:985-1059), allocate, initialise ----
+  int finalize() override {
+    Ptot = 0; Ksum = 0; tot = 0; blk.clear();
+    for (auto& c0 : cl) { c0.off = Ptot; Ptot += c0.P; for (auto& b0 : c0.blocks) { b0.off = tot; tot += (int64_t)b0.n * b0.n; Ksum += b0.n; blk.push_back(&b0); } }
+    std::vector<int64_t> boff; std::vector<int32_t> bn; for (Block* b0 : blk) { boff.push_back(b0->off); bn.push_back(b0->n); } boff.push_back(tot);
+    d_boff = upload(boff); d_bn = upload(bn); bt.off = d_boff; bt.n = d_bn; bt.nblocks = (int)blk.size();
+    num** flat[] = {&X, &Y, &Cm, &L, &Minv, &Xi, &R, &P, &dX, &dY, &T1, &TXY, &U};
+    for (auto f : flat) *f = dalloc<num>(tot);
+    { std::vector<num> hC(tot); for (Block* b0 : blk) std::copy(b0->hC.begin(), b0->hC.end(), hC.begin() + b0->off); CK(cudaMemcpyAsync(Cm, hC.data(), tot * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+    x = dalloc<num>(Ptot); d = dalloc<num>(Ptot); dx = dalloc<num>(Ptot); tr = dalloc<num>(Ptot);
+    y = dalloc<num>(N); p = dalloc<num>(N); dy = dalloc<num>(N); tmpN = dalloc<num>(N); Q = dalloc<num>((size_t)N * N); QMinv = dalloc<num>((size_t)N * N);
+    { std::vector<num> hc; for (auto& c0 : cl) hc.insert(hc.end(), c0.hc.begin(), c0.hc.end()); c = upload(hc); b = upload(hb); }
+    Td = dalloc<double>(tot); lamX = dalloc<double>(blk.size()); lamY = dalloc<double>(blk.size());
+    { std::vector<EigTask> et; size_t vtot = 0; for (Block* b0 : blk) vtot += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); eigV = dalloc<double>(vtot); size_t o = 0;
+      for (Block* b0 : blk) { EigTask t; t.T = Td + b0->off; t.n = b0->n; t.V = eigV + o; o += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); et.push_back(t); } eigT = upload(et); }
+    for (auto& c0 : cl) {
+      c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.LinvB = dalloc<num>((size_t)c0.P * N); c0.t = dalloc<num>(c0.P);
+      for (auto& b0 : c0.blocks) if (int rc = finalize_block(c0, b0)) return rc;
+    }
+    // scalars
+    { std::vector<num> h(SC_COUNT); for (auto& v : h) mp_zero(v);
+      mp_set_i32(h[SC_K], Ksum); mp_set_i32(h[SC_ONE], 1);
+      h[SC_BETA_INF] = hopt[0]; h[SC_BETA_FEAS] = hopt[1]; h[SC_GAMMA] = hopt[2]; h[SC_OMEGA_P] = hopt[3]; h[SC_OMEGA_D] = hopt[4];
+      h[SC_GAPTHR] = hopt[5]; h[SC_DERRTHR] = hopt[6]; h[SC_PERRTHR] = hopt[7]; h[SC_MAXGAP] = hopt[8]; h[SC_STEPTHR] = hopt[9]; h[SC_CONSTANT] = hconst;
+      CK(cudaMemcpyAsync(sc, h.data(), SC_COUNT * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+    // x = 0, y = 0, X = omega_p I, Y = omega_d I  (src/solver.jl:187-201)
+    for (Block* b0 : blk) { k_set_diag<NL><<<(b0->n + 127) / 128, 128, 0, st>>>(b0->n, X + b0->off, b0->n, sc + SC_OMEGA_P); k_set_diag<NL><<<(b0->n + 127) / 128, 128, 0, st>>>(b0->n, Y + b0->off, b0->n, sc + SC_OMEGA_D); }
+    finalized = true;
+    initial_quantities();
+    return 0;
+  }
+  int finalize_block(Clu& c0, Block& b0) {
+    const int n = b0.n, m = b0.m, dl = b0.delta;
+    own(b0.YS); own(b0.XiS); own(b0.MS);
+    if (b0.high_rank) {
+      b0.np = (int)b0.dense_p.size();
+      std::vector<int32_t> pl(b0.dense_p.begin(), b0.dense_p.end()); b0.d_plist = upload(pl);
+      std::vector<num> all((size_t)b0.np * n * n); for (int i = 0; i < b0.np; i++) std::copy(b0.dense_A[i].begin(), b0.dense_A[i].end(), all.begin() + (size_t)i * n * n);
+      b0.Aall = upload(all); b0.dense_A.clear(); b0.dense_A.shrink_to_fit();
+      b0.T1 = dalloc<num>((size_t)b0.np * n * n); b0.T2 = dalloc<num>((size_t)b0.np * n * n); b0.Sd = dalloc<num>((size_t)b0.np * b0.np);
+      own(b0.AallB); own(b0.AallV); own(b0.T1S); own(b0.T2V);
+      if (b0.np > 0) {
+        VecView v; v.base = b0.Aall; v.bstride = (int64_t)n * n; v.vper = n; v.sv = 1; v.sk = n; v.nvec = b0.np * n; v.K = n; split(b0.AallB, v, false);   // columns of every A_p
+        VecView w; w.base = b0.Aall; w.bstride = 0; w.vper = b0.np; w.sv = (int64_t)n * n; w.sk = 1; w.nvec = b0.np; w.K = n * n; split(b0.AallV, w, true);   // A_q flattened
+      }
+      return 0;
+    }
+    // low rank: deduplicated bases per subblock row r
+    std::map<std::tuple<int, int, int, int>, int> find;
+    for (size_t e = 0; e < b0.lr.size(); e++) { auto& t = b0.lr[e]; find[{t.r, t.s, t.p, t.k}] = (int)e; if (t.r >= m || t.s >= m || t.p >= c0.P) { err = "low-rank term out of range"; return CLRS_ERR_ARG; } }
+    b0.u_r.assign(m, 0); b0.ul_r.assign(m, 0); b0.V.assign(m, nullptr); b0.W.assign(m, nullptr); b0.Vs.resize(m); b0.Ws.resize(m);
+    for (int r = 0; r < m; r++) {
+      std::vector<int> uv, uw;
+      for (int s = 0; s < m; s++) for (size_t e = 0; e < b0.lr.size(); e++) { auto& t = b0.lr[e]; if (t.r != r || t.s != s) continue;
+        int f = -1; for (size_t u = 0; u < uv.size(); u++) if (same_vec(b0.lr[uv[u]].v, t.v)) { f = (int)u; break; }
+        if (f < 0) { f = (int)uv.size(); uv.push_back((int)e); } t.colV = f;
+        f = -1; for (size_t u = 0; u < uw.size(); u++) if (same_vec(b0.lr[uw[u]].w, t.w)) { f = (int)u; break; }
+        if (f < 0) { f = (int)uw.size(); uw.push_back((int)e); } t.rowW = f; }
+      b0.u_r[r] = (int)uv.size(); b0.ul_r[r] = (int)uw.size(); b0.umax = std::max(b0.umax, std::max(b0.u_r[r], b0.ul_r[r]));
+      std::vector<num> hV((size_t)dl * uv.size()), hW((size_t)uw.size() * dl);
+      for (size_t u = 0; u < uv.size(); u++) for (int a = 0; a < dl; a++) hV[(size_t)a * uv.size() + u] = b0.lr[uv[u]].v[a];
+      for (size_t u = 0; u < uw.size(); u++) for (int a = 0; a < dl; a++) hW[u * dl + a] = b0.lr[uw[u]].w[a];
+      b0.V[r] = upload(hV); b0.W[r] = upload(hW);
+      own(b0.Vs[r]); own(b0.Ws[r]);
+      split_cols(b0.Vs[r], b0.V[r], b0.u_r[r], dl, b0.u_r[r]); split_rows(b0.Ws[r], b0.W[r], dl, b0.ul_r[r], dl);
+    }
+    // constraint-sorted term table
+    std::vector<int> order(b0.lr.size()); for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b_) { return b0.lr[a].p < b0.lr[b_].p; });
+    std::vector<int> pos(b0.lr.size()); for (size_t i = 0; i < order.size(); i++) pos[order[i]] = (int)i;
+    std::vector<LRTermDev> terms(order.size()); std::vector<num> lam(order.size()); std::vector<int32_t> plist, tstart;
+    for (size_t i = 0; i < order.size(); i++) { auto& t = b0.lr[order[i]]; auto it = find.find({t.s, t.r, t.p, t.k});
+      if (it == find.end()) { err = "low-rank term without its transposed subblock (src/solver.jl:1009)"; return CLRS_ERR_ARG; }
+      auto& tt = b0.lr[it->second];
+      LRTermDev d0; d0.p = t.p; d0.r = t.r; d0.s = t.s; d0.lam = (int)i; d0.colV = t.colV; d0.rowW = t.rowW; d0.rowW_t = tt.rowW; d0.colV_t = tt.colV; terms[i] = d0; lam[i] = t.lam;
+      if (plist.empty() || plist.back() != t.p) { plist.push_back(t.p); tstart.push_back((int)i); } }
+    tstart.push_back((int)order.size());
+    b0.nP = (int)plist.size(); b0.lr_plist = upload(plist); b0.lr_tstart = upload(tstart); b0.lr_terms = upload(terms); b0.lr_lam = upload(lam);
+    // pairing matrices
+    b0.BX.assign(m * m, nullptr); b0.BY.assign(m * m, nullptr); b0.ZV.assign(m * m, nullptr);
+    std::vector<MatRef> rBX(m * m), rBY(m * m), rZV(m * m), rW(m);
+    for (int s = 0; s < m; s++) for (int r = 0; r < m; r++) { size_t sz = (size_t)b0.ul_r[s] * b0.u_r[r];
+      b0.BX[s * m + r] = dalloc<num>(sz); b0.BY[s * m + r] = dalloc<num>(sz); rBX[s * m + r] = {b0.BX[s * m + r], b0.u_r[r]}; rBY[s * m + r] = {b0.BY[s * m + r], b0.u_r[r]}; }
+    for (int r = 0; r < m; r++) { rW[r] = {b0.W[r], dl}; for (int s = 0; s <= r; s++) { b0.ZV[r * m + s] = dalloc<num>((size_t)dl * b0.u_r[r]); rZV[r * m + s] = {b0.ZV[r * m + s], b0.u_r[r]}; } }
+    b0.d_BX = upload(rBX); b0.d_BY = upload(rBY); b0.d_ZV = upload(rZV); b0.d_W = upload(rW);
+    b0.part = dalloc<num>((size_t)n * std::max(b0.umax, 1));
+    // per (r,s<=r): piece lists for sum_p a_p A_p
+    b0.rs.resize(m * m);
+    for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { auto& q = b0.rs[r * m + s]; std::vector<int32_t> el; std::vector<num> H;
+      for (size_t e = 0; e < b0.lr.size(); e++) { auto& t = b0.lr[e]; if (t.r != r || t.s != s) continue; el.push_back(pos[e]); for (int a = 0; a < dl; a++) H.push_back(t.w[a]); }
+      q.cnt = (int)el.size(); if (q.cnt == 0) continue;
+      q.elist = upload(el); q.H = upload(H); q.G = dalloc<num>((size_t)dl * q.cnt); own(q.Hs); split_cols(q.Hs, q.H, dl, q.cnt, dl); }
+    return 0;
+  }
+
+  // ---- pieces of the iteration ---------------------------------------------------------
+  // dst_b = sum_p a_p A_p per block  (compute_weighted_A!, src/solver.jl:1410-1470)
+  void weighted_A(num* dst, const num* a) {
+    for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
+      num* M = dst + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; const num* aj = a + c0.off;
+      if (b0.high_rank) { k_weighted_dense<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, aj, M); continue; }
+      zero(M, (int64_t)n * n);
+      for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { auto& q = b0.rs[r * m + s]; if (q.cnt == 0) continue;
+        k_weighted_cols<NL><<<(q.cnt * dl + 127) / 128, 128, 0, st>>>(q.cnt, q.elist, b0.lr_terms, b0.lr_lam, aj, MatRef{b0.V[r], b0.u_r[r]}, dl, q.G, q.cnt);
+        split_rows(tA, q.G, q.cnt, dl, q.cnt);
+        gemm(tA, 0, q.Hs, 0, dl, dl, M + (int64_t)r * dl * n + (int64_t)s * dl, n); }
+      if (m > 1) k_mirror<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, M, n, 0);
+    }
+  }
+  // out[p] = <A_p, Z>  (trace_A with vectors, src/solver.jl:1290-1366)
+  void trace_vectors(num* out, const num* Z) {
+    zero(out, Ptot);
+    for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
+      const num* Zb = Z + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; num* oj = out + c0.off;
+      if (b0.high_rank) { if (b0.np) k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, Zb, oj); continue; }
+      if (b0.nP == 0) continue;
+      for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { if (b0.rs[r * m + s].cnt == 0) continue;
+        split_rows(tA, Zb + (int64_t)r * dl * n + (int64_t)s * dl, n, dl, dl); gemm(tA, 0, b0.Vs[r], 0, dl, b0.u_r[r], b0.ZV[r * m + s], b0.u_r[r]); }
+      k_trace_vectors<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_W, b0.d_ZV, m, dl, oj);
+    }
+  }
+  // out[p] = <A_p, Y> from the stored pairings (src/solver.jl:1368-1407)
+  void trace_pairings(num* out) {
+    zero(out, Ptot);
+    for (auto& c0 : cl) for (auto& b0 : c0.blocks) { num* oj = out + c0.off;
+      if (b0.high_rank) { if (b0.np) k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)b0.n * b0.n, Y + b0.off, oj); continue; }
+      if (b0.nP) k_trace_pairings<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BY, b0.m, oj); }
+  }
+  // P, d, p  (compute_residuals!, src/solver.jl:863-918); `tr` must hold <A_*, Y>
+  void residuals() {
+    weighted_A(P, x);
+    k_residual_P<NL><<<grid_for(tot), 256, 0, st>>>(tot, P, X, Cm, maximize);
+    // d = c - B y - tr
+    addsub(d, c, 1, tr, -1, Ptot);
+    if (N > 0) for (auto& c0 : cl) if (c0.P) k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.B, N, y, d + c0.off, -1, 1);
+    // p = +-b - sum_j B_j^T x_j
+    if (N > 0) { addsub(p, b, maximize ? 1 : -1, b, 0, N);
+      for (auto& c0 : cl) if (c0.P) k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1); }
+  }
+  void errors() { reduce(P, nullptr, tot, sc + SC_ERRP, 0); reduce(p, nullptr, N, sc + SC_ERRp, 0); reduce(d, nullptr, Ptot, sc + SC_ERRd, 0); }
+  void objectives() {
+    reduce(c, x, Ptot, sc + SC_CX, 0); reduce(Cm, Y, tot, sc + SC_CY, 0); reduce(b, y, N, sc + SC_BY, 0);
+    scalar(4);
+  }
+  void scalar(int phase, const num* M = nullptr, const num* dM = nullptr, const double* lam = nullptr, int which = 0) {
+    ScalarCfg cfg{opt.correctoronly, opt.safe_step, maximize};
+    k_scalar<NL><<<1, 32, 0, st>>>(phase, sc, flags, dinfo, cfg, (int)blk.size(), d_bn, d_boff, M, dM, lam, which);
+  }
+  void pull_info() {
+    double h[32]; int f[FL_COUNT];
+    CK(cudaMemcpyAsync(h, dinfo, sizeof(h), cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(f, flags, sizeof(f), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    memcpy(hinfo, h, sizeof(h)); memcpy(hflags, f, sizeof(f));
+  }
+  double hinfo[32]; int hflags[FL_COUNT];
+  // initial objectives / residuals / errors  (src/solver.jl:319-333)
+  void initial_quantities() {
+    CK(cudaMemsetAsync(flags, 0, FL_COUNT * sizeof(int), st));
+    objectives();
+    trace_vectors(tr, Y);
+    residuals(); errors(); scalar(5);
+    reduce(X, Y, tot, sc + SC_D0, 0);
+    pull_info();
+    h_dobj = hinfo[INFO_DOBJ + 10]; h_pobj = hinfo[INFO_POBJ + 10]; h_gap = hinfo[INFO_GAP + 10];
+    h_derr = std::max(hinfo[INFO_ERRP], hinfo[INFO_ERRp]); h_perr = hinfo[INFO_ERRd]; h_pdfeas = hflags[FL_PDFEAS];
+    fetch_thresholds();
+    iter = 1;
+  }
+  // terminate() compares full-precision values; the host copy keeps them as device numbers compared on demand
+  num h_gapn, h_derrn, h_perrn, h_thr[3];
+  void fetch_thresholds() {
+    num h[SC_COUNT]; CK(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    h_gapn = h[SC_GAP]; h_derrn = mp_cmp_abs(h[SC_ERRP], h[SC_ERRp]) > 0 ? h[SC_ERRP] : h[SC_ERRp]; h_perrn = h[SC_ERRd];
+    h_thr[0] = h[SC_GAPTHR]; h_thr[1] = h[SC_DERRTHR]; h_thr[2] = h[SC_PERRTHR];
+  }
+
+  // Schur complement S_j and its factorisation  (compute_T_decomposition!, src/solver.jl:1229-1287)
+  void schur_block_lowrank(Clu& c0, Block& b0) {
+    const int n = b0.n, m = b0.m, dl = b0.delta;
+    if (b0.nP == 0) return;
+    for (int pass = 0; pass < 2; pass++) {
+      const num* Src = (pass == 0 ? Y : Xi) + b0.off; auto& Bout = pass == 0 ? b0.BY : b0.BX;
+      for (int r = 0; r < m; r++) { if (b0.u_r[r] == 0) continue;
+        split_rows(tA, Src + (int64_t)r * dl, n, n, dl);
+        gemm(tA, 0, b0.Vs[r], 0, n, b0.u_r[r], b0.part, b0.u_r[r]);                                   // part = Src[:, r-cols] V_r   (:1125,:1137)
+        for (int s = 0; s < m; s++) { if (b0.ul_r[s] == 0) continue;
+          split_cols(tB, b0.part + (int64_t)s * dl * b0.u_r[r], b0.u_r[r], dl, b0.u_r[r]);
+          gemm(b0.Ws[s], 0, tB, 0, b0.ul_r[s], b0.u_r[r], Bout[s * m + r], b0.u_r[r]); } }                // W_s part[s-rows]            (:1131,:1143)
+    }
+    int64_t np2 = (int64_t)b0.nP * b0.nP;
+    k_schur_lowrank<NL><<<(unsigned)((np2 + 127) / 128), 128, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BX, b0.d_BY, m, c0.S, c0.P);
+  }
+  void schur_block_dense(Clu& c0, Block& b0) {        // T = X^-1 A_p Y, S[p,q] += <A_q, T>   (src/solver.jl:1089-1104)
+    const int n = b0.n, np = b0.np; if (np == 0) return; const int64_t nn = (int64_t)n * n;
+    gemm(b0.XiS, 0, b0.AallB, 0, n, n, b0.T1, n, 0, nullptr, 0, np, 0, n, nn, 0);
+    { VecView v; v.base = b0.T1; v.bstride = nn; v.vper = n; v.sv = n; v.sk = 1; v.nvec = np * n; v.K = n; split(b0.T1S, v, true); }
+    gemm(b0.T1S, 0, b0.YS, 0, n, n, b0.T2, n, 0, nullptr, 0, np, n, 0, nn, 0);
+    { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true); }
+    gemm(b0.T2V, 0, b0.AallV, 0, np, np, b0.Sd, np);
+    k_scatter_upper<NL><<<(unsigned)(((int64_t)np * np + 127) / 128), 128, 0, st>>>(np, b0.d_plist, b0.Sd, c0.S, c0.P);
+  }
+  void decomposition(int e0) {
+    for (auto& c0 : cl) { zero(c0.S, (int64_t)c0.P * c0.P);
+      for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_block_dense(c0, b0); else schur_block_lowrank(c0, b0); }
+      if (c0.P) k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); }
+    CK(cudaEventRecord(ev[e0], st));
+    for (auto& c0 : cl) chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S);
+    CK(cudaEventRecord(ev[e0 + 1], st));
+    if (N > 0) {
+      bool first = true;
+      for (auto& c0 : cl) { if (c0.P == 0) continue;
+        mm(c0.Minv, c0.P, c0.B, N, c0.P, N, c0.P, c0.LinvB, N); }                                       // LinvB = L^-1 B  (:1258)
+      CK(cudaEventRecord(ev[e0 + 2], st));
+      for (auto& c0 : cl) { if (c0.P == 0) continue;
+        split_cols(tA, c0.LinvB, N, c0.P, N);
+        gemm(tA, 0, tA, 0, N, N, Q, N, first ? 0 : 2, Q, N); first = false; }                            // Q = sum LinvB^T LinvB  (:1268-1269)
+      CK(cudaEventRecord(ev[e0 + 3], st));
+      chol(Q, N, N, QMinv, N, CLRS_ERR_CHOL_Q);
+    } else { CK(cudaEventRecord(ev[e0 + 2], st)); CK(cudaEventRecord(ev[e0 + 3], st)); }
+    CK(cudaEventRecord(ev[e0 + 4], st));
+  }
+  // search direction  (compute_search_direction!, src/solver.jl:1474-1616)
+  void direction() {
+    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, P + b0->off, n, n, n); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // P Y
+    addsub(T1, T1, 1, R, -1, tot);
+    for (Block* b0 : blk) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); }    // Z = X^-1 (P Y - R)
+    k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
+    trace_vectors(tr, dY);
+    if (Ptot) k_vec_rhs<NL><<<(Ptot + 127) / 128, 128, 0, st>>>(Ptot, dx, d, tr);                                                          // rhs_x = -d - <A_*, Z>
+    // block elimination  (:1527-1582)
+    if (N > 0) copy(dy, p, N);
+    for (auto& c0 : cl) { if (c0.P == 0) continue;
+      k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, dx + c0.off, c0.t, 1, 0);                              // t_j = L_j^-1 rhs_j
+      if (N > 0) k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, dy, -1, 1); }                                     // dy -= LinvB_j^T t_j
+    if (N > 0) { k_gemv_n<NL><<<(N * 32 + 255) / 256, 256, 0, st>>>(N, N, QMinv, N, dy, tmpN, 1, 0);
+      k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(N, N, QMinv, N, tmpN, dy, 1, 0); }                                                       // dy = Q^-1 dy
+    for (auto& c0 : cl) { if (c0.P == 0) continue;
+      if (N > 0) k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
+      k_gemv_t<NL><<<(c0.P + 127) / 128, 128, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, c0.t, dx + c0.off, 1, 0); }                                 // dx_j = L_j^-T t_j
+    weighted_A(dX, dx); addsub(dX, dX, 1, P, 1, tot);                                                                                       // dX = P + sum dx_p A_p
+    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // dX Y
+    addsub(T1, R, 1, T1, -1, tot);
+    for (Block* b0 : blk) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); }    // dY = X^-1 (R - dX Y)
+    k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
+  }
+  // lambda_min( L^-1 dM L^-T ) per block in Float64  (compute_step_length, src/solver.jl:1620-1693); Mi holds L^-1
+  void step_eigs(const num* Mi, const num* dM, double* lam, bool have_MS) {
+    for (Block* b0 : blk) { const int n = b0->n; if (n == 1) continue;
+      if (!have_MS) split_rows(b0->MS, Mi + b0->off, n, n, n);
+      split_cols(tB, dM + b0->off, n, n, n); gemm(b0->MS, 0, tB, 0, n, n, U + b0->off, n);             // U = L^-1 dM
+      split_rows(tA, U + b0->off, n, n, n); gemm(tA, 0, b0->MS, 0, n, n, T1 + b0->off, n); }            // T = U L^-T
+    k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, T1, Td);
+    k_min_eig<<<(unsigned)blk.size(), 256, 0, st>>>(eigT, lam);
+  }
+
+  int check_status() { return hflags[FL_STATUS]; }
+  bool host_terminate(int& reason) {   // terminate(), src/solver.jl:921-950, on full-precision values
+    bool gap_opt = mp_cmp(h_gapn, h_thr[0]) < 0, dual_feas = mp_cmp(h_derrn, h_thr[1]) < 0, primal_feas = mp_cmp(h_perrn, h_thr[2]) < 0;
+    if (opt.need_dual_feasible && dual_feas) { reason = CLRS_STOP_DUAL_FEASIBLE; return true; }
+    if (opt.need_primal_feasible && primal_feas) { reason = CLRS_STOP_PRIMAL_FEASIBLE; return true; }
+    if (!opt.correctoronly && dual_feas && primal_feas && gap_opt) { reason = CLRS_STOP_OPTIMAL; return true; }
+    return false;
+  }
+
+  // ---- one iteration  (loop body src/solver.jl:362-592) -----------------------------------
+  int iterate(clrs_iter_info* info) override {
+    if (!finalized) { err = "clrs_finalize has not been called"; return CLRS_ERR_ARG; }
+    memset(info, 0, sizeof(*info)); info->iter = iter; info->d_obj = h_dobj; info->p_obj = h_pobj; info->gap = h_gap; info->pd_feasible = h_pdfeas;
+    int reason = 0; if (host_terminate(reason)) { info->stop = reason; return 0; }
+    CK(cudaMemsetAsync(flags + FL_STOP, 0, 2 * sizeof(int), st));
+    CK(cudaEventRecord(ev[0], st));
+    scalar(0);                                                        // mu, mu_p  (SC_D0 = <X,Y> is kept current)
+    // R = mu_p I - X Y
+    for (Block* b0 : blk) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n); split_rows(tA, X + b0->off, n, n, n); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); }
+    k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, (const num*)nullptr, sc + SC_MUP);
+    CK(cudaEventRecord(ev[1], st));
+    // Cholesky of X, L^-1, X^-1  (src/solver.jl:388-399, 1117)
+    copy(L, X, tot);
+    for (Block* b0 : blk) { const int n = b0->n; chol(L + b0->off, n, n, Minv + b0->off, n, CLRS_ERR_CHOL_X);
+      split_cols(tA, Minv + b0->off, n, n, n); gemm(tA, 0, tA, 0, n, n, Xi + b0->off, n);               // X^-1 = L^-T L^-1
+      split_rows(b0->XiS, Xi + b0->off, n, n, n); }
+    CK(cudaEventRecord(ev[2], st));
+    decomposition(3);                                                 // events 3..7
+    trace_pairings(tr); residuals();
+    CK(cudaEventRecord(ev[8], st));
+    direction();                                                      // predictor
+    CK(cudaEventRecord(ev[9], st));
+    reduce(X, dY, tot, sc + SC_D1, 0); reduce(dX, Y, tot, sc + SC_D2, 0); reduce(dX, dY, tot, sc + SC_D3, 0);
+    errors(); scalar(1);
+    CK(cudaEventRecord(ev[10], st));
+    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n); split_cols(tB, dY + b0->off, n, n, n); gemm(tA, 0, tB, 0, n, n, T1 + b0->off, n); }
+    k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, T1, sc + SC_MUC);                     // R = mu_c I - XY - dXdY
+    CK(cudaEventRecord(ev[11], st));
+    direction();                                                      // corrector
+    CK(cudaEventRecord(ev[12], st));
+    // step lengths: X reuses its factor of this iteration (X is unchanged); Y is factored here
+    step_eigs(Minv, dX, lamX, false); scalar(2, X, dX, lamX, SC_ALPHAD);
+    copy(L, Y, tot);
+    for (Block* b0 : blk) { const int n = b0->n; if (n > 1) chol(L + b0->off, n, n, Minv + b0->off, n, CLRS_ERR_CHOL_STEP); }
+    step_eigs(Minv, dY, lamY, false); scalar(2, Y, dY, lamY, SC_ALPHAP);
+    scalar(3);
+    CK(cudaEventRecord(ev[13], st));
+    // the step  (src/solver.jl:485-495)
+    if (Ptot) k_axpy<NL><<<grid_for(Ptot), 256, 0, st>>>(Ptot, x, dx, sc + SC_ALPHAD);
+    if (N) k_axpy<NL><<<grid_for(N), 256, 0, st>>>(N, y, dy, sc + SC_ALPHAP);
+    k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, X, dX, sc + SC_ALPHAD);
+    k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, Y, dY, sc + SC_ALPHAP);
+    objectives();
+    reduce(X, Y, tot, sc + SC_D0, 0);                                  // <X,Y> of the new iterate for the next mu
+    CK(cudaEventRecord(ev[14], st));
+    pull_info();
+    if (int s = check_status()) {
+      const char* msg = s == CLRS_ERR_CHOL_X ? "The cholesky decomposition of X was not computed correctly. Try again with higher precision"
+                      : s == CLRS_ERR_CHOL_S ? "S was not decomposed succesfully, try again with higher precision."
+                      : s == CLRS_ERR_CHOL_Q ? "Q was not decomposed correctly. Try restarting with a higher precision."
+                      : "The cholesky decomposition could not be computed during the computation of the step length.";
+      err = msg; return s;
+    }
+    info->stop = hflags[FL_STOP]; info->pd_feasible = hflags[FL_PDFEAS];
+    info->mu = hinfo[INFO_MU]; info->err_P = hinfo[INFO_ERRP]; info->err_p = hinfo[INFO_ERRp]; info->err_d = hinfo[INFO_ERRd];
+    info->alpha_d = hinfo[INFO_ALPHAD]; info->alpha_p = hinfo[INFO_ALPHAP]; info->beta_c = hinfo[INFO_BETAC];
+    info->d_obj_new = hinfo[INFO_DOBJ + 10]; info->p_obj_new = hinfo[INFO_POBJ + 10]; info->gap_new = hinfo[INFO_GAP + 10];
+    auto ms = [&](int a, int b_) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b_]); return (double)t; };
+    info->phase_ms[0] = ms(2, 7); info->phase_ms[1] = ms(8, 9); info->phase_ms[2] = ms(11, 12); info->phase_ms[3] = ms(12, 13); info->phase_ms[4] = ms(1, 2);
+    info->phase_ms[5] = ms(0, 1) + ms(10, 11); info->phase_ms[6] = ms(7, 8);
+    info->phase_ms[7] = ms(2, 3); info->phase_ms[8] = ms(3, 4); info->phase_ms[9] = ms(4, 5); info->phase_ms[10] = ms(5, 6); info->phase_ms[11] = ms(6, 7);
+    h_pdfeas = hflags[FL_PDFEAS];
+    h_derr = std::max(info->err_P, info->err_p); h_perr = info->err_d;
+    if (info->stop == 0) { h_dobj = info->d_obj_new; h_pobj = info->p_obj_new; h_gap = info->gap_new; iter++; }
+    fetch_thresholds();
+    return 0;
+  }
+  int get_objectives(void* d_, void* p_, void* g_) override {
+    objectives(); num h[SC_COUNT]; CK(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    mpn_to_wire(d_, h[SC_DOBJ]); mpn_to_wire(p_, h[SC_POBJ]); mpn_to_wire(g_, h[SC_GAP]); return 0;
+  }
+  int64_t matrix_count() const override { return tot; }
+  int set_state(const void* x_, const void* X_, const void* y_, const void* Y_) override {
+    auto up = [&](num* dst, const void* w, size_t n) { if (!w || !n) return; std::vector<num> h(n); for (size_t i = 0; i < n; i++) wire_to_mpn(h[i], (const char*)w + i * wire_size()); CK(cudaMemcpyAsync(dst, h.data(), n * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); };
+    up(x, x_, Ptot); up(X, X_, tot); up(y, y_, N); up(Y, Y_, tot); initial_quantities(); return 0;
+  }
+  int get_state(void* x_, void* X_, void* y_, void* Y_) override {
+    if (x_) download_wire(x_, x, Ptot); if (X_) download_wire(X_, X, tot); if (y_ && N) download_wire(y_, y, N); if (Y_) download_wire(Y_, Y, tot); return 0;
+  }
+  // ---- standalone kernels -----------------------------------------------------------------
+  int mp_gemm(int M, int N_, int K, const void* A, const void* B, void* C, int path, double* ms) override {
+    num* dA = upload_wire(A, (size_t)M * K); num* dB = upload_wire(B, (size_t)K * N_); num* dC = dalloc<num>((size_t)M * N_);
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    (void)path;
+    CK(cudaEventRecord(e0, st)); mm(dA, K, dB, N_, M, N_, K, dC, N_); CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st));
+    float t = 0; cudaEventElapsedTime(&t, e0, e1); if (ms) *ms = t; cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    download_wire(C, dC, (size_t)M * N_); return 0;
+  }
+  int mp_cholesky(int n, const void* A, void* Lw) override {
+    num* dA = upload_wire(A, (size_t)n * n); num* dM = dalloc<num>((size_t)n * n);
+    CK(cudaMemsetAsync(flags, 0, FL_COUNT * sizeof(int), st));
+    chol(dA, n, n, dM, n, CLRS_ERR_CHOL_X);
+    int f[FL_COUNT]; CK(cudaMemcpyAsync(f, flags, sizeof(f), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+    download_wire(Lw, dA, (size_t)n * n);
+    if (f[FL_STATUS]) { err = "non-positive pivot"; return f[FL_STATUS]; }
+    return 0;
+  }
+  int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) override {
+    std::string w(what); const num* src = nullptr; int64_t n = 0;
+    if (w == "S") { src = cl[j].S; n = (int64_t)cl[j].P * cl[j].P; } else if (w == "LinvB") { src = cl[j].LinvB; n = (int64_t)cl[j].P * N; }
+    else if (w == "Q") { src = Q; n = (int64_t)N * N; } else if (w == "d") { src = d; n = Ptot; } else if (w == "p") { src = p; n = N; }
+    else if (w == "dx") { src = dx; n = Ptot; } else if (w == "dy") { src = dy; n = N; } else if (w == "x") { src = x; n = Ptot; } else if (w == "y") { src = y; n = N; }
+    else { Block& b0 = cl[j].blocks[l]; n = (int64_t)b0.n * b0.n; const num* base = nullptr;
+      if (w == "Xinv") base = Xi; else if (w == "R") base = R; else if (w == "P") base = P; else if (w == "dX") base = dX; else if (w == "dY") base = dY; else if (w == "X") base = X; else if (w == "Y") base = Y; else if (w == "L") base = L;
+      if (!base) return -1; src = base + b0.off; }
+    if (n > cap) return -n; if (n) download_wire(out, src, n); return n;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+struct clrs_handle { SolverBase* s; std::string err; };
+#define GUARD(h, body) try { body } catch (const std::exception& e) { (h)->err = e.what(); if ((h)->s) (h)->s->err = e.what(); return CLRS_ERR_CUDA; }
+
+extern "C" {
+void clrs_default_options(clrs_options* o) {
+  memset(o, 0, sizeof(*o)); o->prec = 256; o->beta_infeasible = 0.3; o->beta_feasible = 0.1; o->gamma = 0.9; o->omega_p = 1e10; o->omega_d = 1e10;
+  o->duality_gap_threshold = 1e-15; o->dual_error_threshold = 1e-30; o->primal_error_threshold = 1e-30; o->max_complementary_gap = 1e100; o->step_length_threshold = 1e-7; o->safe_step = 1;
+}
+int clrs_create(const clrs_options* opt, clrs_handle** out) {
+  clrs_handle* h = new clrs_handle(); h->s = nullptr; *out = h;
+  try {
+    if (opt->prec <= 0 || opt->prec > 256) { h->err = "this build supports prec <= 256 bits"; return CLRS_ERR_UNSUPPORTED; }
+    h->s = new Solver<8>(*opt);
+  } catch (const std::exception& e) { h->err = e.what(); return CLRS_ERR_CUDA; }
+  return CLRS_OK;
+}
+void clrs_destroy(clrs_handle* h) { if (!h) return; delete h->s; delete h; }
+const char* clrs_last_error(const clrs_handle* h) { if (!h) return ""; if (h->s && !h->s->err.empty()) return h->s->err.c_str(); return h->err.c_str(); }
+size_t clrs_wire_size(const clrs_handle* h) { return h->s->wire_size(); }
+int clrs_set_option_num(clrs_handle* h, int which, const void* w) { GUARD(h, return h->s->set_option_num(which, w);) }
+int clrs_set_free(clrs_handle* h, int32_t N, const void* b, const void* c, int32_t mx) { GUARD(h, return h->s->set_free(N, b, c, mx);) }
+int clrs_add_cluster(clrs_handle* h, int32_t j, int32_t P, const void* B, const void* c) { GUARD(h, return h->s->add_cluster(j, P, B, c);) }
+int clrs_add_block(clrs_handle* h, int32_t j, int32_t l, int32_t m, int32_t delta, int32_t hr, const void* C) { GUARD(h, return h->s->add_block(j, l, m, delta, hr, C);) }
+int clrs_add_dense_term(clrs_handle* h, int32_t j, int32_t l, int32_t p, const void* A) { GUARD(h, return h->s->add_dense_term(j, l, p, A);) }
+int clrs_add_lowrank_term(clrs_handle* h, int32_t j, int32_t l, int32_t r, int32_t s, int32_t p, int32_t rank, const void* lam, const void* vs, const void* ws) { GUARD(h, return h->s->add_lowrank_term(j, l, r, s, p, rank, lam, vs, ws);) }
+int clrs_finalize(clrs_handle* h) { GUARD(h, return h->s->finalize();) }
+int clrs_set_state(clrs_handle* h, const void* x, const void* X, const void* y, const void* Y) { GUARD(h, return h->s->set_state(x, X, y, Y);) }
+int clrs_get_state(clrs_handle* h, void* x, void* X, void* y, void* Y) { GUARD(h, return h->s->get_state(x, X, y, Y);) }
+int64_t clrs_state_matrix_count(const clrs_handle* h) { return h->s->matrix_count(); }
+int clrs_iterate(clrs_handle* h, clrs_iter_info* info) { GUARD(h, return h->s->iterate(info);) }
+int clrs_get_objectives(clrs_handle* h, void* d, void* p, void* g) { GUARD(h, return h->s->get_objectives(d, p, g);) }
+int clrs_comm_init(clrs_handle* h, int32_t rank, int32_t nranks, const void*) { if (nranks == 1 && rank == 0) return CLRS_OK; h->err = "multi-GPU sharding is not built in this round"; return CLRS_ERR_UNSUPPORTED; }
+int clrs_comm_unique_id(void* out128) { memset(out128, 0, 128); return CLRS_OK; }
+int clrs_mp_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, const void* A, const void* B, void* C, int32_t path, double* ms) { GUARD(h, return h->s->mp_gemm(M, N, K, A, B, C, path, ms);) }
+int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L) { GUARD(h, return h->s->mp_cholesky(n, A, L);) }
+int64_t clrs_debug_get(clrs_handle* h, const char* what, int32_t j, int32_t l, void* out, int64_t cap) { try { return h->s->debug_get(what, j, l, out, cap); } catch (const std::exception& e) { h->err = e.what(); return -1; } }
+}

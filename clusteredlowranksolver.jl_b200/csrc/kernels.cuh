@@ -1,0 +1,503 @@
+// kernels.cuh — CUDA-core kernels of the IPM iteration (sm_100a).
+//
+//  * fused elementwise / reduction kernels on multi-limb numbers (north star
+//    subsystem 3): HBM-bound, 40 B per number, flat over the concatenated block
+//    storage so ONE launch covers every PSD block of the SDP;
+//  * panel kernels for the blocked Cholesky / triangular inverse (subsystem 2);
+//  * the int8 slice pipeline on CUDA cores: per-vector exponent, split into
+//    balanced radix-256 digits, dp4a slice-pair GEMM with in-register exact
+//    recombination (the small-shape / fallback path of subsystem 1; the large
+//    shapes go to the tcgen05 kernel in gemm_tc.cuh, same slices, same integers).
+#pragma once
+#include <cuda_runtime.h>
+#include "mpf.cuh"
+#include "i8split.cuh"
+
+// ---------------------------------------------------------------------------
+// block table for flat kernels over block-diagonal storage
+// ---------------------------------------------------------------------------
+struct BlockTab { const int64_t* off; const int32_t* n; int nblocks; };   // off has nblocks+1 entries
+__device__ __forceinline__ int blk_find(const BlockTab& t, int64_t idx) {
+  int lo = 0, hi = t.nblocks - 1;
+  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (t.off[mid] <= idx) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------
+// elementwise
+// ---------------------------------------------------------------------------
+template <int NL> __global__ void k_zero(int64_t n, mpn<NL>* a) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mp_zero(a[i]);
+}
+template <int NL> __global__ void k_copy(int64_t n, mpn<NL>* r, const mpn<NL>* a) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) r[i] = a[i];
+}
+// r = sa*a + sb*b with sa, sb in {-1,0,+1}
+template <int NL> __global__ void k_addsub(int64_t n, mpn<NL>* r, const mpn<NL>* a, int sa, const mpn<NL>* b, int sb) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    mpn<NL> x = a[i], y = b[i], z; x.sign *= sa; y.sign *= sb; mp_add(z, x, y); r[i] = z;
+  }
+}
+// P = P - X -/+ C   (compute_residuals!, src/solver.jl:885-893)
+template <int NL> __global__ void k_residual_P(int64_t n, mpn<NL>* P, const mpn<NL>* X, const mpn<NL>* C, int maximize) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    mpn<NL> p = P[i], x = X[i], c = C[i]; mp_sub(p, p, x); if (maximize) mp_sub(p, p, c); else mp_add(p, p, c); P[i] = p;
+  }
+}
+// y += alpha * x   (the step, src/solver.jl:485-495).  alpha lives in device memory.
+template <int NL> __global__ void k_axpy(int64_t n, mpn<NL>* y, const mpn<NL>* x, const mpn<NL>* alpha) {
+  const mpn<NL> a = *alpha;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    mpn<NL> t = x[i], v = y[i]; mp_mul(t, t, a); mp_add(v, v, t); y[i] = v;
+  }
+}
+// R = mu*I - T  [ - T2 ]   (compute_residual_R!, src/solver.jl:961-983)
+template <int NL> __global__ void k_residual_R(BlockTab bt, int64_t n, mpn<NL>* R, const mpn<NL>* T, const mpn<NL>* T2, const mpn<NL>* mu) {
+  const mpn<NL> m = *mu;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = blk_find(bt, i); int64_t loc = i - bt.off[b]; int nn = bt.n[b];
+    mpn<NL> r; mp_zero(r); if (loc / nn == loc % nn) r = m;
+    mpn<NL> t = T[i]; mp_sub(r, r, t);
+    if (T2) { t = T2[i]; mp_sub(r, r, t); }
+    R[i] = r;
+  }
+}
+// A = (A + A^T)/2 per block  (src/solver.jl:1509-1511, 1607-1609)
+template <int NL> __global__ void k_symmetrize(BlockTab bt, int64_t n, mpn<NL>* A) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = blk_find(bt, i); int64_t loc = i - bt.off[b]; int nn = bt.n[b]; int r = (int)(loc / nn), c = (int)(loc % nn);
+    if (r < c) { mpn<NL>* base = A + bt.off[b]; mpn<NL> x = base[(int64_t)r * nn + c], y = base[(int64_t)c * nn + r];
+      mp_add(x, x, y); if (x.sign) x.exp -= 1; base[(int64_t)r * nn + c] = x; base[(int64_t)c * nn + r] = x; }
+  }
+}
+// single matrix: mirror the upper triangle into the lower (symmetric!, src/tools.jl:43-57) or lower into upper
+template <int NL> __global__ void k_mirror(int n, mpn<NL>* A, int ld, int from_upper) {
+  int64_t tot = (int64_t)n * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / n), c = (int)(i % n);
+    if (r < c) { if (from_upper) A[(int64_t)c * ld + r] = A[(int64_t)r * ld + c]; else A[(int64_t)r * ld + c] = A[(int64_t)c * ld + r]; }
+  }
+}
+// zero the strict upper triangle (approx_cholesky!, src/tools.jl:100-105)
+template <int NL> __global__ void k_zero_upper(int n, mpn<NL>* A, int ld) {
+  int64_t tot = (int64_t)n * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / n), c = (int)(i % n); if (r < c) mp_zero(A[(int64_t)r * ld + c]);
+  }
+}
+// Float64 copy of the symmetric part of each block (input of the Float64 eigenvalue step, src/solver.jl:1659)
+template <int NL> __global__ void k_to_double_sym(BlockTab bt, int64_t n, const mpn<NL>* A, double* out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = blk_find(bt, i); int64_t loc = i - bt.off[b]; int nn = bt.n[b]; int r = (int)(loc / nn), c = (int)(loc % nn);
+    const mpn<NL>* base = A + bt.off[b];
+    out[i] = 0.5 * (mp_to_double(base[(int64_t)r * nn + c]) + mp_to_double(base[(int64_t)c * nn + r]));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// reductions: dot and max-abs, deterministic two-stage
+// ---------------------------------------------------------------------------
+template <int NL> __device__ void block_reduce_sum(mpn<NL>& v, mpn<NL>* sh) {
+  const int tid = threadIdx.x; sh[tid] = v; __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) { if (tid < s) { mpn<NL> a = sh[tid], b = sh[tid + s]; mp_add(a, a, b); sh[tid] = a; } __syncthreads(); }
+  v = sh[0];
+}
+template <int NL> __device__ void block_reduce_max(mpn<NL>& v, mpn<NL>* sh) {
+  const int tid = threadIdx.x; sh[tid] = v; __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) { if (tid < s) { mpn<NL> a = sh[tid], b = sh[tid + s]; if (mp_cmp_abs(b, a) > 0) sh[tid] = b; } __syncthreads(); }
+  v = sh[0];
+}
+// stage 1: partial[blockIdx.x] = sum_i a_i*b_i (b == nullptr: max |a_i|)
+template <int NL> __global__ void k_reduce_partial(int64_t n, const mpn<NL>* a, const mpn<NL>* b, mpn<NL>* partial) {
+  extern __shared__ unsigned char smraw[]; mpn<NL>* sh = (mpn<NL>*)smraw;
+  mpn<NL> acc; mp_zero(acc);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    mpn<NL> x = a[i];
+    if (b) { mpn<NL> y = b[i]; mp_mul(x, x, y); mp_add(acc, acc, x); }
+    else if (mp_cmp_abs(x, acc) > 0) acc = x;
+  }
+  if (b) block_reduce_sum(acc, sh); else block_reduce_max(acc, sh);
+  if (threadIdx.x == 0) { if (!b && acc.sign < 0) acc.sign = 1; partial[blockIdx.x] = acc; }
+}
+// stage 2: out (op) reduce(partial[0..np)).  mode 0: out = r ; 1: out += r ; 2: out = max(out, r)
+template <int NL> __global__ void k_reduce_final(int np, const mpn<NL>* partial, int is_max, mpn<NL>* out, int mode) {
+  extern __shared__ unsigned char smraw[]; mpn<NL>* sh = (mpn<NL>*)smraw;
+  mpn<NL> acc; mp_zero(acc);
+  for (int i = threadIdx.x; i < np; i += blockDim.x) { mpn<NL> x = partial[i]; if (is_max) { if (mp_cmp_abs(x, acc) > 0) acc = x; } else mp_add(acc, acc, x); }
+  if (is_max) block_reduce_max(acc, sh); else block_reduce_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    if (mode == 0) *out = acc; else if (mode == 1) { mpn<NL> o = *out; mp_add(o, o, acc); *out = o; } else { mpn<NL> o = *out; if (mp_cmp_abs(acc, o) > 0) *out = acc; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// matrix-vector products (free-variable coupling: B y, B^T x, LinvB^T t, ...)
+// ---------------------------------------------------------------------------
+// y[i] = beta*y[i] + alpha * sum_k A[i,k] x[k]  (alpha, beta in {-1,0,1}); one warp per row
+template <int NL> __global__ void k_gemv_n(int M, int K, const mpn<NL>* A, int lda, const mpn<NL>* x, mpn<NL>* y, int alpha, int beta) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  mpn<NL> acc; mp_zero(acc);
+  for (int k = lane; k < K; k += 32) { mpn<NL> a = A[(int64_t)warp * lda + k], b = x[k]; mp_mul(a, a, b); mp_add(acc, acc, a); }
+  for (int o = 16; o > 0; o >>= 1) {
+    mpn<NL> other;
+#pragma unroll
+    for (int i = 0; i < NL; i++) other.l[i] = __shfl_down_sync(0xffffffffu, acc.l[i], o);
+    other.exp = __shfl_down_sync(0xffffffffu, acc.exp, o); other.sign = __shfl_down_sync(0xffffffffu, acc.sign, o);
+    mp_add(acc, acc, other);
+  }
+  if (lane == 0) { acc.sign *= alpha; if (beta) { mpn<NL> o = y[warp]; o.sign *= beta; mp_add(acc, acc, o); } y[warp] = acc; }
+}
+// y[j] = beta*y[j] + alpha * sum_k A[k,j] x[k]; one thread per column, rows in chunks across blockIdx.y is not needed for N <= few thousand
+template <int NL> __global__ void k_gemv_t(int K, int N, const mpn<NL>* A, int lda, const mpn<NL>* x, mpn<NL>* y, int alpha, int beta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= N) return;
+  mpn<NL> acc; mp_zero(acc);
+  for (int k = 0; k < K; k++) { mpn<NL> a = A[(int64_t)k * lda + j], b = x[k]; mp_mul(a, a, b); mp_add(acc, acc, a); }
+  acc.sign *= alpha; if (beta) { mpn<NL> o = y[j]; o.sign *= beta; mp_add(acc, acc, o); } y[j] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// panel kernel: Cholesky of one diagonal block (nb <= 32) and the inverse of its
+// factor, one CTA of 32x32 threads, the block in registers/shared memory.
+// status[0] is set to `code` if a pivot is not strictly positive
+// (approx_cholesky!, src/tools.jl:92-95).
+// ---------------------------------------------------------------------------
+template <int NL> __global__ void __launch_bounds__(256) k_potrf_diag(int nb, mpn<NL>* A, int lda, mpn<NL>* Minv, int ldm, int* status, int code) {
+  extern __shared__ unsigned char smraw[];
+  mpn<NL>* Ls = (mpn<NL>*)smraw;                          // 32 x 32 working block
+  mpn<NL>* Ms = Ls + 32 * 32;                             // 32 x 32 inverse
+  mpn<NL>* sinv = Ms + 32 * 32;                           // 32 reciprocal pivots
+  __shared__ int bad;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < 32 * 32; idx += 256) { const int i = idx >> 5, j = idx & 31; mpn<NL> a; mp_zero(a); if (i < nb && j <= i) a = A[(int64_t)i * lda + j]; Ls[idx] = a; mp_zero(Ms[idx]); }
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  for (int c = 0; c < nb; c++) {
+    if (tid == 0) {
+      mpn<NL> a = Ls[c * 32 + c];
+      if (a.sign <= 0) { bad = 1; mp_set_i32(a, 1); }
+      mpn<NL> s, r; mp_sqrt_rsqrt(s, r, a); Ls[c * 32 + c] = s; sinv[c] = r;
+    }
+    __syncthreads();
+    for (int i = c + 1 + tid; i < nb; i += 256) { mpn<NL> a = Ls[i * 32 + c]; mp_mul(a, a, sinv[c]); Ls[i * 32 + c] = a; }
+    __syncthreads();
+    const int w = nb - c - 1;
+    for (int idx = tid; idx < w * w; idx += 256) {
+      const int i = c + 1 + idx / w, j = c + 1 + idx % w;
+      if (j <= i) { mpn<NL> a = Ls[i * 32 + j], t; mp_mul(t, Ls[i * 32 + c], Ls[j * 32 + c]); mp_sub(a, a, t); Ls[i * 32 + j] = a; }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < nb * nb; idx += 256) { const int i = idx / nb, j = idx % nb; A[(int64_t)i * lda + j] = Ls[i * 32 + j]; }
+  if (tid == 0 && bad) atomicCAS(status, 0, code);
+  // inverse of the factor by forward substitution, all 32 columns in parallel:
+  // 8 lanes per column, M[r][j] = -inv_r * sum_{k=j}^{r-1} L[r][k] M[k][j]
+  const int j = tid >> 3, g = tid & 7;
+  if (g == 0 && j < nb) Ms[j * 32 + j] = sinv[j];
+  __syncthreads();
+  for (int r = 1; r < nb; r++) {
+    mpn<NL> acc; mp_zero(acc);
+    if (j < r) for (int k = j + g; k < r; k += 8) { mpn<NL> t; mp_mul(t, Ls[r * 32 + k], Ms[k * 32 + j]); mp_add(acc, acc, t); }
+    for (int o = 4; o > 0; o >>= 1) {
+      mpn<NL> other;
+#pragma unroll
+      for (int i = 0; i < NL; i++) other.l[i] = __shfl_down_sync(0xffffffffu, acc.l[i], o, 8);
+      other.exp = __shfl_down_sync(0xffffffffu, acc.exp, o, 8); other.sign = __shfl_down_sync(0xffffffffu, acc.sign, o, 8);
+      mp_add(acc, acc, other);
+    }
+    if (g == 0 && j < r) { mp_mul(acc, acc, sinv[r]); acc.sign = -acc.sign; Ms[r * 32 + j] = acc; }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < nb * nb; idx += 256) { const int i = idx / nb, jj = idx % nb; Minv[(int64_t)i * ldm + jj] = Ms[i * 32 + jj]; }
+}
+#define POTRF_SMEM(NL) ((2 * 32 * 32 + 32) * sizeof(mpn<NL>))
+
+// ---------------------------------------------------------------------------
+// int8 slice pipeline on CUDA cores
+// ---------------------------------------------------------------------------
+// A "sliced panel" holds nvec vectors of length K: words sl[vec][k4][NSP] (the
+// int8 digits of 4 consecutive k packed per slice) and one exponent per vector.
+struct VecView {          // how vector `vec`, entry k, is addressed in a multi-limb matrix
+  const void* base; int64_t bstride; int vper; int64_t sv; int64_t sk; int nvec; int K;
+};
+__device__ __forceinline__ int64_t vec_off(const VecView& v, int vec) { return (int64_t)(vec / v.vper) * v.bstride + (int64_t)(vec % v.vper) * v.sv; }
+
+// one warp per vector: E[vec] = max exponent of the nonzero entries
+template <int NL> __global__ void k_vec_exp(VecView v, int32_t* E) {
+  const int vec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (vec >= v.nvec) return;
+  const mpn<NL>* p = (const mpn<NL>*)v.base + vec_off(v, vec);
+  int32_t e = I8_EXP_NONE;
+  for (int k = lane; k < v.K; k += 32) { const mpn<NL>* q = p + (int64_t)k * v.sk; if (q->sign != 0) e = max(e, q->exp); }
+  for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+  if (lane == 0) E[vec] = e;
+}
+// one thread per (vec, k4): split 4 consecutive entries into NS digits and pack them per slice.
+// kfast != 0: consecutive threads take consecutive k4 (unit-stride vectors), else consecutive vectors.
+template <int NL> __global__ void k_split(VecView v, const int32_t* E, int K4, int32_t* sl, int kfast) {
+  constexpr int NS = I8Cfg<NL>::NS, NSP = I8Cfg<NL>::NSP;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)v.nvec * K4) return;
+  int vec, k4; if (kfast) { k4 = (int)(idx % K4); vec = (int)(idx / K4); } else { vec = (int)(idx % v.nvec); k4 = (int)(idx / v.nvec); }
+  const mpn<NL>* p = (const mpn<NL>*)v.base + vec_off(v, vec);
+  const int32_t e = E[vec];
+  uint32_t w[NSP];
+#pragma unroll
+  for (int t = 0; t < NSP; t++) w[t] = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int k = 4 * k4 + q;
+    if (k < v.K) {
+      mpn<NL> a = p[(int64_t)k * v.sk]; int8_t dg[NS]; i8_split<NL>(a, e, dg);
+#pragma unroll
+      for (int t = 0; t < NS; t++) w[t] |= (uint32_t)(uint8_t)dg[t] << (8 * q);
+    }
+  }
+  int4* dst = (int4*)(sl + ((int64_t)vec * K4 + k4) * NSP);
+#pragma unroll
+  for (int t = 0; t < NSP / 4; t++) dst[t] = make_int4((int)w[4 * t], (int)w[4 * t + 1], (int)w[4 * t + 2], (int)w[4 * t + 3]);
+}
+
+struct GemmArgs {
+  int M, N, K4, batch;
+  const int32_t* Asl; const int32_t* EA; int64_t a_bvec;     // vectors per batch step of A (0: shared across the batch)
+  const int32_t* Bsl; const int32_t* EB; int64_t b_bvec;
+  void* C; int ldc; int64_t c_bstride;
+  const void* D; int ldd; int64_t d_bstride;
+  int mode;                                                  // 0: C = AB   1: C = D - AB   2: C = D + AB   3: C = -AB
+  int lower_only;                                            // compute only tiles touching i >= j (square outputs)
+};
+
+// C tile 16x16 per CTA, one output per thread, all NS slice-pair sums of that
+// output in registers (NS(NS+1)/2 dp4a per 4 k).  Exact: the int32 sums are
+// carry-normalised every FLUSH steps.
+template <int NL> __global__ void __launch_bounds__(256) k_gemm_dp4a(GemmArgs g) {
+  constexpr int NS = I8Cfg<NL>::NS, NSP = I8Cfg<NL>::NSP, KC = 4, FLUSH = 512;
+  __shared__ __align__(16) int32_t As[16][KC][NSP];
+  __shared__ __align__(16) int32_t Bs[16][KC][NSP];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16, bz = blockIdx.z;
+  if (g.lower_only && j0 > i0 + 15) return;
+  const int32_t* Ab = g.Asl + ((int64_t)bz * g.a_bvec + i0) * g.K4 * NSP;
+  const int32_t* Bb = g.Bsl + ((int64_t)bz * g.b_bvec + j0) * g.K4 * NSP;
+  int32_t acc[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) acc[s] = 0;
+  int64_t top = 0; int since = 0;
+  for (int k0 = 0; k0 < g.K4; k0 += KC) {
+    // cooperative load of 16 x KC x NSP words for A and B (zero fill outside)
+    for (int w = threadIdx.x; w < 16 * KC * (NSP / 4); w += 256) {
+      const int q = w % (NSP / 4), kk = (w / (NSP / 4)) % KC, v = w / ((NSP / 4) * KC);
+      int4 za = make_int4(0, 0, 0, 0), zb = za;
+      if (k0 + kk < g.K4) {
+        if (i0 + v < g.M) za = *(const int4*)(Ab + ((int64_t)v * g.K4 + k0 + kk) * NSP + 4 * q);
+        if (j0 + v < g.N) zb = *(const int4*)(Bb + ((int64_t)v * g.K4 + k0 + kk) * NSP + 4 * q);
+      }
+      *(int4*)&As[v][kk][4 * q] = za; *(int4*)&Bs[v][kk][4 * q] = zb;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kk = 0; kk < KC; kk++) {
+      int32_t a[NSP], b[NSP];
+#pragma unroll
+      for (int q = 0; q < NSP / 4; q++) {
+        int4 va = *(const int4*)&As[ty][kk][4 * q]; a[4 * q] = va.x; a[4 * q + 1] = va.y; a[4 * q + 2] = va.z; a[4 * q + 3] = va.w;
+        int4 vb = *(const int4*)&Bs[tx][kk][4 * q]; b[4 * q] = vb.x; b[4 * q + 1] = vb.y; b[4 * q + 2] = vb.z; b[4 * q + 3] = vb.w;
+      }
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+#pragma unroll
+        for (int t = 0; t <= s; t++) acc[s] = __dp4a(a[t], b[s - t], acc[s]);
+      }
+    }
+    __syncthreads();
+    since += KC;
+    if (since >= FLUSH) { i8_carry_normalize<NS>(acc, top); since = 0; }
+  }
+  i8_carry_normalize<NS>(acc, top);
+  const int i = i0 + ty, j = j0 + tx;
+  if (i >= g.M || j >= g.N) return;
+  if (g.lower_only && j > i) return;
+  const int32_t ea = g.EA[(int64_t)bz * g.a_bvec + i], eb = g.EB[(int64_t)bz * g.b_bvec + j];
+  mpn<NL> r;
+  if (ea == I8_EXP_NONE || eb == I8_EXP_NONE) mp_zero(r);
+  else { uint32_t dg[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) dg[s] = (uint32_t)acc[s];
+    i8_recombine<NL>(r, top, dg, ea + eb); }
+  mpn<NL>* C = (mpn<NL>*)g.C + (int64_t)bz * g.c_bstride + (int64_t)i * g.ldc + j;
+  if (g.mode == 1 || g.mode == 2) {
+    mpn<NL> d = ((const mpn<NL>*)g.D)[(int64_t)bz * g.d_bstride + (int64_t)i * g.ldd + j];
+    if (g.mode == 1) mp_sub(r, d, r); else mp_add(r, d, r);
+  } else if (g.mode == 3) r.sign = -r.sign;
+  *C = r;
+}
+
+// ---------------------------------------------------------------------------
+// low-rank constraint machinery (pointer tables built on the host at upload)
+// ---------------------------------------------------------------------------
+struct MatRef { const void* p; int ld; };                    // a pairing matrix BX[s][r] / BY[s][r]
+// One low-rank piece e of a block, as the kernels see it.
+struct LRTermDev {
+  int32_t p;          // compact constraint row in the cluster
+  int32_t r, s;       // subblock
+  int32_t lam;        // index into the block's lambda array
+  int32_t colV;       // column of its v vector in V_r          (pointers_right[r][(s,p,k)])
+  int32_t rowW;       // row of its w vector in W_r              (pointers_left[r][(s,p,k)])
+  int32_t rowW_t;     // rowW of the transposed piece (s,r,p,k)  (pointers_left[s][(r,p,k)])
+  int32_t colV_t;     // colV of the transposed piece            (pointers_right[s][(r,p,k)])
+};
+// S[p,q] += sum_{e1 in terms(p)} sum_{e2 in terms(q)} lam1 lam2 BX[s1,r2][rowW_t(e1), colV(e2)] BY[s2,r1][rowW_t(e2), colV(e1)]
+// for q >= p  (src/solver.jl:1176-1212).  One thread per (p,q) among the nP constraints touching the block.
+template <int NL> __global__ void k_schur_lowrank(int nP, const int32_t* plist, const int32_t* tstart, const LRTermDev* terms,
+                                                  const mpn<NL>* lam, const MatRef* BX, const MatRef* BY, int m, mpn<NL>* S, int ldS) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)nP * nP) return;
+  const int a = (int)(idx / nP), b = (int)(idx % nP);
+  if (b < a) return;
+  const int p = plist[a], q = plist[b];
+  mpn<NL> acc; mp_zero(acc);
+  for (int e1 = tstart[a]; e1 < tstart[a + 1]; e1++) {
+    const LRTermDev t1 = terms[e1];
+    for (int e2 = tstart[b]; e2 < tstart[b + 1]; e2++) {
+      const LRTermDev t2 = terms[e2];
+      const MatRef bx = BX[t1.s * m + t2.r], by = BY[t2.s * m + t1.r];
+      mpn<NL> v = lam[t1.lam], w = lam[t2.lam]; mp_mul(v, v, w);
+      w = ((const mpn<NL>*)bx.p)[(int64_t)t1.rowW_t * bx.ld + t2.colV]; mp_mul(v, v, w);
+      w = ((const mpn<NL>*)by.p)[(int64_t)t2.rowW_t * by.ld + t1.colV]; mp_mul(v, v, w);
+      mp_add(acc, acc, v);
+    }
+  }
+  mpn<NL>* dst = S + (int64_t)min(p, q) * ldS + max(p, q);
+  mpn<NL> o = *dst; mp_add(o, o, acc); *dst = o;
+}
+// out[p] += sum over the pieces e of constraint p with s <= r of (r != s ? 2 : 1) lam_e * G_{r,s}[rowW(e), colV_t(e)]
+// where G = BY (A_Y gather + trace_A((Y,A_Y)), src/solver.jl:1152-1170, 1368-1407)
+template <int NL> __global__ void k_trace_pairings(int nP, const int32_t* plist, const int32_t* tstart, const LRTermDev* terms,
+                                                   const mpn<NL>* lam, const MatRef* BY, int m, mpn<NL>* out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x; if (a >= nP) return;
+  mpn<NL> acc; mp_zero(acc);
+  for (int e = tstart[a]; e < tstart[a + 1]; e++) {
+    const LRTermDev t = terms[e]; if (t.s > t.r) continue;
+    const MatRef by = BY[t.r * m + t.s];
+    mpn<NL> v = ((const mpn<NL>*)by.p)[(int64_t)t.rowW * by.ld + t.colV_t], l = lam[t.lam]; mp_mul(v, v, l);
+    if (t.r != t.s) v.exp += (v.sign != 0);
+    mp_add(acc, acc, v);
+  }
+  mpn<NL> o = out[plist[a]]; mp_add(o, o, acc); out[plist[a]] = o;
+}
+// out[p] += sum over pieces e (s <= r) of (r != s ? 2 : 1) lam_e * sum_a W_r[rowW(e), a] * ZV_{r,s}[a, colV(e)]
+// (trace_A with vectors, src/solver.jl:1290-1366); ZV_{r,s} = Z[r-rows, s-cols] * V_r
+template <int NL> __global__ void k_trace_vectors(int nP, const int32_t* plist, const int32_t* tstart, const LRTermDev* terms,
+                                                  const mpn<NL>* lam, const MatRef* W, const MatRef* ZV, int m, int delta, mpn<NL>* out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x; if (a >= nP) return;
+  mpn<NL> acc; mp_zero(acc);
+  for (int e = tstart[a]; e < tstart[a + 1]; e++) {
+    const LRTermDev t = terms[e]; if (t.s > t.r) continue;
+    const MatRef w = W[t.r], zv = ZV[t.r * m + t.s];
+    mpn<NL> d; mp_zero(d);
+    for (int u = 0; u < delta; u++) { mpn<NL> x = ((const mpn<NL>*)w.p)[(int64_t)t.rowW * w.ld + u], y = ((const mpn<NL>*)zv.p)[(int64_t)u * zv.ld + t.colV]; mp_mul(x, x, y); mp_add(d, d, x); }
+    mpn<NL> l = lam[t.lam]; mp_mul(d, d, l);
+    if (t.r != t.s) d.exp += (d.sign != 0);
+    mp_add(acc, acc, d);
+  }
+  mpn<NL> o = out[plist[a]]; mp_add(o, o, acc); out[plist[a]] = o;
+}
+// G[a, e] = x[p(e)] * lam_e * v_e[a] for the pieces e of subblock (r,s), in list order
+// (the V_r D factor of compute_weighted_A!, src/solver.jl:1440-1452)
+template <int NL> __global__ void k_weighted_cols(int cnt, const int32_t* elist, const LRTermDev* terms, const mpn<NL>* lam,
+                                                  const mpn<NL>* x, MatRef V, int delta, mpn<NL>* G, int ldg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= cnt * delta) return;
+  const int e = idx % cnt, a = idx / cnt;
+  const LRTermDev t = terms[elist[e]];
+  mpn<NL> c = x[t.p], l = lam[t.lam], v = ((const mpn<NL>*)V.p)[(int64_t)a * V.ld + t.colV];
+  mp_mul(c, c, l); mp_mul(c, c, v); G[(int64_t)a * ldg + e] = c;
+}
+// dense constraint matrices: M += sum_p x[p] A_p (zero entries skipped), src/solver.jl:1422-1426
+template <int NL> __global__ void k_weighted_dense(int np, const int32_t* plist, const mpn<NL>* Aall, int64_t nn, const mpn<NL>* x, mpn<NL>* M) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
+    mpn<NL> acc; mp_zero(acc);
+    for (int p = 0; p < np; p++) { const mpn<NL>* a = Aall + (int64_t)p * nn + i; if (a->sign == 0) continue; mpn<NL> v = *a, c = x[plist[p]]; mp_mul(v, v, c); mp_add(acc, acc, v); }
+    M[i] = acc;
+  }
+}
+// out[plist[p]] += <A_p, Z>  (dense trace, src/solver.jl:1303-1305); one CTA per p
+template <int NL> __global__ void k_trace_dense(int np, const int32_t* plist, const mpn<NL>* Aall, int64_t nn, const mpn<NL>* Z, mpn<NL>* out) {
+  extern __shared__ unsigned char smraw[]; mpn<NL>* sh = (mpn<NL>*)smraw;
+  const int p = blockIdx.x; mpn<NL> acc; mp_zero(acc);
+  for (int64_t i = threadIdx.x; i < nn; i += blockDim.x) { const mpn<NL>* a = Aall + (int64_t)p * nn + i; if (a->sign == 0) continue; mpn<NL> v = *a, z = Z[i]; mp_mul(v, v, z); mp_add(acc, acc, v); }
+  block_reduce_sum(acc, sh);
+  if (threadIdx.x == 0) { mpn<NL> o = out[plist[p]]; mp_add(o, o, acc); out[plist[p]] = o; }
+}
+
+// ---------------------------------------------------------------------------
+// Float64 smallest eigenvalue per block (stands in for KrylovKit's Lanczos,
+// src/solver.jl:1659-1662): Lanczos with full reorthogonalisation, one CTA per
+// block, followed by Sturm bisection on the tridiagonal.  lam[b] receives the
+// smallest Ritz value; iterated to an invariant subspace or until the residual
+// smallest Ritz value is stationary to 1e-10 over 8 steps (reference tolerance 1e-5).
+// ---------------------------------------------------------------------------
+struct EigTask { const double* T; int n; double* V; };      // V: scratch n x (mmax+1)
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+  const int tid = threadIdx.x; sh[tid] = v; __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) { if (tid < s) sh[tid] += sh[tid + s]; __syncthreads(); }
+  double r = sh[0]; __syncthreads(); return r;
+}
+__device__ inline double tridiag_min_eig(const double* al, const double* be, int m) {
+  double lo = 1e300, hi = -1e300;
+  for (int i = 0; i < m; i++) { double r = (i > 0 ? fabs(be[i - 1]) : 0.0) + (i < m - 1 ? fabs(be[i]) : 0.0); lo = fmin(lo, al[i] - r); hi = fmax(hi, al[i] + r); }
+  for (int it = 0; it < 120; it++) {
+    double mid = 0.5 * (lo + hi); if (mid == lo || mid == hi) break;
+    int cnt = 0; double q = 1.0;
+    for (int i = 0; i < m; i++) { q = al[i] - mid - (i > 0 ? be[i - 1] * be[i - 1] / q : 0.0); if (q == 0.0) q = 1e-300; if (q < 0) cnt++; }
+    if (cnt >= 1) hi = mid; else lo = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+#define EIG_MMAX 320
+__global__ void __launch_bounds__(256) k_min_eig(const EigTask* tasks, double* lam) {
+  __shared__ double sh[256]; __shared__ double al[EIG_MMAX], be[EIG_MMAX]; __shared__ double s_lam, s_prev; __shared__ int s_done, s_close;
+  const EigTask t = tasks[blockIdx.x]; const int n = t.n, tid = threadIdx.x;
+  if (n == 1) { if (tid == 0) lam[blockIdx.x] = t.T[0]; return; }
+  double* V = t.V;                                         // column c at V + c*n
+  // deterministic start vector
+  double nrm = 0; for (int i = tid; i < n; i += blockDim.x) { double v = 1.0 + 0.5 * sin(1.0 + 0.7 * i) + 0.25 * cos(2.3 * i); V[i] = v; nrm += v * v; }
+  nrm = sqrt(block_sum_d(nrm, sh)); for (int i = tid; i < n; i += blockDim.x) V[i] /= nrm;
+  __syncthreads();
+  const int mmax = n < EIG_MMAX ? n : EIG_MMAX;
+  if (tid == 0) { s_done = 0; s_close = 0; s_prev = 1e300; s_lam = 0; }
+  __syncthreads();
+  int m = 0;
+  for (int c = 0; c < mmax; c++) {
+    double* v = V + (int64_t)c * n; double* w = V + (int64_t)(c + 1) * n;
+    // w = T v  (row per thread; T symmetric so column access is coalesced)
+    double a_part = 0;
+    for (int i = tid; i < n; i += blockDim.x) { double s = 0; for (int k = 0; k < n; k++) s += t.T[(int64_t)k * n + i] * v[k]; w[i] = s; a_part += s * v[i]; }
+    double alpha = block_sum_d(a_part, sh);
+    // full reorthogonalisation (twice)
+    for (int pass = 0; pass < 2; pass++) for (int q = 0; q <= c; q++) {
+      const double* u = V + (int64_t)q * n; double d = 0; for (int i = tid; i < n; i += blockDim.x) d += w[i] * u[i];
+      d = block_sum_d(d, sh); for (int i = tid; i < n; i += blockDim.x) w[i] -= d * u[i]; __syncthreads();
+    }
+    double bp = 0; for (int i = tid; i < n; i += blockDim.x) bp += w[i] * w[i];
+    double beta = sqrt(block_sum_d(bp, sh));
+    if (tid == 0) { al[c] = alpha; be[c] = beta; }
+    m = c + 1;
+    __syncthreads();
+    const bool check = (m == mmax) || (beta <= 1e-14 * (fabs(alpha) + 1e-300)) || (m >= 8 && (m % 4) == 0);
+    if (check) {
+      if (tid == 0) {
+        double l = tridiag_min_eig(al, be, m);
+        const bool close = fabs(l - s_prev) <= 1e-10 * fmax(1.0, fabs(l));
+        s_done = (m == mmax) || (beta <= 1e-14 * (fabs(alpha) + 1e-300)) || (close && s_close);
+        s_close = close;
+        s_prev = l; s_lam = l;
+      }
+      __syncthreads();
+      if (s_done) break;
+    }
+    for (int i = tid; i < n; i += blockDim.x) w[i] /= beta;
+    __syncthreads();
+  }
+  if (tid == 0) lam[blockIdx.x] = s_lam;
+}

@@ -1,0 +1,153 @@
+"""Parity of the CUDA path against the CPU oracle (and, for the integer slice
+pipeline, bit-exactly against the host build of the same arithmetic).  All calls
+go through the C ABI (ctypes)."""
+import ctypes as C
+import os
+import random
+from fractions import Fraction
+
+import mpmath
+import numpy as np
+import pytest
+
+import clrs_b200
+from clrs_b200 import wire, workloads, Solver, solvesdp
+
+pytestmark = pytest.mark.gpu
+PREC = 256
+TOL_OBJ = mpmath.mpf(10) ** -25      # north star: objectives agree to a relative 1e-25 at 256 bit
+
+
+def rnd_matrix(rng, r, c, spread, zero_frac=0.05):
+    out = []
+    for _ in range(r):
+        row = []
+        for _ in range(c):
+            if rng.random() < zero_frac:
+                row.append(mpmath.mpf(0)); continue
+            m = mpmath.mpf(rng.getrandbits(300)) / 2 ** 300 + mpmath.mpf(1) / 7
+            row.append(rng.choice([1, -1]) * m * mpmath.mpf(2) ** rng.randint(-spread, spread))
+        out.append(row)
+    return out
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    sdp = workloads.maxcut(workloads.laplacian_cycle(3))
+    s = Solver(sdp, lib="device")
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def tiny_oracle():
+    sdp = workloads.maxcut(workloads.laplacian_cycle(3))
+    s = Solver(sdp, lib="oracle")
+    yield s
+    s.close()
+
+
+def hostcheck():
+    return C.CDLL(os.path.join(os.path.dirname(clrs_b200.DEVICE_LIB), "libclrs_hostcheck.so"))
+
+
+@pytest.mark.parametrize("M,N,K,spread", [(1, 1, 1, 0), (3, 4, 5, 0), (17, 19, 33, 40), (40, 33, 70, 300), (5, 5, 8, 2), (64, 48, 130, 10)])
+def test_gemm_bitexact_vs_host_arithmetic(tiny, M, N, K, spread):
+    """The int8 slice pipeline is exact integer arithmetic: the device result must equal
+    the host build of the same split/recombine code bit for bit."""
+    rng = random.Random(M * 1000 + N * 10 + K)
+    with mpmath.workprec(400):
+        A = wire.to_wire(rnd_matrix(rng, M, K, spread), PREC)
+        B = wire.to_wire(rnd_matrix(rng, K, N, spread), PREC)
+    Cd, _ = tiny.mp_gemm(A, B)
+    Ch = wire.wire_zeros((M, N), PREC)
+    hostcheck().hc_gemm(M, N, K, A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), Ch.ctypes.data_as(C.c_void_p))
+    assert Cd.tobytes() == Ch.tobytes()
+
+
+def test_gemm_vs_oracle(tiny, tiny_oracle):
+    rng = random.Random(7)
+    M, N, K = 20, 24, 50
+    with mpmath.workprec(400):
+        A = wire.to_wire(rnd_matrix(rng, M, K, 30), PREC)
+        B = wire.to_wire(rnd_matrix(rng, K, N, 30), PREC)
+    Cd, _ = tiny.mp_gemm(A, B)
+    Co, _ = tiny_oracle.mp_gemm(A, B)
+    with mpmath.workprec(600):
+        a, b, cd, co = (wire.from_wire(v, PREC) for v in (A, B, Cd, Co))
+        for i in range(M):
+            for j in range(N):
+                scale = max(abs(v) for v in a[i, :]) * max(abs(v) for v in b[:, j])
+                assert abs(cd[i, j] - co[i, j]) <= scale * K * mpmath.mpf(2) ** -250
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 32, 33, 70, 100])
+def test_cholesky_vs_oracle(tiny, tiny_oracle, n):
+    rng = random.Random(n)
+    with mpmath.workprec(400):
+        G = mpmath.matrix(rnd_matrix(rng, n, n, 3, 0.0))
+        A = G * G.T + mpmath.eye(n) * n
+        Aw = wire.to_wire(A, PREC)
+    Ld = tiny.mp_cholesky(Aw)
+    Lo = tiny_oracle.mp_cholesky(Aw)
+    with mpmath.workprec(600):
+        ld, lo = wire.from_wire(Ld, PREC), wire.from_wire(Lo, PREC)
+        scale = max(abs(v) for v in lo.reshape(-1))
+        err = max(abs(x - y) for x, y in zip(ld.reshape(-1), lo.reshape(-1)))
+        assert err <= scale * mpmath.mpf(2) ** -235     # kappa-amplified rounding only
+        for i in range(n):
+            for j in range(i + 1, n):
+                assert ld[i, j] == 0
+
+
+def test_cholesky_reports_nonpositive_pivot(tiny):
+    A = wire.to_wire([[1, 2], [2, 1]], PREC)
+    with pytest.raises(clrs_b200.SolverFailure):
+        tiny.mp_cholesky(A)
+
+
+def _compare(sdp, **kw):
+    dev = solvesdp(sdp, lib="device", duality_gap_threshold=1e-30, **kw)
+    ref = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-30, **kw)
+    assert dev.status == ref.status == "Optimal", (dev, ref)
+    with mpmath.workprec(400):
+        assert abs(dev.p_obj - ref.p_obj) <= TOL_OBJ * max(1, abs(ref.p_obj)), (dev, ref)
+        assert abs(dev.d_obj - ref.d_obj) <= TOL_OBJ * max(1, abs(ref.d_obj)), (dev, ref)
+        assert abs(dev.gap - ref.gap) <= TOL_OBJ
+    assert abs(dev.iterations - ref.iterations) <= 1, (dev.iterations, ref.iterations)
+    return dev, ref
+
+
+def test_first_iteration_intermediates_match_oracle():
+    """Kernel-level parity after one iteration: S, residuals and directions."""
+    sdp = workloads.delsarte(8, 3, Fraction(1, 2))
+    d = Solver(sdp, lib="device"); o = Solver(sdp, lib="oracle")
+    d.iterate(); o.iterate()
+    with mpmath.workprec(400):
+        for what, j, l in [("S", 0, 0), ("d", 0, 0), ("p", 0, 0), ("dx", 0, 0), ("dy", 0, 0), ("dX", 0, 6), ("dY", 0, 7), ("X", 0, 6), ("Y", 0, 7)]:
+            a = wire.from_wire(d.debug_get(what, j, l), PREC); b = wire.from_wire(o.debug_get(what, j, l), PREC)
+            scale = max([abs(v) for v in b] + [mpmath.mpf(2) ** -200])
+            err = max(abs(x - y) for x, y in zip(a, b))
+            assert err <= scale * mpmath.mpf(10) ** -55, (what, float(err / scale))
+    d.close(); o.close()
+
+
+def test_maxcut_three_cycle_known_answer():
+    dev, _ = _compare(workloads.maxcut(workloads.laplacian_cycle(3)))
+    assert abs(dev.p_obj - mpmath.mpf(9) / 4) < mpmath.mpf(10) ** -29      # README.md:70-72
+
+
+def test_polyopt_x2_plus_1():
+    dev, _ = _compare(workloads.polyopt(lambda x: x * x + 1, 1))
+    assert abs(dev.p_obj - 1) < mpmath.mpf(10) ** -29                       # README.md:146-150
+
+
+def test_delsarte_e8_is_240():
+    dev, _ = _compare(workloads.delsarte(8, 3, Fraction(1, 2)))
+    assert abs(dev.p_obj - 240) < mpmath.mpf(10) ** -25                     # test/runtests_solver.jl:86-87
+
+
+def test_maxcut_complete_graph_dense_path():
+    n = 12
+    dev, _ = _compare(workloads.maxcut(workloads.laplacian_complete(n)))
+    assert abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -25   # K_n: n^2/4
