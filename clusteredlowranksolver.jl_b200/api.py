@@ -96,7 +96,7 @@ class Solver:
     """One solver handle (device or oracle) holding one uploaded SDP."""
 
     def __init__(self, sdp: ClusteredSDP, lib: str = "device", device: int = 0, gemm_path: int = 0,
-                 matmul_prec: int = 0, **kwargs):
+                 matmul_prec: int = 0, oracle_skip_zeros: bool = False, **kwargs):
         self.kind = lib
         self.lib = load_library(lib)
         self.pre = "clrs_" if lib == "device" else "clrs_oracle_"
@@ -132,6 +132,10 @@ class Solver:
                 val = mpmath.mpf(v.numerator) / v.denominator if isinstance(v, Fraction) else mpmath.mpf(v)
                 w = wire.to_wire(val, self.prec)
                 self._call("set_option_num", self.h, C.c_int(_OPT_IDS[k]), w.ctypes.data_as(C.c_void_p))
+        if lib == "oracle" and oracle_skip_zeros:
+            fn = self._fn("set_dense_skip_zeros")
+            fn.restype = None
+            fn(self.h, C.c_int32(1))
         self._upload(sdp)
         self.finished = False
 
@@ -239,6 +243,20 @@ class Solver:
             raise KeyError(what)
         return buf[:n]
 
+    # -- measurement hooks (device library only) ------------------------------
+    def profile(self, enable: bool):
+        fn = self._fn("profile"); fn.restype = None; fn(self.h, C.c_int32(int(enable)))
+
+    def profile_get(self):
+        out = (C.c_double * 7)()
+        fn = self._fn("profile_get"); fn.restype = None; fn(self.h, out)
+        return {"dp4a_ms": out[0], "dp4a_mp_flops": out[1], "dp4a_launches": int(out[2]), "tc_ms": out[3],
+                "tc_mp_flops": out[4], "tc_launches": int(out[5]), "kernel_launches": int(out[6])}
+
+    def last_iteration_ms(self) -> float:
+        fn = self._fn("last_iteration_ms"); fn.restype = C.c_double
+        return float(fn(self.h))
+
     # -- standalone kernels -------------------------------------------------
     def mp_gemm(self, A: np.ndarray, B: np.ndarray, path: int = 0):
         M, K = A.shape
@@ -283,10 +301,11 @@ class SolveResult:
 
 
 def solvesdp(sdp: ClusteredSDP, lib: str = "device", maxiterations: int = 500, verbose: bool = False,
-             callback=None, keep_solver: bool = False, device: int = 0, gemm_path: int = 0, **kwargs) -> SolveResult:
+             callback=None, keep_solver: bool = False, device: int = 0, gemm_path: int = 0,
+             oracle_skip_zeros: bool = False, **kwargs) -> SolveResult:
     """Mirror of solvesdp(sdp; kwargs...) (src/solver.jl:100-744) above the C ABI."""
     res = SolveResult()
-    S = Solver(sdp, lib=lib, device=device, gemm_path=gemm_path, **kwargs)
+    S = Solver(sdp, lib=lib, device=device, gemm_path=gemm_path, oracle_skip_zeros=oracle_skip_zeros, **kwargs)
     gap_thr = float(kwargs.get("duality_gap_threshold", 1e-15))
     derr_thr = float(kwargs.get("dual_error_threshold", 1e-30))
     perr_thr = float(kwargs.get("primal_error_threshold", 1e-30))

@@ -126,6 +126,9 @@ struct SolverBase {
   virtual int mp_gemm(int M, int N, int K, const void* A, const void* B, void* C, int path, double* ms) = 0;
   virtual int mp_cholesky(int n, const void* A, void* L) = 0;
   virtual int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) = 0;
+  virtual void profile(int enable) = 0;
+  virtual void profile_get(double* out) = 0;
+  virtual double last_iteration_ms() = 0;
   size_t wire_size() const { return 16 + 8 * (size_t)((prec + 63) / 64); }
 };
 
@@ -141,63 +144,109 @@ template <int NL> struct Solver : SolverBase {
   void download_wire(void* w, const num* d, size_t n) { std::vector<num> h(n); CK(cudaMemcpyAsync(h.data(), d, n * sizeof(num), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); for (size_t i = 0; i < n; i++) mpn_to_wire((char*)w + i * wire_size(), h[i]); }
 
   // ---- sliced panels -------------------------------------------------------
-  struct Sliced { int32_t* sl = nullptr; int32_t* E = nullptr; int nvec = 0, K = 0, K4 = 0; size_t cap_w = 0, cap_v = 0; };
-  void ensure(Sliced& s, int nvec, int K) {
-    int K4 = (K + 3) / 4; size_t need = (size_t)nvec * K4 * NSP;
-    if (need > s.cap_w || (size_t)nvec > s.cap_v) {
-      // grow-only, stream ordered
-      if (s.sl) CK(cudaFreeAsync(s.sl, st)); if (s.E) CK(cudaFreeAsync(s.E, st));
-      s.cap_w = std::max(need, s.cap_w); s.cap_v = std::max<size_t>(nvec, s.cap_v);
-      CK(cudaMallocAsync((void**)&s.sl, std::max<size_t>(s.cap_w, 4) * sizeof(int32_t), st));
-      CK(cudaMallocAsync((void**)&s.E, std::max<size_t>(s.cap_v, 1) * sizeof(int32_t), st));
-    }
-    s.nvec = nvec; s.K = K; s.K4 = K4;
+  // lay 0: dp4a words sl[vec][K4][NSP];  lay 1: tc planes planes[t][vec][Kp] (gemm_tc.cuh)
+  struct Sliced { int32_t* sl = nullptr; int32_t* E = nullptr; uint8_t* planes = nullptr; int nvec = 0, K = 0, K4 = 0, Kp = 0, lay = 0; size_t cap_w = 0, cap_v = 0, cap_b = 0; };
+  void ensure(Sliced& s, int nvec, int K, int lay) {
+    int K4 = (K + 3) / 4; int Kp = (K + 31) & ~31;
+    if ((size_t)nvec > s.cap_v) { if (s.E) CK(cudaFreeAsync(s.E, st)); s.cap_v = nvec; CK(cudaMallocAsync((void**)&s.E, std::max<size_t>(s.cap_v, 1) * sizeof(int32_t), st)); }
+    if (lay == 0) { size_t need = (size_t)nvec * K4 * NSP;
+      if (need > s.cap_w) { if (s.sl) CK(cudaFreeAsync(s.sl, st)); s.cap_w = need; CK(cudaMallocAsync((void**)&s.sl, std::max<size_t>(s.cap_w, 4) * sizeof(int32_t), st)); } }
+    else { size_t need = (size_t)NS * nvec * Kp;
+      if (need > s.cap_b) { if (s.planes) CK(cudaFreeAsync(s.planes, st)); s.cap_b = need; CK(cudaMallocAsync((void**)&s.planes, std::max<size_t>(s.cap_b, 16), st)); } }
+    s.nvec = nvec; s.K = K; s.K4 = K4; s.Kp = Kp; s.lay = lay;
   }
   std::vector<Sliced*> owned_sliced;
   static VecView rows_view(const num* A, int lda, int M, int K) { VecView v; v.base = A; v.bstride = 0; v.vper = M > 0 ? M : 1; v.sv = lda; v.sk = 1; v.nvec = M; v.K = K; return v; }
   static VecView cols_view(const num* B, int ldb, int K, int N) { VecView v; v.base = B; v.bstride = 0; v.vper = N > 0 ? N : 1; v.sv = 1; v.sk = ldb; v.nvec = N; v.K = K; return v; }
-  void split(Sliced& s, const VecView& v, bool kfast) {
-    ensure(s, v.nvec, v.K); if (v.nvec == 0 || v.K == 0) return;
-    k_vec_exp<NL><<<(v.nvec * 32 + 255) / 256, 256, 0, st>>>(v, s.E);
-    int64_t tot = (int64_t)v.nvec * s.K4;
-    k_split<NL><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0);
+  void split(Sliced& s, const VecView& v, bool kfast, int lay = 0) {
+    ensure(s, v.nvec, v.K, lay); if (v.nvec == 0 || v.K == 0) return;
+    nlaunch++, k_vec_exp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 255) / 256), 256, 0, st>>>(v, s.E);
+    if (lay == 0) { int64_t tot_ = (int64_t)v.nvec * s.K4;
+      nlaunch++, k_split<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0); }
+    else { int64_t tot_ = (int64_t)v.nvec * (s.Kp / 4);
+      nlaunch++, k_split_tc<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes, kfast ? 1 : 0); }
   }
-  void split_rows(Sliced& s, const num* A, int lda, int M, int K) { split(s, rows_view(A, lda, M, K), true); }
-  void split_cols(Sliced& s, const num* B, int ldb, int K, int N) { split(s, cols_view(B, ldb, K, N), false); }
+  void split_rows(Sliced& s, const num* A, int lda, int M, int K, int lay = 0) { split(s, rows_view(A, lda, M, K), true, lay); }
+  void split_cols(Sliced& s, const num* B, int ldb, int K, int N, int lay = 0) { split(s, cols_view(B, ldb, K, N), false, lay); }
+  // does a product of this shape go to the tensor cores?
+  bool use_tc(int M, int N, int K) const { if (opt.gemm_path == 1) return false; if (opt.gemm_path == 2) return M >= 1 && N >= 1 && K >= 1; return M >= 128 && N >= 32 && K >= 96; }
 
   // C (M x N) = op(D, A*B);  A, B sliced with vector offsets a0, b0
   void gemm(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0,
             int batch = 1, int64_t a_bvec = 0, int64_t b_bvec = 0, int64_t c_bs = 0, int64_t d_bs = 0, int lower_only = 0) {
     if (M == 0 || N == 0) return;
-    if (A.K4 != B.K4) throw CudaError("gemm: inner dimensions differ");
-    GemmArgs g; g.M = M; g.N = N; g.K4 = A.K4; g.batch = batch;
-    g.Asl = A.sl + (int64_t)a0 * A.K4 * NSP; g.EA = A.E + a0; g.a_bvec = a_bvec;
-    g.Bsl = B.sl + (int64_t)b0 * B.K4 * NSP; g.EB = B.E + b0; g.b_bvec = b_bvec;
-    g.C = C; g.ldc = ldc; g.c_bstride = c_bs; g.D = D; g.ldd = ldd; g.d_bstride = d_bs; g.mode = mode; g.lower_only = lower_only;
-    if (A.K4 == 0) {   // empty inner dimension: C = op(D, 0)
-      throw CudaError("gemm: K == 0 not supported");
+    if (A.K != B.K || A.lay != B.lay) throw CudaError("gemm: operand panels do not match");
+    if (A.K == 0) throw CudaError("gemm: K == 0 not supported");
+    prof_begin();
+    if (A.lay == 1) gemm_tc(A, a0, B, b0, M, N, C, ldc, mode, D, ldd, batch, a_bvec, b_bvec, c_bs, d_bs, lower_only);
+    else {
+      GemmArgs g; g.M = M; g.N = N; g.K4 = A.K4; g.batch = batch;
+      g.Asl = A.sl + (int64_t)a0 * A.K4 * NSP; g.EA = A.E + a0; g.a_bvec = a_bvec;
+      g.Bsl = B.sl + (int64_t)b0 * B.K4 * NSP; g.EB = B.E + b0; g.b_bvec = b_bvec;
+      g.C = C; g.ldc = ldc; g.c_bstride = c_bs; g.D = D; g.ldd = ldd; g.d_bstride = d_bs; g.mode = mode; g.lower_only = lower_only;
+      dim3 grid((N + 15) / 16, (M + 15) / 16, batch);
+      nlaunch++, k_gemm_dp4a<NL><<<grid, 256, 0, st>>>(g);
     }
-    dim3 grid((N + 15) / 16, (M + 15) / 16, batch);
-    k_gemm_dp4a<NL><<<grid, 256, 0, st>>>(g);
-    n_gemm_launch++;
+    prof_end(2.0 * M * N * (double)A.K * batch * (lower_only ? 0.5 : 1.0), A.lay);
   }
-  long n_gemm_launch = 0;
+  // ---- tensor-core path ---------------------------------------------------------------
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeFn encode_fn = nullptr;
+  uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0;
+  CUtensorMap make_map(const Sliced& P, int box_rows) {
+    if (!encode_fn) { void* fn = nullptr; cudaDriverEntryPointQueryResult q; CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q)); if (!fn) throw CudaError("cuTensorMapEncodeTiled not available"); encode_fn = (EncodeFn)fn; }
+    CUtensorMap m; cuuint64_t dims[3] = {(cuuint64_t)P.Kp, (cuuint64_t)P.nvec, (cuuint64_t)NS};
+    cuuint64_t strides[2] = {(cuuint64_t)P.Kp, (cuuint64_t)P.Kp * (cuuint64_t)P.nvec};
+    cuuint32_t box[3] = {(cuuint32_t)tc::KC, (cuuint32_t)box_rows, 1}; cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, P.planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+  }
+  void gemm_tc(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode, const num* D, int ldd,
+               int batch, int64_t a_bvec, int64_t b_bvec, int64_t c_bs, int64_t d_bs, int lower_only) {
+    if (a0 != 0 || b0 != 0) throw CudaError("gemm_tc: panel offsets are not supported");
+    const int ntn = (N + 127) / 128; int BN = ((N + ntn - 1) / ntn + 15) & ~15; if (BN > 128) BN = 128;
+    const int Npitch = (N + 15) & ~15;
+    const size_t outs = (size_t)batch * M * Npitch;
+    if (outs > tc_cap) { if (tc_bytes) CK(cudaFreeAsync(tc_bytes, st)); if (tc_top) CK(cudaFreeAsync(tc_top, st)); tc_cap = outs;
+      CK(cudaMallocAsync((void**)&tc_bytes, tc_cap * NS, st)); CK(cudaMallocAsync((void**)&tc_top, tc_cap * sizeof(int32_t), st)); }
+    CUtensorMap mA = make_map(A, tc::BM), mB = make_map(B, BN);
+    const int KMAX = 3584; int cur_mode = mode; const num* curD = D; int cur_ldd = ldd; int64_t cur_dbs = d_bs;
+    for (int k0 = 0; k0 < A.Kp; k0 += KMAX) {
+      tc::Args a; a.M = M; a.N = N; a.Kp = std::min(KMAX, A.Kp - k0); a.k0 = k0; a.BN = BN; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch; a.batch = batch;
+      a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = lower_only;
+      dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, batch);
+      nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
+      const int64_t tot_ = (int64_t)batch * M * N;
+      nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, curD, cur_ldd, cur_dbs, cur_mode, lower_only);
+      // later K ranges accumulate onto C
+      cur_mode = (mode == 1 || mode == 3) ? 1 : 2; curD = C; cur_ldd = ldc; cur_dbs = c_bs;
+    }
+  }
+  // ---- optional per-launch GEMM profile (bench.py roofline) ------------------------------------
+  bool prof_on = false; cudaEvent_t pe0 = nullptr, pe1 = nullptr; double prof_ms[2] = {0, 0}, prof_flops[2] = {0, 0}; long prof_n[2] = {0, 0};
+  void prof_begin() { if (prof_on) CK(cudaEventRecord(pe0, st)); }
+  void prof_end(double mp_flops, int lay) { if (!prof_on) return; CK(cudaEventRecord(pe1, st)); CK(cudaEventSynchronize(pe1)); float t = 0; cudaEventElapsedTime(&t, pe0, pe1); prof_ms[lay] += t; prof_flops[lay] += mp_flops; prof_n[lay]++; }
+  long nlaunch = 0;
   Sliced tA, tB;    // scratch panels
   // C = op(D, A*B) for plain matrices A (M x K, lda), B (K x N, ldb)
   void mm(const num* A, int lda, const num* B, int ldb, int M, int N, int K, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0) {
-    split_rows(tA, A, lda, M, K); split_cols(tB, B, ldb, K, N); gemm(tA, 0, tB, 0, M, N, C, ldc, mode, D, ldd);
+    const int lay = use_tc(M, N, K) ? 1 : 0;
+    split_rows(tA, A, lda, M, K, lay); split_cols(tB, B, ldb, K, N, lay); gemm(tA, 0, tB, 0, M, N, C, ldc, mode, D, ldd);
   }
 
   // ---- flat helpers ------------------------------------------------------------
-  void zero(num* a, int64_t n) { if (n) k_zero<NL><<<grid_for(n), 256, 0, st>>>(n, a); }
-  void copy(num* r, const num* a, int64_t n) { if (n) k_copy<NL><<<grid_for(n), 256, 0, st>>>(n, r, a); }
-  void addsub(num* r, const num* a, int sa, const num* b, int sb, int64_t n) { if (n) k_addsub<NL><<<grid_for(n), 256, 0, st>>>(n, r, a, sa, b, sb); }
+  void zero(num* a, int64_t n) { if (n) nlaunch++, k_zero<NL><<<grid_for(n), 256, 0, st>>>(n, a); }
+  void copy(num* r, const num* a, int64_t n) { if (n) nlaunch++, k_copy<NL><<<grid_for(n), 256, 0, st>>>(n, r, a); }
+  void addsub(num* r, const num* a, int sa, const num* b, int sb, int64_t n) { if (n) nlaunch++, k_addsub<NL><<<grid_for(n), 256, 0, st>>>(n, r, a, sa, b, sb); }
   num* partial = nullptr;
   void reduce(const num* a, const num* b, int64_t n, num* out, int mode) {   // b == null: max-abs
     if (n == 0) { if (mode == 0) zero(out, 1); return; }
     int g = grid_for(n, 128, 256);
-    k_reduce_partial<NL><<<g, 128, 128 * sizeof(num), st>>>(n, a, b, partial);
-    k_reduce_final<NL><<<1, 128, 128 * sizeof(num), st>>>(g, partial, b ? 0 : 1, out, mode);
+    nlaunch++, k_reduce_partial<NL><<<g, 128, 128 * sizeof(num), st>>>(n, a, b, partial);
+    nlaunch++, k_reduce_final<NL><<<1, 128, 128 * sizeof(num), st>>>(g, partial, b ? 0 : 1, out, mode);
   }
 
   // ---- blocked Cholesky with explicit factor inverse -----------------------------------
@@ -209,7 +258,7 @@ template <int NL> struct Solver : SolverBase {
     if (ldm == n) zero(Minv, (int64_t)n * n); else for (int r = 0; r < n; r++) zero(Minv + (int64_t)r * ldm, n);
     for (int k0 = 0; k0 < n; k0 += 32) {
       const int nb = std::min(32, n - k0), rem = n - k0 - nb;
-      k_potrf_diag<NL><<<1, 256, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code);
+      nlaunch++, k_potrf_diag<NL><<<1, 256, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code);
       if (rem > 0) {
         num* A21 = A + (int64_t)(k0 + nb) * lda + k0; num* A22 = A + (int64_t)(k0 + nb) * lda + k0 + nb;
         split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);
@@ -218,7 +267,7 @@ template <int NL> struct Solver : SolverBase {
         gemm(tA, 0, tA, 0, rem, rem, A22, lda, 1, A22, lda, 1, 0, 0, 0, 0, 1);   // A22 -= L21 L21^T (lower)
       }
     }
-    k_zero_upper<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, A, lda);
+    nlaunch++, k_zero_upper<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, A, lda);
     // rows of the inverse below the diagonal blocks: M[i,0:k0] = -inv(L_ii) * (L[i,0:k0] * M[0:k0,0:k0])
     if (n > 32) {
       size_t need = (size_t)32 * n; if (need > chol_W_cap) { chol_W = dalloc<num>(need); chol_W_cap = need; }
@@ -246,8 +295,8 @@ template <int NL> struct Solver : SolverBase {
     num* part = nullptr; int umax = 0;
     struct RS { int cnt = 0; int32_t* elist = nullptr; num* H = nullptr; Sliced Hs; num* G = nullptr; };
     std::vector<RS> rs;                                                                     // index r*m+s, s <= r
-    // per-iteration cached panels
-    Sliced YS, XiS, MS;
+    // per-iteration cached panels (layout `lay`: 1 = tensor-core panels for large blocks)
+    Sliced YS, XiS, MS; int lay = 0;
   };
   struct Clu { int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; int off = 0; };
   std::vector<Clu> cl; std::vector<Block*> blk;   // blk: all blocks in (j,l) order
@@ -271,6 +320,8 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaStreamCreate(&st));
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
+    CK(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaEventCreate(&pe0)); CK(cudaEventCreate(&pe1));
     mp_zero(hconst);
     double dv[10] = {o.beta_infeasible, o.beta_feasible, o.gamma, o.omega_p, o.omega_d, o.duality_gap_threshold, o.dual_error_threshold, o.primal_error_threshold, o.max_complementary_gap, o.step_length_threshold};
     for (int i = 0; i < 10; i++) mp_from_double(hopt[i], dv[i]);
@@ -278,8 +329,9 @@ template <int NL> struct Solver : SolverBase {
   }
   ~Solver() {
     cudaStreamSynchronize(st);
-    for (Sliced* s : owned_sliced) { if (s->sl) cudaFree(s->sl); if (s->E) cudaFree(s->E); }
-    if (tA.sl) cudaFree(tA.sl); if (tA.E) cudaFree(tA.E); if (tB.sl) cudaFree(tB.sl); if (tB.E) cudaFree(tB.E);
+    owned_sliced.push_back(&tA); owned_sliced.push_back(&tB);
+    for (Sliced* s : owned_sliced) { if (s->sl) cudaFree(s->sl); if (s->E) cudaFree(s->E); if (s->planes) cudaFree(s->planes); }
+    if (tc_bytes) cudaFree(tc_bytes); if (tc_top) cudaFree(tc_top); if (pe0) cudaEventDestroy(pe0); if (pe1) cudaEventDestroy(pe1);
     for (void* p : allocs) cudaFree(p);
     for (auto& e : ev) cudaEventDestroy(e);
     cudaStreamDestroy(st);
@@ -347,14 +399,14 @@ template <int NL> struct Solver : SolverBase {
       h[SC_GAPTHR] = hopt[5]; h[SC_DERRTHR] = hopt[6]; h[SC_PERRTHR] = hopt[7]; h[SC_MAXGAP] = hopt[8]; h[SC_STEPTHR] = hopt[9]; h[SC_CONSTANT] = hconst;
       CK(cudaMemcpyAsync(sc, h.data(), SC_COUNT * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
     // x = 0, y = 0, X = omega_p I, Y = omega_d I  (src/solver.jl:187-201)
-    for (Block* b0 : blk) { k_set_diag<NL><<<(b0->n + 127) / 128, 128, 0, st>>>(b0->n, X + b0->off, b0->n, sc + SC_OMEGA_P); k_set_diag<NL><<<(b0->n + 127) / 128, 128, 0, st>>>(b0->n, Y + b0->off, b0->n, sc + SC_OMEGA_D); }
+    for (Block* b0 : blk) { nlaunch++, k_set_diag<NL><<<(b0->n + 127) / 128, 128, 0, st>>>(b0->n, X + b0->off, b0->n, sc + SC_OMEGA_P); nlaunch++, k_set_diag<NL><<<(b0->n + 127) / 128, 128, 0, st>>>(b0->n, Y + b0->off, b0->n, sc + SC_OMEGA_D); }
     finalized = true;
     initial_quantities();
     return 0;
   }
   int finalize_block(Clu& c0, Block& b0) {
     const int n = b0.n, m = b0.m, dl = b0.delta;
-    own(b0.YS); own(b0.XiS); own(b0.MS);
+    own(b0.YS); own(b0.XiS); own(b0.MS); b0.lay = use_tc(n, n, n) ? 1 : 0;
     if (b0.high_rank) {
       b0.np = (int)b0.dense_p.size();
       std::vector<int32_t> pl(b0.dense_p.begin(), b0.dense_p.end()); b0.d_plist = upload(pl);
@@ -363,8 +415,8 @@ template <int NL> struct Solver : SolverBase {
       b0.T1 = dalloc<num>((size_t)b0.np * n * n); b0.T2 = dalloc<num>((size_t)b0.np * n * n); b0.Sd = dalloc<num>((size_t)b0.np * b0.np);
       own(b0.AallB); own(b0.AallV); own(b0.T1S); own(b0.T2V);
       if (b0.np > 0) {
-        VecView v; v.base = b0.Aall; v.bstride = (int64_t)n * n; v.vper = n; v.sv = 1; v.sk = n; v.nvec = b0.np * n; v.K = n; split(b0.AallB, v, false);   // columns of every A_p
-        VecView w; w.base = b0.Aall; w.bstride = 0; w.vper = b0.np; w.sv = (int64_t)n * n; w.sk = 1; w.nvec = b0.np; w.K = n * n; split(b0.AallV, w, true);   // A_q flattened
+        VecView v; v.base = b0.Aall; v.bstride = (int64_t)n * n; v.vper = n; v.sv = 1; v.sk = n; v.nvec = b0.np * n; v.K = n; split(b0.AallB, v, false, b0.lay);   // columns of every A_p
+        VecView w; w.base = b0.Aall; w.bstride = 0; w.vper = b0.np; w.sv = (int64_t)n * n; w.sk = 1; w.nvec = b0.np; w.K = n * n; split(b0.AallV, w, true, use_tc(b0.np, b0.np, n * n) ? 1 : 0);   // A_q flattened
       }
       return 0;
     }
@@ -421,13 +473,13 @@ template <int NL> struct Solver : SolverBase {
   void weighted_A(num* dst, const num* a) {
     for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
       num* M = dst + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; const num* aj = a + c0.off;
-      if (b0.high_rank) { k_weighted_dense<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, aj, M); continue; }
+      if (b0.high_rank) { nlaunch++, k_weighted_dense<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, aj, M); continue; }
       zero(M, (int64_t)n * n);
       for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { auto& q = b0.rs[r * m + s]; if (q.cnt == 0) continue;
-        k_weighted_cols<NL><<<(q.cnt * dl + 127) / 128, 128, 0, st>>>(q.cnt, q.elist, b0.lr_terms, b0.lr_lam, aj, MatRef{b0.V[r], b0.u_r[r]}, dl, q.G, q.cnt);
+        nlaunch++, k_weighted_cols<NL><<<(q.cnt * dl + 127) / 128, 128, 0, st>>>(q.cnt, q.elist, b0.lr_terms, b0.lr_lam, aj, MatRef{b0.V[r], b0.u_r[r]}, dl, q.G, q.cnt);
         split_rows(tA, q.G, q.cnt, dl, q.cnt);
         gemm(tA, 0, q.Hs, 0, dl, dl, M + (int64_t)r * dl * n + (int64_t)s * dl, n); }
-      if (m > 1) k_mirror<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, M, n, 0);
+      if (m > 1) nlaunch++, k_mirror<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, M, n, 0);
     }
   }
   // out[p] = <A_p, Z>  (trace_A with vectors, src/solver.jl:1290-1366)
@@ -435,19 +487,19 @@ template <int NL> struct Solver : SolverBase {
     zero(out, Ptot);
     for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
       const num* Zb = Z + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; num* oj = out + c0.off;
-      if (b0.high_rank) { if (b0.np) k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, Zb, oj); continue; }
+      if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, Zb, oj); continue; }
       if (b0.nP == 0) continue;
       for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { if (b0.rs[r * m + s].cnt == 0) continue;
         split_rows(tA, Zb + (int64_t)r * dl * n + (int64_t)s * dl, n, dl, dl); gemm(tA, 0, b0.Vs[r], 0, dl, b0.u_r[r], b0.ZV[r * m + s], b0.u_r[r]); }
-      k_trace_vectors<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_W, b0.d_ZV, m, dl, oj);
+      nlaunch++, k_trace_vectors<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_W, b0.d_ZV, m, dl, oj);
     }
   }
   // out[p] = <A_p, Y> from the stored pairings (src/solver.jl:1368-1407)
   void trace_pairings(num* out) {
     zero(out, Ptot);
     for (auto& c0 : cl) for (auto& b0 : c0.blocks) { num* oj = out + c0.off;
-      if (b0.high_rank) { if (b0.np) k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)b0.n * b0.n, Y + b0.off, oj); continue; }
-      if (b0.nP) k_trace_pairings<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BY, b0.m, oj); }
+      if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)b0.n * b0.n, Y + b0.off, oj); continue; }
+      if (b0.nP) nlaunch++, k_trace_pairings<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BY, b0.m, oj); }
   }
   // P, d, p  (compute_residuals!, src/solver.jl:863-918); `tr` must hold <A_*, Y>
   void residuals() {
@@ -455,10 +507,10 @@ template <int NL> struct Solver : SolverBase {
     k_residual_P<NL><<<grid_for(tot), 256, 0, st>>>(tot, P, X, Cm, maximize);
     // d = c - B y - tr
     addsub(d, c, 1, tr, -1, Ptot);
-    if (N > 0) for (auto& c0 : cl) if (c0.P) k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.B, N, y, d + c0.off, -1, 1);
+    if (N > 0) for (auto& c0 : cl) if (c0.P) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.B, N, y, d + c0.off, -1, 1);
     // p = +-b - sum_j B_j^T x_j
     if (N > 0) { addsub(p, b, maximize ? 1 : -1, b, 0, N);
-      for (auto& c0 : cl) if (c0.P) k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1); }
+      for (auto& c0 : cl) if (c0.P) nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1); }
   }
   void errors() { reduce(P, nullptr, tot, sc + SC_ERRP, 0); reduce(p, nullptr, N, sc + SC_ERRp, 0); reduce(d, nullptr, Ptot, sc + SC_ERRd, 0); }
   void objectives() {
@@ -467,7 +519,7 @@ template <int NL> struct Solver : SolverBase {
   }
   void scalar(int phase, const num* M = nullptr, const num* dM = nullptr, const double* lam = nullptr, int which = 0) {
     ScalarCfg cfg{opt.correctoronly, opt.safe_step, maximize};
-    k_scalar<NL><<<1, 32, 0, st>>>(phase, sc, flags, dinfo, cfg, (int)blk.size(), d_bn, d_boff, M, dM, lam, which);
+    nlaunch++, k_scalar<NL><<<1, 32, 0, st>>>(phase, sc, flags, dinfo, cfg, (int)blk.size(), d_bn, d_boff, M, dM, lam, which);
   }
   void pull_info() {
     double h[32]; int f[FL_COUNT];
@@ -510,21 +562,24 @@ template <int NL> struct Solver : SolverBase {
           gemm(b0.Ws[s], 0, tB, 0, b0.ul_r[s], b0.u_r[r], Bout[s * m + r], b0.u_r[r]); } }                // W_s part[s-rows]            (:1131,:1143)
     }
     int64_t np2 = (int64_t)b0.nP * b0.nP;
-    k_schur_lowrank<NL><<<(unsigned)((np2 + 127) / 128), 128, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BX, b0.d_BY, m, c0.S, c0.P);
+    nlaunch++, k_schur_lowrank<NL><<<(unsigned)((np2 + 127) / 128), 128, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BX, b0.d_BY, m, c0.S, c0.P);
   }
   void schur_block_dense(Clu& c0, Block& b0) {        // T = X^-1 A_p Y, S[p,q] += <A_q, T>   (src/solver.jl:1089-1104)
     const int n = b0.n, np = b0.np; if (np == 0) return; const int64_t nn = (int64_t)n * n;
-    gemm(b0.XiS, 0, b0.AallB, 0, n, n, b0.T1, n, 0, nullptr, 0, np, 0, n, nn, 0);
-    { VecView v; v.base = b0.T1; v.bstride = nn; v.vper = n; v.sv = n; v.sk = 1; v.nvec = np * n; v.K = n; split(b0.T1S, v, true); }
-    gemm(b0.T1S, 0, b0.YS, 0, n, n, b0.T2, n, 0, nullptr, 0, np, n, 0, nn, 0);
-    { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true); }
+    // T1t[(p,j)][i] = sum_k A_p[k][j] X^-1[i][k]   (= (X^-1 A_p)^T; the 90000-row operand sits on the 128-lane M side)
+    gemm(b0.AallB, 0, b0.XiS, 0, np * n, n, b0.T1, n);
+    // T2[(p,i)][b] = sum_j T1_p[i][j] Y[j][b]
+    { VecView v; v.base = b0.T1; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = np * n; v.K = n; split(b0.T1S, v, false, b0.lay); }
+    gemm(b0.T1S, 0, b0.YS, 0, np * n, n, b0.T2, n);
+    // S[p,q] += sum_ab T2_p[ab] A_q[ab]
+    { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true, b0.AallV.lay); }
     gemm(b0.T2V, 0, b0.AallV, 0, np, np, b0.Sd, np);
-    k_scatter_upper<NL><<<(unsigned)(((int64_t)np * np + 127) / 128), 128, 0, st>>>(np, b0.d_plist, b0.Sd, c0.S, c0.P);
+    nlaunch++, k_scatter_upper<NL><<<(unsigned)(((int64_t)np * np + 127) / 128), 128, 0, st>>>(np, b0.d_plist, b0.Sd, c0.S, c0.P);
   }
   void decomposition(int e0) {
     for (auto& c0 : cl) { zero(c0.S, (int64_t)c0.P * c0.P);
       for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_block_dense(c0, b0); else schur_block_lowrank(c0, b0); }
-      if (c0.P) k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); }
+      if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); }
     CK(cudaEventRecord(ev[e0], st));
     for (auto& c0 : cl) chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S);
     CK(cudaEventRecord(ev[e0 + 1], st));
@@ -534,7 +589,7 @@ template <int NL> struct Solver : SolverBase {
         mm(c0.Minv, c0.P, c0.B, N, c0.P, N, c0.P, c0.LinvB, N); }                                       // LinvB = L^-1 B  (:1258)
       CK(cudaEventRecord(ev[e0 + 2], st));
       for (auto& c0 : cl) { if (c0.P == 0) continue;
-        split_cols(tA, c0.LinvB, N, c0.P, N);
+        split_cols(tA, c0.LinvB, N, c0.P, N, use_tc(N, N, c0.P) ? 1 : 0);
         gemm(tA, 0, tA, 0, N, N, Q, N, first ? 0 : 2, Q, N); first = false; }                            // Q = sum LinvB^T LinvB  (:1268-1269)
       CK(cudaEventRecord(ev[e0 + 3], st));
       chol(Q, N, N, QMinv, N, CLRS_ERR_CHOL_Q);
@@ -543,36 +598,36 @@ template <int NL> struct Solver : SolverBase {
   }
   // search direction  (compute_search_direction!, src/solver.jl:1474-1616)
   void direction() {
-    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, P + b0->off, n, n, n); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // P Y
+    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, P + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // P Y
     addsub(T1, T1, 1, R, -1, tot);
-    for (Block* b0 : blk) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); }    // Z = X^-1 (P Y - R)
-    k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
+    for (Block* b0 : blk) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n, b0->lay); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); }    // Z = X^-1 (P Y - R)
+    nlaunch++, k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
     trace_vectors(tr, dY);
-    if (Ptot) k_vec_rhs<NL><<<(Ptot + 127) / 128, 128, 0, st>>>(Ptot, dx, d, tr);                                                          // rhs_x = -d - <A_*, Z>
+    if (Ptot) nlaunch++, k_vec_rhs<NL><<<(Ptot + 127) / 128, 128, 0, st>>>(Ptot, dx, d, tr);                                                          // rhs_x = -d - <A_*, Z>
     // block elimination  (:1527-1582)
     if (N > 0) copy(dy, p, N);
     for (auto& c0 : cl) { if (c0.P == 0) continue;
-      k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, dx + c0.off, c0.t, 1, 0);                              // t_j = L_j^-1 rhs_j
-      if (N > 0) k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, dy, -1, 1); }                                     // dy -= LinvB_j^T t_j
-    if (N > 0) { k_gemv_n<NL><<<(N * 32 + 255) / 256, 256, 0, st>>>(N, N, QMinv, N, dy, tmpN, 1, 0);
-      k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(N, N, QMinv, N, tmpN, dy, 1, 0); }                                                       // dy = Q^-1 dy
+      nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, dx + c0.off, c0.t, 1, 0);                              // t_j = L_j^-1 rhs_j
+      if (N > 0) nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, dy, -1, 1); }                                     // dy -= LinvB_j^T t_j
+    if (N > 0) { nlaunch++, k_gemv_n<NL><<<(N * 32 + 255) / 256, 256, 0, st>>>(N, N, QMinv, N, dy, tmpN, 1, 0);
+      nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(N, N, QMinv, N, tmpN, dy, 1, 0); }                                                       // dy = Q^-1 dy
     for (auto& c0 : cl) { if (c0.P == 0) continue;
-      if (N > 0) k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
-      k_gemv_t<NL><<<(c0.P + 127) / 128, 128, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, c0.t, dx + c0.off, 1, 0); }                                 // dx_j = L_j^-T t_j
+      if (N > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
+      nlaunch++, k_gemv_t<NL><<<(c0.P + 127) / 128, 128, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, c0.t, dx + c0.off, 1, 0); }                                 // dx_j = L_j^-T t_j
     weighted_A(dX, dx); addsub(dX, dX, 1, P, 1, tot);                                                                                       // dX = P + sum dx_p A_p
-    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // dX Y
+    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // dX Y
     addsub(T1, R, 1, T1, -1, tot);
-    for (Block* b0 : blk) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); }    // dY = X^-1 (R - dX Y)
-    k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
+    for (Block* b0 : blk) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n, b0->lay); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); }    // dY = X^-1 (R - dX Y)
+    nlaunch++, k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
   }
   // lambda_min( L^-1 dM L^-T ) per block in Float64  (compute_step_length, src/solver.jl:1620-1693); Mi holds L^-1
   void step_eigs(const num* Mi, const num* dM, double* lam, bool have_MS) {
     for (Block* b0 : blk) { const int n = b0->n; if (n == 1) continue;
-      if (!have_MS) split_rows(b0->MS, Mi + b0->off, n, n, n);
-      split_cols(tB, dM + b0->off, n, n, n); gemm(b0->MS, 0, tB, 0, n, n, U + b0->off, n);             // U = L^-1 dM
-      split_rows(tA, U + b0->off, n, n, n); gemm(tA, 0, b0->MS, 0, n, n, T1 + b0->off, n); }            // T = U L^-T
-    k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, T1, Td);
-    k_min_eig<<<(unsigned)blk.size(), 256, 0, st>>>(eigT, lam);
+      if (!have_MS) split_rows(b0->MS, Mi + b0->off, n, n, n, b0->lay);
+      split_cols(tB, dM + b0->off, n, n, n, b0->lay); gemm(b0->MS, 0, tB, 0, n, n, U + b0->off, n);             // U = L^-1 dM
+      split_rows(tA, U + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->MS, 0, n, n, T1 + b0->off, n); }            // T = U L^-T
+    nlaunch++, k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, T1, Td);
+    nlaunch++, k_min_eig<<<(unsigned)blk.size(), 256, 0, st>>>(eigT, lam);
   }
 
   int check_status() { return hflags[FL_STATUS]; }
@@ -593,14 +648,14 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaEventRecord(ev[0], st));
     scalar(0);                                                        // mu, mu_p  (SC_D0 = <X,Y> is kept current)
     // R = mu_p I - X Y
-    for (Block* b0 : blk) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n); split_rows(tA, X + b0->off, n, n, n); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); }
+    for (Block* b0 : blk) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n, b0->lay); split_rows(tA, X + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); }
     k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, (const num*)nullptr, sc + SC_MUP);
     CK(cudaEventRecord(ev[1], st));
     // Cholesky of X, L^-1, X^-1  (src/solver.jl:388-399, 1117)
     copy(L, X, tot);
     for (Block* b0 : blk) { const int n = b0->n; chol(L + b0->off, n, n, Minv + b0->off, n, CLRS_ERR_CHOL_X);
-      split_cols(tA, Minv + b0->off, n, n, n); gemm(tA, 0, tA, 0, n, n, Xi + b0->off, n);               // X^-1 = L^-T L^-1
-      split_rows(b0->XiS, Xi + b0->off, n, n, n); }
+      split_cols(tA, Minv + b0->off, n, n, n, b0->lay); gemm(tA, 0, tA, 0, n, n, Xi + b0->off, n);               // X^-1 = L^-T L^-1
+      split_rows(b0->XiS, Xi + b0->off, n, n, n, b0->lay); }
     CK(cudaEventRecord(ev[2], st));
     decomposition(3);                                                 // events 3..7
     trace_pairings(tr); residuals();
@@ -610,7 +665,7 @@ template <int NL> struct Solver : SolverBase {
     reduce(X, dY, tot, sc + SC_D1, 0); reduce(dX, Y, tot, sc + SC_D2, 0); reduce(dX, dY, tot, sc + SC_D3, 0);
     errors(); scalar(1);
     CK(cudaEventRecord(ev[10], st));
-    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n); split_cols(tB, dY + b0->off, n, n, n); gemm(tA, 0, tB, 0, n, n, T1 + b0->off, n); }
+    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); split_cols(tB, dY + b0->off, n, n, n, b0->lay); gemm(tA, 0, tB, 0, n, n, T1 + b0->off, n); }
     k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, T1, sc + SC_MUC);                     // R = mu_c I - XY - dXdY
     CK(cudaEventRecord(ev[11], st));
     direction();                                                      // corrector
@@ -623,10 +678,10 @@ template <int NL> struct Solver : SolverBase {
     scalar(3);
     CK(cudaEventRecord(ev[13], st));
     // the step  (src/solver.jl:485-495)
-    if (Ptot) k_axpy<NL><<<grid_for(Ptot), 256, 0, st>>>(Ptot, x, dx, sc + SC_ALPHAD);
-    if (N) k_axpy<NL><<<grid_for(N), 256, 0, st>>>(N, y, dy, sc + SC_ALPHAP);
-    k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, X, dX, sc + SC_ALPHAD);
-    k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, Y, dY, sc + SC_ALPHAP);
+    if (Ptot) nlaunch++, k_axpy<NL><<<grid_for(Ptot), 256, 0, st>>>(Ptot, x, dx, sc + SC_ALPHAD);
+    if (N) nlaunch++, k_axpy<NL><<<grid_for(N), 256, 0, st>>>(N, y, dy, sc + SC_ALPHAP);
+    nlaunch++, k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, X, dX, sc + SC_ALPHAD);
+    nlaunch++, k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, Y, dY, sc + SC_ALPHAP);
     objectives();
     reduce(X, Y, tot, sc + SC_D0, 0);                                  // <X,Y> of the new iterate for the next mu
     CK(cudaEventRecord(ev[14], st));
@@ -643,6 +698,7 @@ template <int NL> struct Solver : SolverBase {
     info->alpha_d = hinfo[INFO_ALPHAD]; info->alpha_p = hinfo[INFO_ALPHAP]; info->beta_c = hinfo[INFO_BETAC];
     info->d_obj_new = hinfo[INFO_DOBJ + 10]; info->p_obj_new = hinfo[INFO_POBJ + 10]; info->gap_new = hinfo[INFO_GAP + 10];
     auto ms = [&](int a, int b_) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b_]); return (double)t; };
+    last_ms = ms(0, 14);
     info->phase_ms[0] = ms(2, 7); info->phase_ms[1] = ms(8, 9); info->phase_ms[2] = ms(11, 12); info->phase_ms[3] = ms(12, 13); info->phase_ms[4] = ms(1, 2);
     info->phase_ms[5] = ms(0, 1) + ms(10, 11); info->phase_ms[6] = ms(7, 8);
     info->phase_ms[7] = ms(2, 3); info->phase_ms[8] = ms(3, 4); info->phase_ms[9] = ms(4, 5); info->phase_ms[10] = ms(5, 6); info->phase_ms[11] = ms(6, 7);
@@ -668,8 +724,8 @@ template <int NL> struct Solver : SolverBase {
   int mp_gemm(int M, int N_, int K, const void* A, const void* B, void* C, int path, double* ms) override {
     num* dA = upload_wire(A, (size_t)M * K); num* dB = upload_wire(B, (size_t)K * N_); num* dC = dalloc<num>((size_t)M * N_);
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    (void)path;
-    CK(cudaEventRecord(e0, st)); mm(dA, K, dB, N_, M, N_, K, dC, N_); CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st));
+    const int saved = opt.gemm_path; if (path) opt.gemm_path = path;
+    CK(cudaEventRecord(e0, st)); mm(dA, K, dB, N_, M, N_, K, dC, N_); CK(cudaEventRecord(e1, st)); opt.gemm_path = saved; CK(cudaStreamSynchronize(st));
     float t = 0; cudaEventElapsedTime(&t, e0, e1); if (ms) *ms = t; cudaEventDestroy(e0); cudaEventDestroy(e1);
     CK(cudaGetLastError());
     download_wire(C, dC, (size_t)M * N_); return 0;
@@ -683,6 +739,10 @@ template <int NL> struct Solver : SolverBase {
     if (f[FL_STATUS]) { err = "non-positive pivot"; return f[FL_STATUS]; }
     return 0;
   }
+  double last_ms = 0;
+  void profile(int enable) override { prof_on = enable != 0; for (int i = 0; i < 2; i++) { prof_ms[i] = 0; prof_flops[i] = 0; prof_n[i] = 0; } nlaunch = 0; }
+  void profile_get(double* o) override { o[0] = prof_ms[0]; o[1] = prof_flops[0]; o[2] = (double)prof_n[0]; o[3] = prof_ms[1]; o[4] = prof_flops[1]; o[5] = (double)prof_n[1]; o[6] = (double)nlaunch; }
+  double last_iteration_ms() override { return last_ms; }
   int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) override {
     std::string w(what); const num* src = nullptr; int64_t n = 0;
     if (w == "S") { src = cl[j].S; n = (int64_t)cl[j].P * cl[j].P; } else if (w == "LinvB") { src = cl[j].LinvB; n = (int64_t)cl[j].P * N; }
@@ -733,5 +793,8 @@ int clrs_comm_init(clrs_handle* h, int32_t rank, int32_t nranks, const void*) { 
 int clrs_comm_unique_id(void* out128) { memset(out128, 0, 128); return CLRS_OK; }
 int clrs_mp_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, const void* A, const void* B, void* C, int32_t path, double* ms) { GUARD(h, return h->s->mp_gemm(M, N, K, A, B, C, path, ms);) }
 int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L) { GUARD(h, return h->s->mp_cholesky(n, A, L);) }
+void clrs_profile(clrs_handle* h, int32_t enable) { h->s->profile(enable); }
+void clrs_profile_get(clrs_handle* h, double* out7) { h->s->profile_get(out7); }
+double clrs_last_iteration_ms(clrs_handle* h) { return h->s->last_iteration_ms(); }
 int64_t clrs_debug_get(clrs_handle* h, const char* what, int32_t j, int32_t l, void* out, int64_t cap) { try { return h->s->debug_get(what, j, l, out, cap); } catch (const std::exception& e) { h->err = e.what(); return -1; } }
 }

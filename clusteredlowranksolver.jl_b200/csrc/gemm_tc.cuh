@@ -1,2 +1,283 @@
-// gemm_tc.cuh — tcgen05 int8 slice-pair GEMM (filled in below the CUDA-core path).
+// gemm_tc.cuh — the int8 slice-pair GEMM on the 5th-generation tensor cores
+// (north star subsystem 1): TMA -> shared memory -> tcgen05.mma kind::i8 -> int32
+// accumulators in TMEM -> carry-propagating epilogue.
+//
+// Operands are "tc panels": for every slice t an int8 matrix [nvec][Kp] (K-major,
+// Kp = K rounded up to 32), i.e. one 3-D tensor {Kp, nvec, NS} described to TMA.
+// An output tile is 128 (rows of the left panel) x BN (rows of the right panel).
+// The slice-pair sums D_s = sum_{t+u=s} A_t B_u^T are produced four diagonals at
+// a time, least significant first:
+//
+//   group g = diagonals d0..d1 (d0 = 4g): four int32 accumulators of BN columns in
+//   TMEM.  For every 128-byte K chunk the slices stream through one shared-memory
+//   ring:  A_0..A_d1  and  B_d1..B_0 ; A_i meets the window B_{d0-i..d1-i}, so each
+//   operand chunk is loaded once per group and used by up to four MMAs.
+//   Epilogue (4 warps, one TMEM lane = one output row per thread): low byte of
+//   each diagonal (plus carry) goes to a byte plane in HBM, the carry moves up;
+//   the carry out of the group is written back into TMEM as the initial value of
+//   the next group's least significant accumulator, so carries never leave the SM.
+//
+// The result is NS byte planes + one int32 plane per output: the exact integer
+// sum_s D_s 256^(NS-1-s) in two's complement radix 256.  k_tc_recombine turns it
+// into multi-limb numbers (same i8_recombine as the CUDA-core path: the two paths
+// produce identical bits).
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "mpf.cuh"
+#include "i8split.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;            // rows per tile = TMEM lanes
+constexpr int KC = 128;            // bytes of K per ring slot (one 128B swizzle atom row)
+constexpr int SLOT_BYTES = BM * KC;   // 16 KiB
+constexpr int NSLOT = 12;
+constexpr int GROUP = 4;           // diagonals resident in TMEM
+constexpr int NTHREADS = 192;      // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+struct Args {
+  int M, N, Kp;            // Kp: padded K (multiple of 32) of this launch's K range
+  int k0;                  // first K byte of the range (multiple of 128)
+  int BN;                  // tile width, multiple of 16, <= 128
+  int a_bvec, b_bvec;      // panel rows per batch step (0: shared)
+  int NS;                  // slices
+  int Npitch, batch;
+  uint8_t* obytes;         // [NS][batch][M][Npitch]
+  int32_t* otop;           // [batch][M][Npitch]
+  int lower_only;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* ring = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(ring + NSLOT * SLOT_BYTES);
+  uint64_t* empty = full + NSLOT;
+  uint64_t* tmem_full = empty + NSLOT;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * a.BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
+  if (a.lower_only && n0 > m0 + BM - 1) return;
+  const int NS = a.NS, BN = a.BN;
+  const int ngroups = (NS + GROUP - 1) / GROUP;
+  const int nkc = (a.Kp + KC - 1) / KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1); mbar_init(tmem_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+      uint32_t L = 0;
+      const int arow = bz * a.a_bvec + m0, brow = bz * a.b_bvec + n0;
+      const uint32_t abytes = BM * KC, bbytes = (uint32_t)BN * KC;
+      for (int g = ngroups - 1; g >= 0; g--) {
+        const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
+        for (int kc = 0; kc < nkc; kc++) {
+          const int kcoord = a.k0 + kc * KC;
+          auto load = [&](bool isA, int slice) {
+            const uint32_t slot = L % NSLOT, use = L / NSLOT;
+            mbar_wait(&empty[slot], (use & 1) ^ 1);
+            mbar_expect_tx(&full[slot], isA ? abytes : bbytes);
+            tma_load_3d(ring + slot * SLOT_BYTES, isA ? &tmA : &tmB, &full[slot], kcoord, isA ? arow : brow, slice);
+            L++;
+          };
+          for (int sp = 0; sp < w; sp++) load(false, d1 - sp);
+          for (int i = 0; i <= d1; i++) { if (i + w <= d1) load(false, d1 - (i + w)); load(true, i); }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t Lbase = 0; uint32_t epi_parity = 0;
+      for (int g = ngroups - 1; g >= 0; g--) {
+        const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
+        const bool carry_in = (g != ngroups - 1);
+        if (carry_in) { mbar_wait(tmem_empty, epi_parity); epi_parity ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        for (int kc = 0; kc < nkc; kc++) {
+          const int ninstr = min(KC / 32, (a.Kp - kc * KC) / 32);
+          for (int i = 0; i <= d1; i++) {
+            const uint32_t LA = Lbase + (uint32_t)(min(i + w, d1) + 1 + i);
+            const uint32_t slotA = LA % NSLOT;
+            mbar_wait(&full[slotA], (LA / NSLOT) & 1);
+            const uint64_t descA = make_desc(smem_u32(ring + slotA * SLOT_BYTES));
+            const int sp_hi = min(d1, i + w);
+            for (int sp = i; sp <= sp_hi; sp++) {
+              const uint32_t LB = Lbase + (uint32_t)(sp < w ? sp : 2 * sp - w);
+              const uint32_t slotB = LB % NSLOT;
+              mbar_wait(&full[slotB], (LB / NSLOT) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint64_t descB = make_desc(smem_u32(ring + slotB * SLOT_BYTES));
+              const int acc = (i + (d1 - sp)) - d0;                       // diagonal index inside the group
+              const uint32_t tcol = tmem_base + (uint32_t)(acc * BN);
+              for (int kk = 0; kk < ninstr; kk++) {
+                const uint32_t accumulate = (kc == 0 && i == 0 && kk == 0) ? ((carry_in && acc == w) ? 1u : 0u) : 1u;
+                umma_i8(tcol, descA + (uint64_t)(2 * kk), descB + (uint64_t)(2 * kk), idesc, accumulate);
+              }
+            }
+            umma_commit(&empty[slotA]);                                   // A_i is done after this step
+            { const uint32_t LB = Lbase + (uint32_t)(i < w ? i : 2 * i - w); umma_commit(&empty[LB % NSLOT]); }   // so is B_{s'=i}
+          }
+          Lbase += 2u * (uint32_t)(d1 + 1);
+        }
+        umma_commit(tmem_full);
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, one output row per thread =====================
+    const int quad = warp & 3;                                   // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int m = m0 + row;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const size_t plane = (size_t)a.batch * a.M * a.Npitch;
+    const size_t rowoff = ((size_t)bz * a.M + m) * a.Npitch;
+    uint32_t full_parity = 0;
+    for (int g = ngroups - 1; g >= 0; g--) {
+      const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
+      mbar_wait(tmem_full, full_parity); full_parity ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        int32_t carry[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) carry[q] = 0;
+        const bool store_ok = (m < a.M) && (n0 + c0 < a.Npitch);
+        for (int acc = w; acc >= 0; acc--) {
+          uint32_t v[16];
+          tmem_ld16(tlane + (uint32_t)(acc * BN + c0), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            const int32_t t = (int32_t)v[q] + carry[q];
+            packed[q >> 2] |= (uint32_t)(t & 255) << (8 * (q & 3));
+            carry[q] = t >> 8;
+          }
+          if (store_ok) *(uint4*)(a.obytes + (size_t)(d0 + acc) * plane + rowoff + n0 + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        if (g > 0) {
+          uint32_t cv[16];
+#pragma unroll
+          for (int q = 0; q < 16; q++) cv[q] = (uint32_t)carry[q];
+          tmem_st16(tlane + (uint32_t)((GROUP - 1) * BN + c0), cv);   // initial value of the next group's least significant diagonal
+        } else if (store_ok) {
+          int4* dst = (int4*)(a.otop + rowoff + n0 + c0);
+          dst[0] = make_int4(carry[0], carry[1], carry[2], carry[3]); dst[1] = make_int4(carry[4], carry[5], carry[6], carry[7]);
+          dst[2] = make_int4(carry[8], carry[9], carry[10], carry[11]); dst[3] = make_int4(carry[12], carry[13], carry[14], carry[15]);
+        }
+      }
+      if (g > 0) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(tmem_empty);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+}  // namespace tc
+
+// split into the tc panel layout: planes[t][vec][Kp] int8; one thread per (vec, 4 consecutive k)
+template <int NL> __global__ void k_split_tc(VecView v, const int32_t* E, int Kp, int64_t nvec_pitch, uint8_t* planes, int kfast) {
+  constexpr int NS = I8Cfg<NL>::NS;
+  const int K4 = Kp / 4;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)v.nvec * K4) return;
+  int vec, k4; if (kfast) { k4 = (int)(idx % K4); vec = (int)(idx / K4); } else { vec = (int)(idx % v.nvec); k4 = (int)(idx / v.nvec); }
+  const mpn<NL>* p = (const mpn<NL>*)v.base + vec_off(v, vec);
+  const int32_t e = E[vec];
+  uint32_t w[NS];
+#pragma unroll
+  for (int t = 0; t < NS; t++) w[t] = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int k = 4 * k4 + q;
+    if (k < v.K) {
+      mpn<NL> a = p[(int64_t)k * v.sk]; int8_t dg[NS]; i8_split<NL>(a, e, dg);
+#pragma unroll
+      for (int t = 0; t < NS; t++) w[t] |= (uint32_t)(uint8_t)dg[t] << (8 * q);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NS; t++) *(uint32_t*)(planes + ((int64_t)t * nvec_pitch + vec) * Kp + 4 * k4) = w[t];
+}
+
+// byte planes + top -> multi-limb C (op with D), one thread per output
+template <int NL> __global__ void k_tc_recombine(int M, int N, int Npitch, int batch, const uint8_t* obytes, const int32_t* otop,
+                                                 const int32_t* EA, int64_t a_bvec, const int32_t* EB, int64_t b_bvec,
+                                                 mpn<NL>* C, int ldc, int64_t c_bs, const mpn<NL>* D, int ldd, int64_t d_bs, int mode, int lower_only) {
+  constexpr int NS = I8Cfg<NL>::NS;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)batch * M * N) return;
+  const int n = (int)(idx % N), m = (int)((idx / N) % M), bz = (int)(idx / ((int64_t)N * M));
+  if (lower_only && n > m) return;
+  const size_t plane = (size_t)batch * M * Npitch, off = ((size_t)bz * M + m) * Npitch + n;
+  uint32_t dg[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) dg[s] = obytes[(size_t)s * plane + off];
+  const int64_t top = (int64_t)otop[off] * 256 + (int64_t)dg[0];
+  const int32_t ea = EA[(int64_t)bz * a_bvec + m], eb = EB[(int64_t)bz * b_bvec + n];
+  mpn<NL> r;
+  if (ea == I8_EXP_NONE || eb == I8_EXP_NONE) mp_zero(r); else i8_recombine<NL>(r, top, dg, ea + eb);
+  if (mode == 1 || mode == 2) { mpn<NL> d = D[(int64_t)bz * d_bs + (int64_t)m * ldd + n]; if (mode == 1) mp_sub(r, d, r); else mp_add(r, d, r); }
+  else if (mode == 3) r.sign = -r.sign;
+  C[(int64_t)bz * c_bs + (int64_t)m * ldc + n] = r;
+}

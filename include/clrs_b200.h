@@ -199,6 +199,16 @@ int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L);
  * "Q","d","p","dx","dy","x","y","LinvB" (cluster j).  Returns count written. */
 int64_t clrs_debug_get(clrs_handle* h, const char* what, int32_t j, int32_t l, void* out, int64_t capacity);
 
+/* ---- measurement hooks (bench.py) --------------------------------------- */
+/* enable != 0: time every multi-precision GEMM launch with CUDA events on the
+ * library's stream and count kernel launches; resets the counters. */
+void clrs_profile(clrs_handle* h, int32_t enable);
+/* out7 = { ms, mp_flops, launches } of the CUDA-core int8 path, the same three
+ * for the tcgen05 path, then the number of kernel launches since clrs_profile. */
+void clrs_profile_get(clrs_handle* h, double* out7);
+/* device time of the last clrs_iterate (CUDA events on the library's stream), ms */
+double clrs_last_iteration_ms(clrs_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -240,6 +240,8 @@ struct LRTerm { int r, s, p, k; Num lambda; Mat v, w; int colV = -1, rowW = -1; 
 struct Block {
   int m = 1, delta = 1, n = 1; bool high_rank = false; Mat C;
   std::vector<int> dense_p; std::vector<Mat> dense_A;
+  std::vector<std::vector<int>> dense_cols;                   // nonzero columns of A_p   (zero-skipping mode)
+  std::vector<std::vector<std::pair<int, int>>> dense_nz;     // nonzero entries of A_p, row-major
   std::vector<LRTerm> lr;                                   // insertion order
   std::vector<std::vector<std::vector<int>>> rs;            // rs[r][s] -> term indices in order
   std::map<std::tuple<int, int, int, int>, int> find;       // (r,s,p,k) -> term
@@ -272,6 +274,10 @@ struct Oracle {
   bool finalized = false;
   // optional sampling of the dense Schur path for the bounded CPU baseline
   int dense_p_limit = -1;
+  // Zero-skipping evaluation of the dense Schur path.  Bit-identical to the plain path: every
+  // skipped operation is an exact `x + 0*y` (tests/test_oracle.py checks S bit for bit); it only
+  // makes full-size MAX-CUT instances (A_p = E_pp stored dense) affordable on the CPU.
+  bool dense_skip_zeros = false;
 
   template <class F> void for_blocks(F f) { for (auto& c : cl) for (auto& b : c.blocks) f(c, b); }
 
@@ -359,7 +365,7 @@ struct Oracle {
       Mat& M = b.*dst; M.zero(); Num t, cur, av;
       if (b.high_rank) {
         for (size_t i = 0; i < b.dense_p.size(); i++) { mpfr_cp ap = a(off[j] + b.dense_p[i], 0);
-          for (size_t e = 0; e < M.e.size(); e++) { mpfr_mul(t.p(), &b.dense_A[i].e[e], ap, RN); mpfr_add(&M.e[e], &M.e[e], t.p(), RN); } }
+          for (size_t e = 0; e < M.e.size(); e++) { if (dense_skip_zeros && is_zero(&b.dense_A[i].e[e])) continue; mpfr_mul(t.p(), &b.dense_A[i].e[e], ap, RN); mpfr_add(&M.e[e], &M.e[e], t.p(), RN); } }
         continue;
       }
       for (int r = 0; r < b.m; r++) for (int s = 0; s <= r; s++) for (int e : b.rs[r][s]) {
@@ -439,8 +445,27 @@ struct Oracle {
       for (auto& b : c.blocks) {
         if (b.high_rank) {   // dense path :1089-1104
           int np = (int)b.dense_p.size(); int lim = dense_p_limit >= 0 ? std::min(np, dense_p_limit) : np;
-          for (int i = 0; i < lim; i++) { Mat T1, T2; solve_cho(T1, b.Xinv, b.dense_A[i]); gemm(T2, T1, b.Y);
+          if (dense_skip_zeros && b.dense_cols.empty()) {
+            b.dense_cols.resize(np); b.dense_nz.resize(np);
+            for (int i = 0; i < np; i++) { std::vector<char> used(b.n, 0);
+              for (int a = 0; a < b.n; a++) for (int c2 = 0; c2 < b.n; c2++) if (!is_zero(b.dense_A[i](a, c2))) { b.dense_nz[i].push_back({a, c2}); used[c2] = 1; }
+              for (int c2 = 0; c2 < b.n; c2++) if (used[c2]) b.dense_cols[i].push_back(c2); }
+          }
+          for (int i = 0; i < lim; i++) {
             int pi = b.dense_p[i];
+            if (dense_skip_zeros) {
+              const std::vector<int>& J = b.dense_cols[i]; const int nj = (int)J.size();
+              Mat Ap(b.n, nj), T1; for (int a = 0; a < b.n; a++) for (int k = 0; k < nj; k++) set(Ap(a, k), b.dense_A[i](a, J[k]));
+              solve_cho(T1, b.Xinv, Ap);                                    // the nonzero columns of X^-1 A_p
+#pragma omp parallel for schedule(dynamic, 1)
+              for (int q = 0; q < np; q++) { int qi = b.dense_p[q]; if (qi < pi) continue; Num t, u, acc, tot;
+                for (auto& ab : b.dense_nz[q]) { acc.v._exp = EXP_ZERO; acc.v._sign = 1;
+                  for (int k = 0; k < nj; k++) { mpfr_mul(u.p(), T1(ab.first, k), b.Y(J[k], ab.second), RN); mpfr_add(acc.p(), acc.p(), u.p(), RN); }   // (T1 Y)[a,b]
+                  mpfr_mul(t.p(), b.dense_A[q](ab.first, ab.second), acc.p(), RN); mpfr_add(tot.p(), tot.p(), t.p(), RN); }
+                mpfr_add(c.S(pi, qi), c.S(pi, qi), tot.p(), RN); }
+              continue;
+            }
+            Mat T1, T2; solve_cho(T1, b.Xinv, b.dense_A[i]); gemm(T2, T1, b.Y);
 #pragma omp parallel for schedule(dynamic, 1)
             for (int q = 0; q < np; q++) { int qi = b.dense_p[q]; if (qi < pi) continue; Num t; dot(t.p(), b.dense_A[q], T2); mpfr_add(c.S(pi, qi), c.S(pi, qi), t.p(), RN); } }
           continue;
@@ -675,6 +700,7 @@ int clrs_oracle_get_objectives(Oracle* h, void* d_obj, void* p_obj, void* gap) {
   to_wire(d_obj, h->d_obj.p()); to_wire(p_obj, h->p_obj.p()); to_wire(gap, h->gap.p()); return 0;
 }
 void clrs_oracle_set_dense_p_limit(Oracle* h, int32_t lim) { h->dense_p_limit = lim; }
+void clrs_oracle_set_dense_skip_zeros(Oracle* h, int32_t on) { h->dense_skip_zeros = on != 0; }
 // standalone kernels for parity tests
 int clrs_oracle_mp_gemm(Oracle*, int32_t M, int32_t N, int32_t K, const void* A, const void* B, void* C) {
   Mat a(M, K), b(K, N), c; mat_from_wire(a, A); mat_from_wire(b, B); gemm(c, a, b); mat_to_wire(C, c); return 0;

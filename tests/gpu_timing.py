@@ -1,0 +1,23 @@
+"""Ad-hoc GPU timing of a few workloads (not a test)."""
+import sys, time
+from fractions import Fraction
+sys.path.insert(0, ".")
+import clrs_b200
+from clrs_b200 import workloads, solvesdp, PHASES
+import numpy as np
+
+def run(name, sdp, iters=None, **kw):
+    t = time.time()
+    r = solvesdp(sdp, lib="device", duality_gap_threshold=1e-30, maxiterations=iters or 500, **kw)
+    dt = time.time() - t
+    ph = np.array([h["phase_ms"] for h in r.history[1:]])
+    print(f"{name}: {sdp.describe()}\n   {r}\n   wall {dt:.2f}s  {r.iterations/dt:.1f} it/s  phases(ms/it): " +
+          " ".join(f"{PHASES[i]}={ph[:, i].mean():.2f}" for i in range(12)), flush=True)
+
+which = sys.argv[1:] or ["poly", "del", "sp", "mc40"]
+if "poly" in which: run("polyopt20", workloads.polyopt_random(20))
+if "del" in which: run("delsarte16", workloads.delsarte(8, 16, Fraction(1, 2)))
+if "sp" in which: run("sphere(2,15)", workloads.sphere_packing(8, 15, [Fraction(1, 2), Fraction(1, 2)]))
+if "mc40" in which: run("maxcut40", workloads.maxcut(workloads.laplacian_random(40)))
+if "mc100" in which: run("maxcut100", workloads.maxcut(workloads.laplacian_random(100)), iters=5)
+if "mc300" in which: run("maxcut300", workloads.maxcut(workloads.laplacian_random(300)), iters=3)

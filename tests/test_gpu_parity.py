@@ -31,6 +31,18 @@ def rnd_matrix(rng, r, c, spread, zero_frac=0.05):
     return out
 
 
+def rand_wire(seed, shape, spread, zero_frac=0.02):
+    """Random wire matrix built directly in the wire format (fast, numpy)."""
+    rng = np.random.default_rng(seed)
+    out = wire.wire_zeros(shape, PREC)
+    limbs = rng.integers(0, 2 ** 63, size=shape + (4,), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape + (4,), dtype=np.uint64)
+    limbs[..., 3] |= np.uint64(1) << np.uint64(63)
+    out["limb"] = limbs
+    out["exp"] = rng.integers(-spread, spread + 1, size=shape)
+    out["sign"] = np.where(rng.random(shape) < zero_frac, 0, rng.choice([-1, 1], size=shape))
+    return out
+
+
 @pytest.fixture(scope="module")
 def tiny():
     sdp = workloads.maxcut(workloads.laplacian_cycle(3))
@@ -128,7 +140,10 @@ def test_first_iteration_intermediates_match_oracle():
             a = wire.from_wire(d.debug_get(what, j, l), PREC); b = wire.from_wire(o.debug_get(what, j, l), PREC)
             scale = max([abs(v) for v in b] + [mpmath.mpf(2) ** -200])
             err = max(abs(x - y) for x, y in zip(a, b))
-            assert err <= scale * mpmath.mpf(10) ** -55, (what, float(err / scale))
+            # X, Y contain the step lengths, which come from a Float64 eigenvalue (src/solver.jl:1659-1662):
+            # the reference itself only reproduces them to its Lanczos tolerance 1e-5
+            tol = mpmath.mpf(10) ** (-9 if what in ("X", "Y") else -55)
+            assert err <= scale * tol, (what, float(err / scale))
     d.close(); o.close()
 
 
@@ -151,3 +166,52 @@ def test_maxcut_complete_graph_dense_path():
     n = 12
     dev, _ = _compare(workloads.maxcut(workloads.laplacian_complete(n)))
     assert abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -25   # K_n: n^2/4
+
+
+def test_polyopt_config1_shape():
+    """BASELINE config 1: degree-40 polynomial, Chebyshev basis/samples, one rank-1 block of size 21."""
+    _compare(workloads.polyopt_random(20, seed=0))
+
+
+def test_delsarte_config3_d16():
+    dev, _ = _compare(workloads.delsarte(8, 16, Fraction(1, 2)))
+    assert abs(dev.p_obj - 240) < mpmath.mpf(10) ** -20
+
+
+def test_sphere_packing_two_radii_small():
+    """Config 5 family at small degree: several clusters, subblocks m=2, 50 free variables."""
+    sdp = workloads.sphere_packing(8, 7, [Fraction(1, 2), Fraction(1, 2)])
+    # at 256 bit this ill-conditioned family runs out of precision near gap 1e-28 in BOTH arms
+    # (the reference's own test uses prec=300, test/runtests_solver.jl:21); compare at 1e-20
+    dev = solvesdp(sdp, lib="device", duality_gap_threshold=1e-20)
+    ref = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-20)
+    assert dev.status == ref.status == "Optimal", (dev, ref)
+    assert abs(dev.p_obj - ref.p_obj) <= mpmath.mpf(10) ** -19 and abs(dev.d_obj - ref.d_obj) <= mpmath.mpf(10) ** -19
+    assert abs(dev.iterations - ref.iterations) <= 1
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 96), (130, 40, 100), (257, 100, 200)])
+def test_gemm_tcgen05_bitexact_vs_host_arithmetic(tiny, M, N, K):
+    A = rand_wire(M + N, (M, K), 20); B = rand_wire(K + N, (K, N), 20)
+    Cd, _ = tiny.mp_gemm(A, B, path=2)
+    Ch = wire.wire_zeros((M, N), PREC)
+    hostcheck().hc_gemm(M, N, K, A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), Ch.ctypes.data_as(C.c_void_p))
+    assert Cd.tobytes() == Ch.tobytes()
+
+
+@pytest.mark.parametrize("M,N,K,spread", [(300, 300, 300, 5), (512, 304, 300, 200), (1, 1, 1, 0), (129, 17, 33, 3), (256, 48, 3700, 10)])
+def test_gemm_tcgen05_equals_cuda_core_path(tiny, M, N, K, spread):
+    """Both GEMM paths compute the same exact integer slice-pair sums: identical bits."""
+    A = rand_wire(1, (M, K), spread); B = rand_wire(2, (K, N), spread)
+    C1, _ = tiny.mp_gemm(A, B, path=1)
+    C2, _ = tiny.mp_gemm(A, B, path=2)
+    assert C1.tobytes() == C2.tobytes()
+
+
+def test_maxcut_complete_graph_tensor_core_block():
+    """n = 130 > 128: the X/Y block products and the dense Schur path run on the tcgen05 kernel."""
+    n = 130
+    dev = solvesdp(workloads.maxcut(workloads.laplacian_complete(n)), lib="device", duality_gap_threshold=1e-30)
+    assert dev.status == "Optimal"
+    assert abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -24
+    assert abs(dev.d_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -24
