@@ -99,12 +99,22 @@ template <int NL> __global__ void k_vec_rhs(int n, mpn<NL>* dx, const mpn<NL>* d
 template <int NL> __global__ void k_set_diag(int n, mpn<NL>* A, int ld, const mpn<NL>* v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return; A[(int64_t)i * ld + i] = *v;
 }
-// S[plist[a], plist[b]] += T[a,b] for b >= a
+// S[plist[a], plist[b]] += T[b,a] for b >= a
 template <int NL> __global__ void k_scatter_upper(int np, const int32_t* plist, const mpn<NL>* T, mpn<NL>* S, int ldS) {
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (idx >= (int64_t)np * np) return;
   int a = (int)(idx / np), b = (int)(idx % np); if (b < a) return;
   int p = plist[a], q = plist[b]; mpn<NL>* dst = S + (int64_t)min(p, q) * ldS + max(p, q);
-  mpn<NL> o = *dst, t = T[idx]; mp_add(o, o, t); *dst = o;
+  mpn<NL> o = *dst, t = T[(int64_t)b * np + a]; mp_add(o, o, t); *dst = o;     // T holds the lower triangle T[q][p]
+}
+
+// pseudo-random multi-limb numbers for kernel benchmarks (splitmix-style hash)
+template <int NL> __global__ void k_fill_random(int64_t n, mpn<NL>* a, uint64_t seed, int spread) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1); mpn<NL> v;
+#pragma unroll
+    for (int k = 0; k < NL; k++) { z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31; v.l[k] = (uint32_t)z; z += 0x9E3779B97F4A7C15ull; }
+    v.l[NL - 1] |= 0x80000000u; v.exp = spread ? (int32_t)((z >> 8) % (2 * spread + 1)) - spread : 0; v.sign = (z & 1) ? 1 : -1; a[i] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -129,6 +139,7 @@ struct SolverBase {
   virtual void profile(int enable) = 0;
   virtual void profile_get(double* out) = 0;
   virtual double last_iteration_ms() = 0;
+  virtual int bench_gemm(int M, int N, int K, int reps, int path, double* out) = 0;
   size_t wire_size() const { return 16 + 8 * (size_t)((prec + 63) / 64); }
 };
 
@@ -209,21 +220,24 @@ template <int NL> struct Solver : SolverBase {
     if (a0 != 0 || b0 != 0) throw CudaError("gemm_tc: panel offsets are not supported");
     const int ntn = (N + 127) / 128; int BN = ((N + ntn - 1) / ntn + 15) & ~15; if (BN > 128) BN = 128;
     const int Npitch = (N + 15) & ~15;
-    const size_t outs = (size_t)batch * M * Npitch;
-    if (outs > tc_cap) { if (tc_bytes) CK(cudaFreeAsync(tc_bytes, st)); if (tc_top) CK(cudaFreeAsync(tc_top, st)); tc_cap = outs;
-      CK(cudaMallocAsync((void**)&tc_bytes, tc_cap * NS, st)); CK(cudaMallocAsync((void**)&tc_top, tc_cap * sizeof(int32_t), st)); }
     CUtensorMap mA = make_map(A, tc::BM), mB = make_map(B, BN);
-    const int KMAX = 3584; int cur_mode = mode; const num* curD = D; int cur_ldd = ldd; int64_t cur_dbs = d_bs;
-    for (int k0 = 0; k0 < A.Kp; k0 += KMAX) {
-      tc::Args a; a.M = M; a.N = N; a.Kp = std::min(KMAX, A.Kp - k0); a.k0 = k0; a.BN = BN; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch; a.batch = batch;
-      a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = lower_only;
-      dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, batch);
-      nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
-      const int64_t tot_ = (int64_t)batch * M * N;
-      nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, curD, cur_ldd, cur_dbs, cur_mode, lower_only);
-      // later K ranges accumulate onto C
-      cur_mode = (mode == 1 || mode == 3) ? 1 : 2; curD = C; cur_ldd = ldc; cur_dbs = c_bs;
-    }
+    // K longer than the int32 headroom (35 slices * K * 2^14 < 2^31), or few tiles with a long K: split K over
+    // blockIdx.z (partial results summed in k_tc_recombine), sized to fill whole waves of 148 CTAs
+    const int KMAX = 3584; int tiles = 0;
+    for (int by = 0; by < (M + tc::BM - 1) / tc::BM; by++) for (int bx = 0; bx < (N + BN - 1) / BN; bx++) if (!lower_only || bx * BN <= by * tc::BM + tc::BM - 1) tiles++;
+    int nch = (A.Kp + KMAX - 1) / KMAX;
+    if (batch == 1 && tiles < 148 && A.Kp >= 1024) { const int waves = (tiles * nch + 147) / 148; nch = std::max(nch, std::min(waves * 148 / tiles, A.Kp / 512)); }
+    if (nch > 1 && batch != 1) throw CudaError("gemm_tc: split-K with a batch is not supported");
+    int kch = ((A.Kp + nch - 1) / nch + 127) & ~127; nch = (A.Kp + kch - 1) / kch;
+    const size_t outs2 = (size_t)std::max(batch, nch) * M * Npitch;
+    if (outs2 > tc_cap) { if (tc_bytes) CK(cudaFreeAsync(tc_bytes, st)); if (tc_top) CK(cudaFreeAsync(tc_top, st)); tc_cap = outs2;
+      CK(cudaMallocAsync((void**)&tc_bytes, tc_cap * NS, st)); CK(cudaMallocAsync((void**)&tc_top, tc_cap * sizeof(int32_t), st)); }
+    tc::Args a; a.M = M; a.N = N; a.Kp = A.Kp; a.k0 = 0; a.BN = BN; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch;
+    a.batch = nch > 1 ? nch : batch; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = lower_only; a.kz_stride = nch > 1 ? kch : 0; a.Kp_total = A.Kp;
+    dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, a.batch);
+    nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
+    const int64_t tot_ = (int64_t)batch * M * N;
+    nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1);
   }
   // ---- optional per-launch GEMM profile (bench.py roofline) ------------------------------------
   bool prof_on = false; cudaEvent_t pe0 = nullptr, pe1 = nullptr; double prof_ms[2] = {0, 0}, prof_flops[2] = {0, 0}; long prof_n[2] = {0, 0};
@@ -573,7 +587,7 @@ template <int NL> struct Solver : SolverBase {
     gemm(b0.T1S, 0, b0.YS, 0, np * n, n, b0.T2, n);
     // S[p,q] += sum_ab T2_p[ab] A_q[ab]
     { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true, b0.AallV.lay); }
-    gemm(b0.T2V, 0, b0.AallV, 0, np, np, b0.Sd, np);
+    gemm(b0.AallV, 0, b0.T2V, 0, np, np, b0.Sd, np, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);          // Sd[q][p], q >= p only
     nlaunch++, k_scatter_upper<NL><<<(unsigned)(((int64_t)np * np + 127) / 128), 128, 0, st>>>(np, b0.d_plist, b0.Sd, c0.S, c0.P);
   }
   void decomposition(int e0) {
@@ -743,6 +757,33 @@ template <int NL> struct Solver : SolverBase {
   void profile(int enable) override { prof_on = enable != 0; for (int i = 0; i < 2; i++) { prof_ms[i] = 0; prof_flops[i] = 0; prof_n[i] = 0; } nlaunch = 0; }
   void profile_get(double* o) override { o[0] = prof_ms[0]; o[1] = prof_flops[0]; o[2] = (double)prof_n[0]; o[3] = prof_ms[1]; o[4] = prof_flops[1]; o[5] = (double)prof_n[1]; o[6] = (double)nlaunch; }
   double last_iteration_ms() override { return last_ms; }
+  // kernel-only timing of C = A*B on device-generated operands: out = {split ms, gemm ms per rep (kernel + recombine), kernel-only ms per rep}
+  int bench_gemm(int M, int N_, int K, int reps, int path, double* out) override {
+    num* dA = dalloc<num>((size_t)M * K); num* dB = dalloc<num>((size_t)K * N_); num* dC = dalloc<num>((size_t)M * N_);
+    nlaunch++, k_fill_random<NL><<<grid_for((int64_t)M * K), 256, 0, st>>>((int64_t)M * K, dA, 1234, 4);
+    nlaunch++, k_fill_random<NL><<<grid_for((int64_t)K * N_), 256, 0, st>>>((int64_t)K * N_, dB, 99, 4);
+    const int lay = path == 2 ? 1 : (path == 1 ? 0 : (use_tc(M, N_, K) ? 1 : 0));
+    Sliced sa, sb; cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    CK(cudaEventRecord(e0, st)); split_rows(sa, dA, K, M, K, lay); split_cols(sb, dB, N_, K, N_, lay); CK(cudaEventRecord(e1, st));
+    gemm(sa, 0, sb, 0, M, N_, dC, N_);                      // warm-up
+    CK(cudaEventRecord(e1, st));
+    for (int r = 0; r < reps; r++) gemm(sa, 0, sb, 0, M, N_, dC, N_);
+    CK(cudaEventRecord(e2, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+    float t01 = 0, t12 = 0; cudaEventElapsedTime(&t01, e0, e1); cudaEventElapsedTime(&t12, e1, e2);
+    out[0] = t01; out[1] = t12 / reps; out[2] = 0;
+    if (lay == 1) {      // kernel alone
+      CUtensorMap mA = make_map(sa, tc::BM); const int ntn = (N_ + 127) / 128; int BN = ((N_ + ntn - 1) / ntn + 15) & ~15; if (BN > 128) BN = 128; CUtensorMap mB = make_map(sb, BN);
+      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(3584, sa.Kp); a.k0 = 0; a.BN = BN; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp;
+      dim3 grid((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1);
+      CK(cudaEventRecord(e1, st));
+      for (int r = 0; r < reps; r++) nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
+      CK(cudaEventRecord(e2, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+      cudaEventElapsedTime(&t12, e1, e2); out[2] = t12 / reps;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (sa.sl) cudaFree(sa.sl); if (sa.E) cudaFree(sa.E); if (sa.planes) cudaFree(sa.planes); if (sb.sl) cudaFree(sb.sl); if (sb.E) cudaFree(sb.E); if (sb.planes) cudaFree(sb.planes);
+    return 0;
+  }
   int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) override {
     std::string w(what); const num* src = nullptr; int64_t n = 0;
     if (w == "S") { src = cl[j].S; n = (int64_t)cl[j].P * cl[j].P; } else if (w == "LinvB") { src = cl[j].LinvB; n = (int64_t)cl[j].P * N; }
@@ -796,5 +837,6 @@ int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L) { GUARD(
 void clrs_profile(clrs_handle* h, int32_t enable) { h->s->profile(enable); }
 void clrs_profile_get(clrs_handle* h, double* out7) { h->s->profile_get(out7); }
 double clrs_last_iteration_ms(clrs_handle* h) { return h->s->last_iteration_ms(); }
+int clrs_bench_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, int32_t reps, int32_t path, double* out3) { GUARD(h, return h->s->bench_gemm(M, N, K, reps, path, out3);) }
 int64_t clrs_debug_get(clrs_handle* h, const char* what, int32_t j, int32_t l, void* out, int64_t cap) { try { return h->s->debug_get(what, j, l, out, cap); } catch (const std::exception& e) { h->err = e.what(); return -1; } }
 }

@@ -84,6 +84,8 @@ struct Args {
   uint8_t* obytes;         // [NS][batch][M][Npitch]
   int32_t* otop;           // [batch][M][Npitch]
   int lower_only;
+  int kz_stride;           // > 0: blockIdx.z selects the K range [z*kz_stride, ...) instead of a batch entry (split-K, partial results per z)
+  int Kp_total;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -101,7 +103,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (a.lower_only && n0 > m0 + BM - 1) return;
   const int NS = a.NS, BN = a.BN;
   const int ngroups = (NS + GROUP - 1) / GROUP;
-  const int nkc = (a.Kp + KC - 1) / KC;
+  const int kbase = a.kz_stride > 0 ? a.k0 + bz * a.kz_stride : a.k0;
+  const int Kp = a.kz_stride > 0 ? min(a.kz_stride, a.Kp_total - bz * a.kz_stride) : a.Kp;
+  const int nkc = (Kp + KC - 1) / KC;
+  const int brow_z = a.kz_stride > 0 ? 0 : bz;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -123,12 +128,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
       uint32_t L = 0;
-      const int arow = bz * a.a_bvec + m0, brow = bz * a.b_bvec + n0;
+      const int arow = brow_z * a.a_bvec + m0, brow = brow_z * a.b_bvec + n0;
       const uint32_t abytes = BM * KC, bbytes = (uint32_t)BN * KC;
       for (int g = ngroups - 1; g >= 0; g--) {
         const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
         for (int kc = 0; kc < nkc; kc++) {
-          const int kcoord = a.k0 + kc * KC;
+          const int kcoord = kbase + kc * KC;
           auto load = [&](bool isA, int slice) {
             const uint32_t slot = L % NSLOT, use = L / NSLOT;
             mbar_wait(&empty[slot], (use & 1) ^ 1);
@@ -151,24 +156,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const bool carry_in = (g != ngroups - 1);
         if (carry_in) { mbar_wait(tmem_empty, epi_parity); epi_parity ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
         for (int kc = 0; kc < nkc; kc++) {
-          const int ninstr = min(KC / 32, (a.Kp - kc * KC) / 32);
+          const int ninstr = min(KC / 32, (Kp - kc * KC) / 32);
+          int b_ready = -1;                                               // highest B load of this K chunk already waited for
           for (int i = 0; i <= d1; i++) {
             const uint32_t LA = Lbase + (uint32_t)(min(i + w, d1) + 1 + i);
             const uint32_t slotA = LA % NSLOT;
-            mbar_wait(&full[slotA], (LA / NSLOT) & 1);
-            const uint64_t descA = make_desc(smem_u32(ring + slotA * SLOT_BYTES));
             const int sp_hi = min(d1, i + w);
+            for (int sp = b_ready + 1; sp <= sp_hi; sp++) { const uint32_t LB = Lbase + (uint32_t)(sp < w ? sp : 2 * sp - w); mbar_wait(&full[LB % NSLOT], (LB / NSLOT) & 1); }
+            b_ready = sp_hi;
+            mbar_wait(&full[slotA], (LA / NSLOT) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t descA = make_desc(smem_u32(ring + slotA * SLOT_BYTES));
+            const bool first = (kc == 0 && i == 0);
             for (int sp = i; sp <= sp_hi; sp++) {
               const uint32_t LB = Lbase + (uint32_t)(sp < w ? sp : 2 * sp - w);
-              const uint32_t slotB = LB % NSLOT;
-              mbar_wait(&full[slotB], (LB / NSLOT) & 1);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint64_t descB = make_desc(smem_u32(ring + slotB * SLOT_BYTES));
+              const uint64_t descB = make_desc(smem_u32(ring + (LB % NSLOT) * SLOT_BYTES));
               const int acc = (i + (d1 - sp)) - d0;                       // diagonal index inside the group
               const uint32_t tcol = tmem_base + (uint32_t)(acc * BN);
-              for (int kk = 0; kk < ninstr; kk++) {
-                const uint32_t accumulate = (kc == 0 && i == 0 && kk == 0) ? ((carry_in && acc == w) ? 1u : 0u) : 1u;
-                umma_i8(tcol, descA + (uint64_t)(2 * kk), descB + (uint64_t)(2 * kk), idesc, accumulate);
+              const uint32_t acc0 = first ? ((carry_in && acc == w) ? 1u : 0u) : 1u;
+              if (ninstr == 4) {
+                umma_i8(tcol, descA, descB, idesc, acc0); umma_i8(tcol, descA + 2, descB + 2, idesc, 1u);
+                umma_i8(tcol, descA + 4, descB + 4, idesc, 1u); umma_i8(tcol, descA + 6, descB + 6, idesc, 1u);
+              } else {
+                for (int kk = 0; kk < ninstr; kk++) umma_i8(tcol, descA + (uint64_t)(2 * kk), descB + (uint64_t)(2 * kk), idesc, kk == 0 ? acc0 : 1u);
               }
             }
             umma_commit(&empty[slotA]);                                   // A_i is done after this step
@@ -263,20 +273,27 @@ template <int NL> __global__ void k_split_tc(VecView v, const int32_t* E, int Kp
 // byte planes + top -> multi-limb C (op with D), one thread per output
 template <int NL> __global__ void k_tc_recombine(int M, int N, int Npitch, int batch, const uint8_t* obytes, const int32_t* otop,
                                                  const int32_t* EA, int64_t a_bvec, const int32_t* EB, int64_t b_bvec,
-                                                 mpn<NL>* C, int ldc, int64_t c_bs, const mpn<NL>* D, int ldd, int64_t d_bs, int mode, int lower_only) {
+                                                 mpn<NL>* C, int ldc, int64_t c_bs, const mpn<NL>* D, int ldd, int64_t d_bs, int mode, int lower_only, int nsum) {
   constexpr int NS = I8Cfg<NL>::NS;
+  // nsum > 1: the `batch` planes are split-K partial results of ONE product and are summed here
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)batch * M * N) return;
+  const int nb = nsum > 1 ? 1 : batch;
+  if (idx >= (int64_t)nb * M * N) return;
   const int n = (int)(idx % N), m = (int)((idx / N) % M), bz = (int)(idx / ((int64_t)N * M));
   if (lower_only && n > m) return;
-  const size_t plane = (size_t)batch * M * Npitch, off = ((size_t)bz * M + m) * Npitch + n;
-  uint32_t dg[NS];
-#pragma unroll
-  for (int s = 0; s < NS; s++) dg[s] = obytes[(size_t)s * plane + off];
-  const int64_t top = (int64_t)otop[off] * 256 + (int64_t)dg[0];
+  const size_t plane = (size_t)batch * M * Npitch;
   const int32_t ea = EA[(int64_t)bz * a_bvec + m], eb = EB[(int64_t)bz * b_bvec + n];
-  mpn<NL> r;
-  if (ea == I8_EXP_NONE || eb == I8_EXP_NONE) mp_zero(r); else i8_recombine<NL>(r, top, dg, ea + eb);
+  mpn<NL> r; mp_zero(r);
+  for (int z = 0; z < (nsum > 1 ? nsum : 1); z++) {
+    const size_t off = ((size_t)(nsum > 1 ? z : bz) * M + m) * Npitch + n;
+    uint32_t dg[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) dg[s] = obytes[(size_t)s * plane + off];
+    const int64_t top = (int64_t)otop[off] * 256 + (int64_t)dg[0];
+    mpn<NL> t;
+    if (ea == I8_EXP_NONE || eb == I8_EXP_NONE) mp_zero(t); else i8_recombine<NL>(t, top, dg, ea + eb);
+    if (z == 0) r = t; else mp_add(r, r, t);
+  }
   if (mode == 1 || mode == 2) { mpn<NL> d = D[(int64_t)bz * d_bs + (int64_t)m * ldd + n]; if (mode == 1) mp_sub(r, d, r); else mp_add(r, d, r); }
   else if (mode == 3) r.sign = -r.sign;
   C[(int64_t)bz * c_bs + (int64_t)m * ldc + n] = r;

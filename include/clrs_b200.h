@@ -206,6 +206,9 @@ void clrs_profile(clrs_handle* h, int32_t enable);
 /* out7 = { ms, mp_flops, launches } of the CUDA-core int8 path, the same three
  * for the tcgen05 path, then the number of kernel launches since clrs_profile. */
 void clrs_profile_get(clrs_handle* h, double* out7);
+/* Kernel benchmark of C = A*B (M x K times K x N) on device-generated operands.
+ * out3 = { split ms, ms per product (kernel + recombine), ms per tcgen05 kernel launch alone }. */
+int clrs_bench_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, int32_t reps, int32_t path, double* out3);
 /* device time of the last clrs_iterate (CUDA events on the library's stream), ms */
 double clrs_last_iteration_ms(clrs_handle* h);
 

@@ -278,6 +278,9 @@ struct Oracle {
   // skipped operation is an exact `x + 0*y` (tests/test_oracle.py checks S bit for bit); it only
   // makes full-size MAX-CUT instances (A_p = E_pp stored dense) affordable on the CPU.
   bool dense_skip_zeros = false;
+  // bench.py reference arm: rows p < sample_limit of the dense Schur path run the plain dense algorithm
+  // (timed in t_plain), the others the bit-identical zero-skipping one (timed in t_skip).
+  int sample_limit = -1; double t_plain = 0, t_skip = 0; int t_np = 0;
 
   template <class F> void for_blocks(F f) { for (auto& c : cl) for (auto& b : c.blocks) f(c, b); }
 
@@ -451,9 +454,14 @@ struct Oracle {
               for (int a = 0; a < b.n; a++) for (int c2 = 0; c2 < b.n; c2++) if (!is_zero(b.dense_A[i](a, c2))) { b.dense_nz[i].push_back({a, c2}); used[c2] = 1; }
               for (int c2 = 0; c2 < b.n; c2++) if (used[c2]) b.dense_cols[i].push_back(c2); }
           }
+          t_np = np;
           for (int i = 0; i < lim; i++) {
             int pi = b.dense_p[i];
-            if (dense_skip_zeros) {
+            auto tt0 = std::chrono::steady_clock::now();
+            struct Tm { double* dst; std::chrono::steady_clock::time_point t0; ~Tm() { *dst += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } };
+            const bool skip = dense_skip_zeros && !(sample_limit >= 0 && i < sample_limit);
+            Tm tm{skip ? &t_skip : &t_plain, tt0};
+            if (skip) {
               const std::vector<int>& J = b.dense_cols[i]; const int nj = (int)J.size();
               Mat Ap(b.n, nj), T1; for (int a = 0; a < b.n; a++) for (int k = 0; k < nj; k++) set(Ap(a, k), b.dense_A[i](a, J[k]));
               solve_cho(T1, b.Xinv, Ap);                                    // the nonzero columns of X^-1 A_p
@@ -701,6 +709,8 @@ int clrs_oracle_get_objectives(Oracle* h, void* d_obj, void* p_obj, void* gap) {
 }
 void clrs_oracle_set_dense_p_limit(Oracle* h, int32_t lim) { h->dense_p_limit = lim; }
 void clrs_oracle_set_dense_skip_zeros(Oracle* h, int32_t on) { h->dense_skip_zeros = on != 0; }
+void clrs_oracle_set_sample_limit(Oracle* h, int32_t lim) { h->sample_limit = lim; h->t_plain = h->t_skip = 0; }
+void clrs_oracle_get_sample_times(Oracle* h, double* out3) { out3[0] = h->t_plain; out3[1] = h->t_skip; out3[2] = h->t_np; h->t_plain = h->t_skip = 0; }
 // standalone kernels for parity tests
 int clrs_oracle_mp_gemm(Oracle*, int32_t M, int32_t N, int32_t K, const void* A, const void* B, void* C) {
   Mat a(M, K), b(K, N), c; mat_from_wire(a, A); mat_from_wire(b, B); gemm(c, a, b); mat_to_wire(C, c); return 0;

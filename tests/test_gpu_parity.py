@@ -199,13 +199,26 @@ def test_gemm_tcgen05_bitexact_vs_host_arithmetic(tiny, M, N, K):
     assert Cd.tobytes() == Ch.tobytes()
 
 
-@pytest.mark.parametrize("M,N,K,spread", [(300, 300, 300, 5), (512, 304, 300, 200), (1, 1, 1, 0), (129, 17, 33, 3), (256, 48, 3700, 10)])
+@pytest.mark.parametrize("M,N,K,spread", [(300, 300, 300, 5), (512, 304, 300, 200), (1, 1, 1, 0), (129, 17, 33, 3), (200, 64, 896, 10)])
 def test_gemm_tcgen05_equals_cuda_core_path(tiny, M, N, K, spread):
     """Both GEMM paths compute the same exact integer slice-pair sums: identical bits."""
     A = rand_wire(1, (M, K), spread); B = rand_wire(2, (K, N), spread)
     C1, _ = tiny.mp_gemm(A, B, path=1)
     C2, _ = tiny.mp_gemm(A, B, path=2)
     assert C1.tobytes() == C2.tobytes()
+
+
+def test_gemm_tcgen05_k_split(tiny):
+    """K > 3584 is processed in K ranges (int32 headroom) whose truncated results are added:
+    equal to the single-pass CUDA-core result up to the rounding of those additions."""
+    M, N, K = 256, 48, 3700
+    A = rand_wire(1, (M, K), 10); B = rand_wire(2, (K, N), 10)
+    C1, _ = tiny.mp_gemm(A, B, path=1)
+    C2, _ = tiny.mp_gemm(A, B, path=2)
+    with mpmath.workprec(400):
+        a, b = wire.from_wire(C1, PREC).reshape(-1), wire.from_wire(C2, PREC).reshape(-1)
+        scale = max(abs(v) for v in a)
+        assert max(abs(x - y) for x, y in zip(a, b)) <= scale * mpmath.mpf(2) ** -245
 
 
 def test_maxcut_complete_graph_tensor_core_block():
