@@ -1,0 +1,49 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/clrs_b200.h declares, and
+fails loudly (no CPU fallback) when asked to compute without an sm_100 device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import clrs_b200
+from clrs_b200 import workloads, Options
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "clrs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(clrs_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    lib = clrs_b200.load_library("device")
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_options_struct_matches_header_layout():
+    lib = clrs_b200.load_library("device")
+    o = Options()
+    lib.clrs_default_options(C.byref(o))
+    assert o.prec == 256 and o.gamma == 0.9 and o.beta_infeasible == 0.3 and o.beta_feasible == 0.1
+    assert o.omega_p == 1e10 and o.duality_gap_threshold == 1e-15 and o.step_length_threshold == 1e-7 and o.safe_step == 1
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_a_gpu():
+    with pytest.raises(RuntimeError) as e:
+        clrs_b200.Solver(workloads.maxcut(workloads.laplacian_cycle(3)), lib="device")
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)

