@@ -174,8 +174,10 @@ template <int NL> struct Solver : SolverBase {
     nlaunch++, k_vec_exp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 255) / 256), 256, 0, st>>>(v, s.E);
     if (lay == 0) { int64_t tot_ = (int64_t)v.nvec * s.K4;
       nlaunch++, k_split<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0); }
-    else { int64_t tot_ = (int64_t)v.nvec * (s.Kp / 4);
-      nlaunch++, k_split_tc<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes, kfast ? 1 : 0); }
+    else if (kfast) { int64_t tot_ = (int64_t)v.nvec * (s.Kp / 4);
+      nlaunch++, k_split_tc<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes, 1); }
+    else { dim3 grid((v.nvec + 31) / 32, s.Kp / 32);
+      nlaunch++, k_split_tc_t<NL><<<grid, 256, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes); }
   }
   void split_rows(Sliced& s, const num* A, int lda, int M, int K, int lay = 0) { split(s, rows_view(A, lda, M, K), true, lay); }
   void split_cols(Sliced& s, const num* B, int ldb, int K, int N, int lay = 0) { split(s, cols_view(B, ldb, K, N), false, lay); }
@@ -233,7 +235,7 @@ template <int NL> struct Solver : SolverBase {
     if (outs2 > tc_cap) { if (tc_bytes) CK(cudaFreeAsync(tc_bytes, st)); if (tc_top) CK(cudaFreeAsync(tc_top, st)); tc_cap = outs2;
       CK(cudaMallocAsync((void**)&tc_bytes, tc_cap * NS, st)); CK(cudaMallocAsync((void**)&tc_top, tc_cap * sizeof(int32_t), st)); }
     tc::Args a; a.M = M; a.N = N; a.Kp = A.Kp; a.k0 = 0; a.BN = BN; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch;
-    a.batch = nch > 1 ? nch : batch; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = lower_only; a.kz_stride = nch > 1 ? kch : 0; a.Kp_total = A.Kp;
+    a.batch = nch > 1 ? nch : batch; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = lower_only; a.kz_stride = nch > 1 ? kch : 0; a.Kp_total = A.Kp; a.dbg = nullptr;
     dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, a.batch);
     nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
     const int64_t tot_ = (int64_t)batch * M * N;
@@ -272,7 +274,7 @@ template <int NL> struct Solver : SolverBase {
     if (ldm == n) zero(Minv, (int64_t)n * n); else for (int r = 0; r < n; r++) zero(Minv + (int64_t)r * ldm, n);
     for (int k0 = 0; k0 < n; k0 += 32) {
       const int nb = std::min(32, n - k0), rem = n - k0 - nb;
-      nlaunch++, k_potrf_diag<NL><<<1, 256, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code);
+      nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code);
       if (rem > 0) {
         num* A21 = A + (int64_t)(k0 + nb) * lda + k0; num* A22 = A + (int64_t)(k0 + nb) * lda + k0 + nb;
         split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);
@@ -773,12 +775,14 @@ template <int NL> struct Solver : SolverBase {
     out[0] = t01; out[1] = t12 / reps; out[2] = 0;
     if (lay == 1) {      // kernel alone
       CUtensorMap mA = make_map(sa, tc::BM); const int ntn = (N_ + 127) / 128; int BN = ((N_ + ntn - 1) / ntn + 15) & ~15; if (BN > 128) BN = 128; CUtensorMap mB = make_map(sb, BN);
-      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(3584, sa.Kp); a.k0 = 0; a.BN = BN; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp;
+      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(3584, sa.Kp); a.k0 = 0; a.BN = BN; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp; a.dbg = nullptr;
       dim3 grid((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1);
       CK(cudaEventRecord(e1, st));
       for (int r = 0; r < reps; r++) nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
       CK(cudaEventRecord(e2, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
       cudaEventElapsedTime(&t12, e1, e2); out[2] = t12 / reps;
+      if (getenv("CLRS_TC_TIMELINE")) { long long* dd = dalloc<long long>(128); a.dbg = dd; tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a); long long hh[128]; CK(cudaMemcpyAsync(hh, dd, sizeof(hh), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        fprintf(stderr, "group: wait_epi  mma_issue  | epilogue: wait_mma  work   (cycles, CTA 0)\n"); for (int gg = 0; gg < (NS + 3) / 4; gg++) { long long* q = hh + gg * 8; fprintf(stderr, "%2d: %8lld %8lld | %8lld %8lld   t0=%lld\n", gg, q[1] - q[0], q[2] - q[1], q[4] - q[3], q[5] - q[4], q[0] - hh[0]); } }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     if (sa.sl) cudaFree(sa.sl); if (sa.E) cudaFree(sa.E); if (sa.planes) cudaFree(sa.planes); if (sb.sl) cudaFree(sb.sl); if (sb.E) cudaFree(sb.E); if (sb.planes) cudaFree(sb.planes);

@@ -9,8 +9,8 @@
 // a time, least significant first:
 //
 //   group g = diagonals d0..d1 (d0 = 4g): four int32 accumulators of BN columns in
-//   TMEM.  For every 128-byte K chunk the slices stream through one shared-memory
-//   ring:  A_0..A_d1  and  B_d1..B_0 ; A_i meets the window B_{d0-i..d1-i}, so each
+//   TMEM.  For every 128-byte K chunk the slices stream through two shared-memory
+//   rings:  A_0..A_d1  and  B_d1..B_0 ; A_i meets the window B_{d0-i..d1-i}, so each
 //   operand chunk is loaded once per group and used by up to four MMAs.
 //   Epilogue (4 warps, one TMEM lane = one output row per thread): low byte of
 //   each diagonal (plus carry) goes to a byte plane in HBM, the carry moves up;
@@ -32,7 +32,8 @@ namespace tc {
 constexpr int BM = 128;            // rows per tile = TMEM lanes
 constexpr int KC = 128;            // bytes of K per ring slot (one 128B swizzle atom row)
 constexpr int SLOT_BYTES = BM * KC;   // 16 KiB
-constexpr int NSLOT = 12;
+constexpr int NA = 4, NB = 8;      // ring slots for left / right operand chunks (powers of two)
+constexpr int NSLOT = NA + NB;
 constexpr int GROUP = 4;           // diagonals resident in TMEM
 constexpr int NTHREADS = 192;      // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
 constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + 1024 /*align*/ + 512 /*barriers*/;
@@ -86,15 +87,20 @@ struct Args {
   int lower_only;
   int kz_stride;           // > 0: blockIdx.z selects the K range [z*kz_stride, ...) instead of a batch entry (split-K, partial results per z)
   int Kp_total;
+  long long* dbg;          // optional timeline of CTA (0,0,0): clock64 stamps (kernel tuning only)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* ring = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(ring + NSLOT * SLOT_BYTES);
-  uint64_t* empty = full + NSLOT;
-  uint64_t* tmem_full = empty + NSLOT;
+  unsigned char* ringA = ring;
+  unsigned char* ringB = ring + NA * SLOT_BYTES;
+  uint64_t* full_a = (uint64_t*)(ring + NSLOT * SLOT_BYTES);
+  uint64_t* full_b = full_a + NA;
+  uint64_t* empty_a = full_b + NB;
+  uint64_t* empty_b = empty_a + NA;
+  uint64_t* tmem_full = empty_b + NB;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
 
@@ -109,7 +115,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int brow_z = a.kz_stride > 0 ? 0 : bz;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSLOT; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NA; s++) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < NB; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     mbar_init(tmem_full, 1); mbar_init(tmem_empty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -127,67 +134,81 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
-      uint32_t L = 0;
+      uint32_t ca = 0, cb = 0;                                  // running load counters of the two rings
       const int arow = brow_z * a.a_bvec + m0, brow = brow_z * a.b_bvec + n0;
       const uint32_t abytes = BM * KC, bbytes = (uint32_t)BN * KC;
       for (int g = ngroups - 1; g >= 0; g--) {
         const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
         for (int kc = 0; kc < nkc; kc++) {
           const int kcoord = kbase + kc * KC;
-          auto load = [&](bool isA, int slice) {
-            const uint32_t slot = L % NSLOT, use = L / NSLOT;
-            mbar_wait(&empty[slot], (use & 1) ^ 1);
-            mbar_expect_tx(&full[slot], isA ? abytes : bbytes);
-            tma_load_3d(ring + slot * SLOT_BYTES, isA ? &tmA : &tmB, &full[slot], kcoord, isA ? arow : brow, slice);
-            L++;
+          auto loadB = [&](int slice) {
+            const uint32_t slot = cb & (NB - 1);
+            mbar_wait(&empty_b[slot], ((cb >> 3) & 1) ^ 1);
+            mbar_expect_tx(&full_b[slot], bbytes);
+            tma_load_3d(ringB + slot * SLOT_BYTES, &tmB, &full_b[slot], kcoord, brow, slice);
+            cb++;
           };
-          for (int sp = 0; sp < w; sp++) load(false, d1 - sp);
-          for (int i = 0; i <= d1; i++) { if (i + w <= d1) load(false, d1 - (i + w)); load(true, i); }
+          auto loadA = [&](int slice) {
+            const uint32_t slot = ca & (NA - 1);
+            mbar_wait(&empty_a[slot], ((ca >> 2) & 1) ^ 1);
+            mbar_expect_tx(&full_a[slot], abytes);
+            tma_load_3d(ringA + slot * SLOT_BYTES, &tmA, &full_a[slot], kcoord, arow, slice);
+            ca++;
+          };
+          for (int sp = 0; sp < w; sp++) loadB(d1 - sp);           // B_{s'} holds slice d1 - s'
+          for (int i = 0; i <= d1; i++) { if (i + w <= d1) loadB(d1 - (i + w)); loadA(i); }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      uint32_t Lbase = 0; uint32_t epi_parity = 0;
-      for (int g = ngroups - 1; g >= 0; g--) {
-        const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
-        const bool carry_in = (g != ngroups - 1);
-        if (carry_in) { mbar_wait(tmem_empty, epi_parity); epi_parity ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-        for (int kc = 0; kc < nkc; kc++) {
-          const int ninstr = min(KC / 32, (Kp - kc * KC) / 32);
-          int b_ready = -1;                                               // highest B load of this K chunk already waited for
-          for (int i = 0; i <= d1; i++) {
-            const uint32_t LA = Lbase + (uint32_t)(min(i + w, d1) + 1 + i);
-            const uint32_t slotA = LA % NSLOT;
-            const int sp_hi = min(d1, i + w);
-            for (int sp = b_ready + 1; sp <= sp_hi; sp++) { const uint32_t LB = Lbase + (uint32_t)(sp < w ? sp : 2 * sp - w); mbar_wait(&full[LB % NSLOT], (LB / NSLOT) & 1); }
-            b_ready = sp_hi;
-            mbar_wait(&full[slotA], (LA / NSLOT) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t descA = make_desc(smem_u32(ring + slotA * SLOT_BYTES));
-            const bool first = (kc == 0 && i == 0);
-            for (int sp = i; sp <= sp_hi; sp++) {
-              const uint32_t LB = Lbase + (uint32_t)(sp < w ? sp : 2 * sp - w);
-              const uint64_t descB = make_desc(smem_u32(ring + (LB % NSLOT) * SLOT_BYTES));
-              const int acc = (i + (d1 - sp)) - d0;                       // diagonal index inside the group
-              const uint32_t tcol = tmem_base + (uint32_t)(acc * BN);
-              const uint32_t acc0 = first ? ((carry_in && acc == w) ? 1u : 0u) : 1u;
+    // The whole warp walks the (warp-uniform) schedule; one elected lane issues the MMAs and commits.
+    static_assert(NA == 4 && NB == 8, "ring phase shifts below assume NA = 4, NB = 8");
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint64_t descA0 = make_desc(smem_u32(ringA)), descB0 = make_desc(smem_u32(ringB));   // slot s: + s * (SLOT_BYTES >> 4)
+    const bool leader = (lane == 0);
+    const bool dbgon = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    uint32_t ca = 0, cbase = 0; uint32_t epi_parity = 0;
+    for (int g = ngroups - 1; g >= 0; g--) {
+      const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
+      const bool carry_in = (g != ngroups - 1);
+      if (dbgon && leader) a.dbg[(ngroups - 1 - g) * 8 + 0] = clock64();
+      if (carry_in) { mbar_wait(tmem_empty, epi_parity); epi_parity ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+      if (dbgon && leader) a.dbg[(ngroups - 1 - g) * 8 + 1] = clock64();
+      const uint32_t tcol_top = tmem_base + (uint32_t)(w * BN);            // accumulator of the pair (i, B_{s'=i}), diagonal d1
+      for (int kc = 0; kc < nkc; kc++) {
+        const int ninstr = min(KC / 32, (Kp - kc * KC) / 32);
+        uint32_t cbw = cbase;                                           // next B load (of this K chunk) not yet waited for
+        for (int i = 0; i <= d1; i++) {
+          const int sp_hi = min(d1, i + w);
+          while (cbw <= cbase + (uint32_t)sp_hi) { mbar_wait(&full_b[cbw & (NB - 1)], (cbw >> 3) & 1); cbw++; }
+          const uint32_t slotA = ca & (NA - 1);
+          mbar_wait(&full_a[slotA], (ca >> 2) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t dA = descA0 + (uint64_t)(slotA * (SLOT_BYTES >> 4));
+          const bool first = (kc == 0 && i == 0);
+          uint32_t tcol = tcol_top;
+          for (int sp = i; sp <= sp_hi; sp++, tcol -= (uint32_t)BN) {
+            const uint64_t dB = descB0 + (uint64_t)(((cbase + (uint32_t)sp) & (NB - 1)) * (SLOT_BYTES >> 4));
+            const uint32_t acc0 = first ? ((carry_in && sp == i) ? 1u : 0u) : 1u;    // sp == i is the group's least significant diagonal
+            if (leader) {
               if (ninstr == 4) {
-                umma_i8(tcol, descA, descB, idesc, acc0); umma_i8(tcol, descA + 2, descB + 2, idesc, 1u);
-                umma_i8(tcol, descA + 4, descB + 4, idesc, 1u); umma_i8(tcol, descA + 6, descB + 6, idesc, 1u);
+                umma_i8(tcol, dA, dB, idesc, acc0); umma_i8(tcol, dA + 2, dB + 2, idesc, 1u);
+                umma_i8(tcol, dA + 4, dB + 4, idesc, 1u); umma_i8(tcol, dA + 6, dB + 6, idesc, 1u);
               } else {
-                for (int kk = 0; kk < ninstr; kk++) umma_i8(tcol, descA + (uint64_t)(2 * kk), descB + (uint64_t)(2 * kk), idesc, kk == 0 ? acc0 : 1u);
+                for (int kk = 0; kk < ninstr; kk++) umma_i8(tcol, dA + (uint64_t)(2 * kk), dB + (uint64_t)(2 * kk), idesc, kk == 0 ? acc0 : 1u);
               }
             }
-            umma_commit(&empty[slotA]);                                   // A_i is done after this step
-            { const uint32_t LB = Lbase + (uint32_t)(i < w ? i : 2 * i - w); umma_commit(&empty[LB % NSLOT]); }   // so is B_{s'=i}
           }
-          Lbase += 2u * (uint32_t)(d1 + 1);
+          if (leader) { umma_commit(&empty_a[slotA]); umma_commit(&empty_b[(cbase + (uint32_t)i) & (NB - 1)]); }   // A_i and B_{s'=i} are done
+          __syncwarp();
+          ca++;
         }
-        umma_commit(tmem_full);
+        cbase += (uint32_t)(d1 + 1);
       }
+      if (leader) umma_commit(tmem_full);
+      if (dbgon && leader) a.dbg[(ngroups - 1 - g) * 8 + 2] = clock64();
+      __syncwarp();
     }
   } else {
     // ===================== epilogue: 4 warps, one output row per thread =====================
@@ -200,8 +221,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint32_t full_parity = 0;
     for (int g = ngroups - 1; g >= 0; g--) {
       const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
+      const bool dbge = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
+      if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 3] = clock64();
       mbar_wait(tmem_full, full_parity); full_parity ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 4] = clock64();
       for (int c0 = 0; c0 < BN; c0 += 16) {
         int32_t carry[16];
 #pragma unroll
@@ -231,6 +255,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           dst[2] = make_int4(carry[8], carry[9], carry[10], carry[11]); dst[3] = make_int4(carry[12], carry[13], carry[14], carry[15]);
         }
       }
+      if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 5] = clock64();
       if (g > 0) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -268,6 +293,43 @@ template <int NL> __global__ void k_split_tc(VecView v, const int32_t* E, int Kp
   }
 #pragma unroll
   for (int t = 0; t < NS; t++) *(uint32_t*)(planes + ((int64_t)t * nvec_pitch + vec) * Kp + 4 * k4) = w[t];
+}
+
+// Same split for vectors whose entries are NOT contiguous (columns of a row-major matrix): consecutive
+// threads take consecutive vectors so the 40-byte reads coalesce, and the digits go through a
+// shared-memory transpose so each plane row receives full 32-byte segments.
+template <int NL> __global__ void __launch_bounds__(256) k_split_tc_t(VecView v, const int32_t* E, int Kp, int64_t nvec_pitch, uint8_t* planes) {
+  constexpr int NS = I8Cfg<NL>::NS;
+  __shared__ uint32_t sm[NS][32][9];
+  const int vl = threadIdx.x & 31, kl = threadIdx.x >> 5;
+  const int vec = blockIdx.x * 32 + vl, k4 = blockIdx.y * 8 + kl;
+  uint32_t w[NS];
+#pragma unroll
+  for (int t = 0; t < NS; t++) w[t] = 0;
+  if (vec < v.nvec) {
+    const mpn<NL>* p = (const mpn<NL>*)v.base + vec_off(v, vec);
+    const int32_t e = E[vec];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int k = 4 * k4 + q;
+      if (k < v.K) {
+        mpn<NL> a = p[(int64_t)k * v.sk]; int8_t dg[NS]; i8_split<NL>(a, e, dg);
+#pragma unroll
+        for (int t = 0; t < NS; t++) w[t] |= (uint32_t)(uint8_t)dg[t] << (8 * q);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NS; t++) sm[t][vl][kl] = w[t];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NS * 32; idx += 256) {
+    const int t = idx >> 5, vv = idx & 31, vec2 = blockIdx.x * 32 + vv;
+    if (vec2 < v.nvec) {
+      uint4* dst = (uint4*)(planes + ((int64_t)t * nvec_pitch + vec2) * Kp + 32 * blockIdx.y);
+      dst[0] = make_uint4(sm[t][vv][0], sm[t][vv][1], sm[t][vv][2], sm[t][vv][3]);
+      dst[1] = make_uint4(sm[t][vv][4], sm[t][vv][5], sm[t][vv][6], sm[t][vv][7]);
+    }
+  }
 }
 
 // byte planes + top -> multi-limb C (op with D), one thread per output

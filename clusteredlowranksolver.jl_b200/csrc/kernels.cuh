@@ -158,59 +158,70 @@ template <int NL> __global__ void k_gemv_t(int K, int N, const mpn<NL>* A, int l
 
 // ---------------------------------------------------------------------------
 // panel kernel: Cholesky of one diagonal block (nb <= 32) and the inverse of its
-// factor, one CTA of 32x32 threads, the block in registers/shared memory.
+// factor, one CTA, the block in shared memory.
 // status[0] is set to `code` if a pivot is not strictly positive
 // (approx_cholesky!, src/tools.jl:92-95).
 // ---------------------------------------------------------------------------
-template <int NL> __global__ void __launch_bounds__(256) k_potrf_diag(int nb, mpn<NL>* A, int lda, mpn<NL>* Minv, int ldm, int* status, int code) {
+// Warp-specialised: the pivot chain (the only sequential part: one rsqrt per column) runs on one
+// thread and is overlapped with the trailing update of the block (7 warps) and with the rows of the
+// inverse factor (16 warps); two CTA-wide barriers per column.
+#define POTRF_THREADS 768
+template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(int nb, mpn<NL>* A, int lda, mpn<NL>* Minv, int ldm, int* status, int code) {
   extern __shared__ unsigned char smraw[];
-  mpn<NL>* Ls = (mpn<NL>*)smraw;                          // 32 x 32 working block
-  mpn<NL>* Ms = Ls + 32 * 32;                             // 32 x 32 inverse
-  mpn<NL>* sinv = Ms + 32 * 32;                           // 32 reciprocal pivots
+  mpn<NL>* As = (mpn<NL>*)smraw;                          // 32 x 32 working block (updated lower part)
+  mpn<NL>* Ls = As + 32 * 32;                             // the factor
+  mpn<NL>* Ms = Ls + 32 * 32;                             // its inverse
+  mpn<NL>* rinv = Ms + 32 * 32;                           // 1/L[c][c]
+  mpn<NL>* dpiv = rinv + 32;                              // pivots before the square root
   __shared__ int bad;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < 32 * 32; idx += 256) { const int i = idx >> 5, j = idx & 31; mpn<NL> a; mp_zero(a); if (i < nb && j <= i) a = A[(int64_t)i * lda + j]; Ls[idx] = a; mp_zero(Ms[idx]); }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < 32 * 32; idx += POTRF_THREADS) { const int i = idx >> 5, j = idx & 31; mpn<NL> a; mp_zero(a); if (i < nb && j <= i) a = A[(int64_t)i * lda + j]; As[idx] = a; mp_zero(Ls[idx]); mp_zero(Ms[idx]); }
   if (tid == 0) bad = 0;
   __syncthreads();
-  for (int c = 0; c < nb; c++) {
-    if (tid == 0) {
-      mpn<NL> a = Ls[c * 32 + c];
-      if (a.sign <= 0) { bad = 1; mp_set_i32(a, 1); }
-      mpn<NL> s, r; mp_sqrt_rsqrt(s, r, a); Ls[c * 32 + c] = s; sinv[c] = r;
-    }
-    __syncthreads();
-    for (int i = c + 1 + tid; i < nb; i += 256) { mpn<NL> a = Ls[i * 32 + c]; mp_mul(a, a, sinv[c]); Ls[i * 32 + c] = a; }
-    __syncthreads();
-    const int w = nb - c - 1;
-    for (int idx = tid; idx < w * w; idx += 256) {
-      const int i = c + 1 + idx / w, j = c + 1 + idx % w;
-      if (j <= i) { mpn<NL> a = Ls[i * 32 + j], t; mp_mul(t, Ls[i * 32 + c], Ls[j * 32 + c]); mp_sub(a, a, t); Ls[i * 32 + j] = a; }
-    }
-    __syncthreads();
-  }
-  for (int idx = tid; idx < nb * nb; idx += 256) { const int i = idx / nb, j = idx % nb; A[(int64_t)i * lda + j] = Ls[i * 32 + j]; }
-  if (tid == 0 && bad) atomicCAS(status, 0, code);
-  // inverse of the factor by forward substitution, all 32 columns in parallel:
-  // 8 lanes per column, M[r][j] = -inv_r * sum_{k=j}^{r-1} L[r][k] M[k][j]
-  const int j = tid >> 3, g = tid & 7;
-  if (g == 0 && j < nb) Ms[j * 32 + j] = sinv[j];
+  if (tid == 0) { mpn<NL> a = As[0]; if (a.sign <= 0) { bad = 1; mp_set_i32(a, 1); } dpiv[0] = a; mpn<NL> r; mp_rsqrt(r, a); rinv[0] = r; }
   __syncthreads();
-  for (int r = 1; r < nb; r++) {
-    mpn<NL> acc; mp_zero(acc);
-    if (j < r) for (int k = j + g; k < r; k += 8) { mpn<NL> t; mp_mul(t, Ls[r * 32 + k], Ms[k * 32 + j]); mp_add(acc, acc, t); }
-    for (int o = 4; o > 0; o >>= 1) {
-      mpn<NL> other;
+  for (int c = 0; c < nb; c++) {
+    if (warp == 0) {
+      // ---- pivot chain: d_{c+1} = a_{c+1,c+1} - l_{c+1,c}^2 (columns < c already applied), r_{c+1} = d^-1/2
+      if (lane == 0 && c + 1 < nb) {
+        mpn<NL> l, d; mp_mul(l, As[(c + 1) * 32 + c], rinv[c]); mp_mul(l, l, l); mp_sub(d, As[(c + 1) * 32 + c + 1], l);
+        if (d.sign <= 0) { bad = 1; mp_set_i32(d, 1); }
+        dpiv[c + 1] = d; mpn<NL> r; mp_rsqrt(r, d); rinv[c + 1] = r;
+      }
+    } else if (warp < 8) {
+      // ---- column c of the factor, then the trailing update with it
+      const int ut = tid - 32;                            // 0..223
+      if (ut == 0) { mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[c * 32 + c] = sq; }
+      for (int i = c + 1 + ut; i < nb; i += 224) { mpn<NL> a; mp_mul(a, As[i * 32 + c], rinv[c]); Ls[i * 32 + c] = a; }
+      asm volatile("bar.sync 1, 224;" ::: "memory");
+      const int w = nb - c - 1;
+      for (int idx = ut; idx < w * w; idx += 224) {
+        const int i = c + 1 + idx / w, j = c + 1 + idx % w;
+        if (j <= i && !(i == c + 1 && j == c + 1)) { mpn<NL> a = As[i * 32 + j], t; mp_mul(t, Ls[i * 32 + c], Ls[j * 32 + c]); mp_sub(a, a, t); As[i * 32 + j] = a; }
+      }
+    } else {
+      // ---- row c of the inverse: M[c][c] = r_c, M[c][j] = -r_c sum_{k=j}^{c-1} L[c][k] M[k][j]
+      const int iw = warp - 8;                            // 0..15
+      if (iw == 0 && lane == 0) Ms[c * 32 + c] = rinv[c];
+      for (int j = iw; j < c; j += 16) {
+        mpn<NL> acc; mp_zero(acc);
+        if (lane >= j && lane < c) mp_mul(acc, Ls[c * 32 + lane], Ms[lane * 32 + j]);
+        for (int o = 16; o > 0; o >>= 1) {
+          mpn<NL> other;
 #pragma unroll
-      for (int i = 0; i < NL; i++) other.l[i] = __shfl_down_sync(0xffffffffu, acc.l[i], o, 8);
-      other.exp = __shfl_down_sync(0xffffffffu, acc.exp, o, 8); other.sign = __shfl_down_sync(0xffffffffu, acc.sign, o, 8);
-      mp_add(acc, acc, other);
+          for (int q = 0; q < NL; q++) other.l[q] = __shfl_down_sync(0xffffffffu, acc.l[q], o);
+          other.exp = __shfl_down_sync(0xffffffffu, acc.exp, o); other.sign = __shfl_down_sync(0xffffffffu, acc.sign, o);
+          mp_add(acc, acc, other);
+        }
+        if (lane == 0) { mp_mul(acc, acc, rinv[c]); acc.sign = -acc.sign; Ms[c * 32 + j] = acc; }
+      }
     }
-    if (g == 0 && j < r) { mp_mul(acc, acc, sinv[r]); acc.sign = -acc.sign; Ms[r * 32 + j] = acc; }
-    __syncthreads();
+    __syncthreads();                                      // (element (c+1,c+1) lives on in dpiv; its As copy is not read again)
   }
-  for (int idx = tid; idx < nb * nb; idx += 256) { const int i = idx / nb, jj = idx % nb; Minv[(int64_t)i * ldm + jj] = Ms[i * 32 + jj]; }
+  for (int idx = tid; idx < nb * nb; idx += POTRF_THREADS) { const int i = idx / nb, j = idx % nb; A[(int64_t)i * lda + j] = Ls[i * 32 + j]; Minv[(int64_t)i * ldm + j] = Ms[i * 32 + j]; }
+  if (tid == 0 && bad) atomicCAS(status, 0, code);
 }
-#define POTRF_SMEM(NL) ((2 * 32 * 32 + 32) * sizeof(mpn<NL>))
+#define POTRF_SMEM(NL) ((3 * 32 * 32 + 64) * sizeof(mpn<NL>))
 
 // ---------------------------------------------------------------------------
 // int8 slice pipeline on CUDA cores

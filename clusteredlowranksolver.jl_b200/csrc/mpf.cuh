@@ -214,7 +214,7 @@ template <int NL> HD void mp_recip(mpn<NL>& r, const mpn<NL>& a) {
   mpn<NL> m = a; m.exp = 0; m.sign = 1;                   // mantissa in [1/2,1)
   mpn<NL> x, t, two; mp_from_double(x, 1.0 / mp_to_double(m)); mp_set_i32(two, 2);
 #pragma unroll 1
-  for (int it = 0; it < mp_newton_steps<NL>() + 1; it++) { mp_mul(t, m, x); mp_sub(t, two, t); mp_mul(x, x, t); }
+  for (int it = 0; it < mp_newton_steps<NL>(); it++) { mp_mul(t, m, x); mp_sub(t, two, t); mp_mul(x, x, t); }
   x.exp -= a.exp; x.sign = a.sign; r = x;
 }
 template <int NL> HD void mp_div(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>& b) {
@@ -226,7 +226,7 @@ template <int NL> HD void mp_rsqrt(mpn<NL>& r, const mpn<NL>& a) {
   mpn<NL> m = a; const int odd = a.exp & 1; m.exp = -odd; m.sign = 1;   // m in [1/4,1), a = m 2^(exp+odd), exponent even
   mpn<NL> y, t, three; mp_from_double(y, 1.0 / sqrt(mp_to_double(m))); mp_set_i32(three, 3);
 #pragma unroll 1
-  for (int it = 0; it < mp_newton_steps<NL>() + 1; it++) { mp_mul(t, y, y); mp_mul(t, t, m); mp_sub(t, three, t); mp_mul(y, y, t); y.exp -= 1; }
+  for (int it = 0; it < mp_newton_steps<NL>(); it++) { mp_mul(t, y, y); mp_mul(t, t, m); mp_sub(t, three, t); mp_mul(y, y, t); y.exp -= 1; }
   y.exp -= (a.exp + odd) / 2; r = y;
 }
 // r = sqrt(a), rinv = 1/sqrt(a) for a > 0 (one correction step on the root)

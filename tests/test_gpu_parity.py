@@ -264,14 +264,18 @@ def test_dense_schur_equals_hadamard_identity_at_full_size():
     x, X, y, Y = s.get_state()
     s.iterate()      # S and X^-1 of this iteration are built from the (X, Y) just read
     n = 300
-    S = s.debug_get("L", 0, 0)  # noqa: F841  (factor buffer; S itself is overwritten by its Cholesky factor)
+    Ls = wire.from_wire(s.debug_get("S", 0, 0), PREC).reshape(n, n)      # S is held as its Cholesky factor
     Xinv = wire.from_wire(s.debug_get("Xinv", 0, 0), PREC).reshape(n, n)
     Yw = wire.from_wire(Y, PREC).reshape(n, n)
     Xw = wire.from_wire(X, PREC).reshape(n, n)
     rng = random.Random(0)
     with mpmath.workprec(400):
-        # X^-1 really inverts X (sampled rows), to the accuracy its conditioning allows
-        for _ in range(3):
+        scale = max(abs(Xinv[i, i] * Yw[i, i]) for i in range(n))
+        for _ in range(25):
+            i, j = rng.randrange(n), rng.randrange(n)
+            sij = mpmath.fsum(Ls[i, k] * Ls[j, k] for k in range(min(i, j) + 1))
+            assert abs(sij - Xinv[i, j] * Yw[i, j]) <= scale * mpmath.mpf(10) ** -60, (i, j)
+        for _ in range(3):      # X^-1 really inverts X (sampled rows)
             i = rng.randrange(n)
             row = [mpmath.fsum(Xinv[i, k] * Xw[k, j] for k in range(n)) for j in range(n)]
             assert max(abs(v - (1 if j == i else 0)) for j, v in enumerate(row)) < mpmath.mpf(10) ** -50
