@@ -96,7 +96,9 @@ class Solver:
     """One solver handle (device or oracle) holding one uploaded SDP."""
 
     def __init__(self, sdp: ClusteredSDP, lib: str = "device", device: int = 0, gemm_path: int = 0,
-                 matmul_prec: int = 0, oracle_skip_zeros: bool = False, **kwargs):
+                 matmul_prec: int = 0, oracle_skip_zeros: bool = False, comm=None, **kwargs):
+        """comm = (rank, nranks, unique_id_bytes): shard the clusters of the SDP over `nranks` handles
+        (one per GPU / process); every rank uploads the same SDP and calls iterate() in lock step."""
         self.kind = lib
         self.lib = load_library(lib)
         self.pre = "clrs_" if lib == "device" else "clrs_oracle_"
@@ -132,6 +134,10 @@ class Solver:
                 val = mpmath.mpf(v.numerator) / v.denominator if isinstance(v, Fraction) else mpmath.mpf(v)
                 w = wire.to_wire(val, self.prec)
                 self._call("set_option_num", self.h, C.c_int(_OPT_IDS[k]), w.ctypes.data_as(C.c_void_p))
+        self.rank, self.nranks = (comm[0], comm[1]) if comm else (0, 1)
+        if comm and lib == "device" and comm[1] > 1:
+            uid = (C.c_char * 128).from_buffer_copy(bytes(comm[2]))
+            self._call("comm_init", self.h, C.c_int32(comm[0]), C.c_int32(comm[1]), uid)
         if lib == "oracle" and oracle_skip_zeros:
             fn = self._fn("set_dense_skip_zeros")
             fn.restype = None
@@ -243,6 +249,10 @@ class Solver:
             raise KeyError(what)
         return buf[:n]
 
+    def cluster_owner(self, j: int) -> int:
+        fn = self._fn("cluster_owner"); fn.restype = C.c_int
+        return int(fn(self.h, C.c_int32(j)))
+
     # -- measurement hooks (device library only) ------------------------------
     def profile(self, enable: bool):
         fn = self._fn("profile"); fn.restype = None; fn(self.h, C.c_int32(int(enable)))
@@ -302,10 +312,10 @@ class SolveResult:
 
 def solvesdp(sdp: ClusteredSDP, lib: str = "device", maxiterations: int = 500, verbose: bool = False,
              callback=None, keep_solver: bool = False, device: int = 0, gemm_path: int = 0,
-             oracle_skip_zeros: bool = False, **kwargs) -> SolveResult:
+             oracle_skip_zeros: bool = False, comm=None, **kwargs) -> SolveResult:
     """Mirror of solvesdp(sdp; kwargs...) (src/solver.jl:100-744) above the C ABI."""
     res = SolveResult()
-    S = Solver(sdp, lib=lib, device=device, gemm_path=gemm_path, oracle_skip_zeros=oracle_skip_zeros, **kwargs)
+    S = Solver(sdp, lib=lib, device=device, gemm_path=gemm_path, oracle_skip_zeros=oracle_skip_zeros, comm=comm, **kwargs)
     gap_thr = float(kwargs.get("duality_gap_threshold", 1e-15))
     derr_thr = float(kwargs.get("dual_error_threshold", 1e-30))
     perr_thr = float(kwargs.get("primal_error_threshold", 1e-30))
@@ -366,3 +376,26 @@ def solvesdp(sdp: ClusteredSDP, lib: str = "device", maxiterations: int = 500, v
     else:
         S.close()
     return res
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId for Solver(comm=...); create on rank 0 and broadcast to the other ranks."""
+    lib = load_library("device")
+    buf = (C.c_char * 128)()
+    fn = lib.clrs_comm_unique_id
+    fn.restype = C.c_int
+    if fn(buf) != 0:
+        raise RuntimeError("clrs_comm_unique_id failed (libnccl.so.2 not found?)")
+    return bytes(buf)
+
+
+def partition_clusters(weights, nranks: int):
+    """The library's cluster -> rank partitioner (host only; usable without a GPU)."""
+    lib = load_library("device")
+    w = (C.c_double * len(weights))(*[float(v) for v in weights])
+    out = (C.c_int32 * len(weights))()
+    fn = lib.clrs_partition_clusters
+    fn.restype = C.c_int
+    if fn(C.c_int32(len(weights)), w, C.c_int32(nranks), out) != 0:
+        raise ValueError("clrs_partition_clusters failed")
+    return list(out)

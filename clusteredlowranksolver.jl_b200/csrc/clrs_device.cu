@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <stdexcept>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include "../../include/clrs_b200.h"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
@@ -24,6 +25,33 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 static inline int grid_for(int64_t n, int bs = 256, int cap = 148 * 8) { int64_t g = (n + bs - 1) / bs; if (g < 1) g = 1; return (int)std::min<int64_t>(g, cap); }
+
+// ---- NCCL, loaded at run time (only multi-GPU handles need it) ----
+struct NcclUid { char b[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr; int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr; int (*CommDestroy)(void*) = nullptr; const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    for (const char* n : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = "libnccl.so.2 not found"; return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId"); CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather"); CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy"); GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+// LPT partition of clusters over ranks by weight (the reference balances its threads by the same
+// P_j^3 / n^3 weights, src/threadinginfo.jl:88,97); deterministic on every rank
+static void partition_clusters(const std::vector<double>& w, int R, std::vector<int>& owner) {
+  std::vector<int> order(w.size()); for (size_t i = 0; i < w.size(); i++) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w[a] > w[b]; });
+  std::vector<double> load(R, 0.0); owner.assign(w.size(), 0);
+  for (int j : order) { int best = 0; for (int r = 1; r < R; r++) if (load[r] < load[best]) best = r; owner[j] = best; load[best] += w[j]; }
+}
 
 // scalar slots in device memory
 enum { SC_MU, SC_MUP, SC_MUC, SC_BETA, SC_BETAC, SC_ALPHAD, SC_ALPHAP, SC_D0, SC_D1, SC_D2, SC_D3, SC_DOBJ, SC_POBJ, SC_GAP,
@@ -59,7 +87,7 @@ template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, doub
     fl[FL_PDFEAS] = (mp_cmp(de, sc[SC_DERRTHR]) < 0) && (mp_cmp(sc[SC_ERRd], sc[SC_PERRTHR]) < 0);
     info[INFO_BETAC] = mp_to_double(betac);
     info[INFO_ERRP] = mp_to_double(sc[SC_ERRP]); info[INFO_ERRp] = mp_to_double(sc[SC_ERRp]); info[INFO_ERRd] = mp_to_double(sc[SC_ERRd]);
-  } else if (phase == 2) {     // step length from the per-block smallest eigenvalues (src/solver.jl:1684-1692)
+  } else if (phase == 2) {     // smallest eigenvalue over this rank's blocks (src/solver.jl:1684-1686) -> sc[SC_TMP]
     num mn; bool have = false;
     for (int b = 0; b < nblocks; b++) {
       num ev;
@@ -67,6 +95,10 @@ template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, doub
       else { num c; mp_from_double(ev, lam[b]); mp_from_double(c, 1e-5); mp_sub(ev, ev, c); }
       if (!have || mp_cmp(ev, mn) < 0) { mn = ev; have = true; }
     }
+    if (!have) { mp_set_i32(mn, 1); mn.exp = 1 << 28; }        // a rank without blocks does not constrain the step
+    sc[SC_TMP] = mn;
+  } else if (phase == 6) {     // step length from the global smallest eigenvalue (src/solver.jl:1688-1692)
+    num mn = sc[SC_TMP];
     num ng = sc[SC_GAMMA]; ng.sign = -ng.sign; num alpha;
     const bool unsafe_step = fl[FL_PDFEAS] && !cfg.safe_step;
     if (mp_cmp(mn, ng) > 0 && !unsafe_step) alpha = sc[SC_ONE]; else mp_div(alpha, ng, mn);
@@ -107,6 +139,21 @@ template <int NL> __global__ void k_scatter_upper(int np, const int32_t* plist, 
   mpn<NL> o = *dst, t = T[(int64_t)b * np + a]; mp_add(o, o, t); *dst = o;     // T holds the lower triangle T[q][p]
 }
 
+// out[i] = reduction over ranks of gathered[r*n + i], in rank order (deterministic, identical on every rank)
+// op 0: sum, 1: max |.|, 2: min (signed)
+template <int NL> __global__ void k_combine_gathered(int64_t n, int R, const mpn<NL>* gathered, mpn<NL>* out, int op) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    mpn<NL> acc = gathered[i];
+    for (int r = 1; r < R; r++) { mpn<NL> v = gathered[(int64_t)r * n + i];
+      if (op == 0) mp_add(acc, acc, v); else if (op == 1) { if (mp_cmp_abs(v, acc) > 0) acc = v; } else { if (mp_cmp(v, acc) < 0) acc = v; } }
+    if (op == 1 && acc.sign < 0) acc.sign = 1;
+    out[i] = acc;
+  }
+}
+__global__ void k_combine_flags(int n, int R, const int* gathered, int* out) {
+  int i = threadIdx.x; if (i >= n) return; int m = gathered[i]; for (int r = 1; r < R; r++) m = max(m, gathered[r * n + i]); out[i] = m;
+}
+
 // pseudo-random multi-limb numbers for kernel benchmarks (splitmix-style hash)
 template <int NL> __global__ void k_fill_random(int64_t n, mpn<NL>* a, uint64_t seed, int spread) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -140,6 +187,8 @@ struct SolverBase {
   virtual void profile_get(double* out) = 0;
   virtual double last_iteration_ms() = 0;
   virtual int bench_gemm(int M, int N, int K, int reps, int path, double* out) = 0;
+  virtual int comm_init(int rank, int nranks, const void* uid) = 0;
+  virtual int owner_of(int j) = 0;
   size_t wire_size() const { return 16 + 8 * (size_t)((prec + 63) / 64); }
 };
 
@@ -220,7 +269,10 @@ template <int NL> struct Solver : SolverBase {
   void gemm_tc(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode, const num* D, int ldd,
                int batch, int64_t a_bvec, int64_t b_bvec, int64_t c_bs, int64_t d_bs, int lower_only) {
     if (a0 != 0 || b0 != 0) throw CudaError("gemm_tc: panel offsets are not supported");
-    const int ntn = (N + 127) / 128; int BN = ((N + ntn - 1) / ntn + 15) & ~15; if (BN > 128) BN = 128;
+    // default: both operands in shared memory (k_gemm_tc); CLRS_TC_TS=1 selects the variant with the left
+    // operand chunk in TMEM (k_gemm_ts, tiles of at most 112 columns) — measured slower once four warps issue MMAs
+    static const bool ts = getenv("CLRS_TC_TS") != nullptr;
+    const int bnmax = ts ? 112 : 128; const int ntn = (N + bnmax - 1) / bnmax; int BN = ((N + ntn - 1) / ntn + 15) & ~15; if (BN > bnmax) BN = bnmax;
     const int Npitch = (N + 15) & ~15;
     CUtensorMap mA = make_map(A, tc::BM), mB = make_map(B, BN);
     // K longer than the int32 headroom (35 slices * K * 2^14 < 2^31), or few tiles with a long K: split K over
@@ -237,7 +289,8 @@ template <int NL> struct Solver : SolverBase {
     tc::Args a; a.M = M; a.N = N; a.Kp = A.Kp; a.k0 = 0; a.BN = BN; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch;
     a.batch = nch > 1 ? nch : batch; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = lower_only; a.kz_stride = nch > 1 ? kch : 0; a.Kp_total = A.Kp; a.dbg = nullptr;
     dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, a.batch);
-    nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
+    if (ts) { tc::ArgsTS p; p.g = a; p.planesA = A.planes; p.nvecA = A.nvec; p.KpA = A.Kp; nlaunch++, tc::k_gemm_ts<<<grid, tc::TS_THREADS, tc::TS_SMEM_BYTES, st>>>(mB, p); }
+    else nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
     const int64_t tot_ = (int64_t)batch * M * N;
     nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1);
   }
@@ -251,6 +304,31 @@ template <int NL> struct Solver : SolverBase {
   void mm(const num* A, int lda, const num* B, int ldb, int M, int N, int K, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0) {
     const int lay = use_tc(M, N, K) ? 1 : 0;
     split_rows(tA, A, lda, M, K, lay); split_cols(tB, B, ldb, K, N, lay); gemm(tA, 0, tB, 0, M, N, C, ldc, mode, D, ldd);
+  }
+
+  // ---- multi-GPU: clusters sharded over ranks, partial results combined by all-gather + ordered sum ----
+  int rank = 0, nranks = 1; void* comm = nullptr; num* gbuf = nullptr; size_t gcap = 0; int* gflags = nullptr;
+  int comm_init(int rank_, int nranks_, const void* uid) override {
+    if (finalized) { err = "clrs_comm_init must precede clrs_finalize"; return CLRS_ERR_ARG; }
+    if (nranks_ <= 1) { rank = 0; nranks = 1; return CLRS_OK; }
+    if (!g_nccl.load(err)) return CLRS_ERR_CUDA;
+    NcclUid id; memcpy(id.b, uid, 128);
+    int rc = g_nccl.CommInitRank(&comm, nranks_, id, rank_);
+    if (rc != 0) { err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return CLRS_ERR_CUDA; }
+    rank = rank_; nranks = nranks_; gflags = dalloc<int>((size_t)nranks * FL_COUNT); return CLRS_OK;
+  }
+  int owner_of(int j) override { return (j >= 0 && j < (int)cl.size()) ? cl[j].owner : -1; }
+  void allreduce(num* v, int64_t n, int op) {      // op 0 sum, 1 max-abs, 2 min
+    if (nranks == 1 || n == 0) return;
+    if ((size_t)n * nranks > gcap) { gcap = (size_t)n * nranks; gbuf = dalloc<num>(gcap); }
+    int rc = g_nccl.AllGather(v, gbuf, (size_t)n * sizeof(num), /*ncclChar*/ 0, comm, st);
+    if (rc != 0) throw CudaError("ncclAllGather failed");
+    nlaunch++, k_combine_gathered<NL><<<grid_for(n), 256, 0, st>>>(n, nranks, gbuf, v, op);
+  }
+  void allreduce_flags() {
+    if (nranks == 1) return;
+    int rc = g_nccl.AllGather(flags, gflags, FL_COUNT * sizeof(int), 0, comm, st); if (rc != 0) throw CudaError("ncclAllGather failed");
+    nlaunch++, k_combine_flags<<<1, 32, 0, st>>>(FL_COUNT, nranks, gflags, flags);
   }
 
   // ---- flat helpers ------------------------------------------------------------
@@ -298,7 +376,8 @@ template <int NL> struct Solver : SolverBase {
   // ---- problem description -------------------------------------------------------------
   struct HTerm { int r, s, p, k; num lam; std::vector<num> v, w; int colV = -1, rowW = -1; };
   struct Block {
-    int j = 0, l = 0, m = 1, delta = 1, n = 1; bool high_rank = false; int64_t off = 0;   // offset in the flat block storage
+    int j = 0, l = 0, m = 1, delta = 1, n = 1; bool high_rank = false; int64_t off = 0;   // offset in the flat block storage (owned blocks)
+    int64_t goff = 0;                                                                      // offset in the global (all ranks) block order
     std::vector<num> hC;
     // dense
     std::vector<int> dense_p; std::vector<std::vector<num>> dense_A;
@@ -314,12 +393,14 @@ template <int NL> struct Solver : SolverBase {
     // per-iteration cached panels (layout `lay`: 1 = tensor-core panels for large blocks)
     Sliced YS, XiS, MS; int lay = 0;
   };
-  struct Clu { int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; int off = 0; };
+  struct Clu { int owner = 0; bool owned = true; int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; int off = 0; };
   std::vector<Clu> cl; std::vector<Block*> blk;   // blk: all blocks in (j,l) order
   int N = 0, Ptot = 0, Ksum = 0, maximize = 1; std::vector<num> hb; num hconst;
-  int64_t tot = 0;   // numbers in the flat block storage
+  int64_t tot = 0;   // numbers in the flat block storage of the blocks this rank owns
+  int64_t gtot = 0;  // numbers in all blocks of the SDP
   // device state
   num *X = nullptr, *Y = nullptr, *Cm = nullptr, *L = nullptr, *Minv = nullptr, *Xi = nullptr, *R = nullptr, *P = nullptr, *dX = nullptr, *dY = nullptr, *T1 = nullptr, *TXY = nullptr, *U = nullptr;
+  num* tmpU = nullptr;
   num *x = nullptr, *y = nullptr, *c = nullptr, *b = nullptr, *d = nullptr, *p = nullptr, *dx = nullptr, *dy = nullptr, *tr = nullptr, *Q = nullptr, *QMinv = nullptr, *tmpN = nullptr;
   num* sc = nullptr; int* flags = nullptr; double* dinfo = nullptr; double* Td = nullptr; double* lamX = nullptr; double* lamY = nullptr; double* eigV = nullptr; EigTask* eigT = nullptr;
   int64_t* d_boff = nullptr; int32_t* d_bn = nullptr; BlockTab bt;
@@ -337,6 +418,7 @@ template <int NL> struct Solver : SolverBase {
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
     CK(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_gemm_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TS_SMEM_BYTES));
     CK(cudaEventCreate(&pe0)); CK(cudaEventCreate(&pe1));
     mp_zero(hconst);
     double dv[10] = {o.beta_infeasible, o.beta_feasible, o.gamma, o.omega_p, o.omega_d, o.duality_gap_threshold, o.dual_error_threshold, o.primal_error_threshold, o.max_complementary_gap, o.step_length_threshold};
@@ -345,6 +427,7 @@ template <int NL> struct Solver : SolverBase {
   }
   ~Solver() {
     cudaStreamSynchronize(st);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     owned_sliced.push_back(&tA); owned_sliced.push_back(&tB);
     for (Sliced* s : owned_sliced) { if (s->sl) cudaFree(s->sl); if (s->E) cudaFree(s->E); if (s->planes) cudaFree(s->planes); }
     if (tc_bytes) cudaFree(tc_bytes); if (tc_top) cudaFree(tc_top); if (pe0) cudaEventDestroy(pe0); if (pe1) cudaEventDestroy(pe1);
@@ -391,8 +474,11 @@ template <int NL> struct Solver : SolverBase {
 
   // ---- finalize: build tables (precompute_matrices_bilinear_pairings, src/solver.jl:985-1059), allocate, initialise ----
   int finalize() override {
-    Ptot = 0; Ksum = 0; tot = 0; blk.clear();
-    for (auto& c0 : cl) { c0.off = Ptot; Ptot += c0.P; for (auto& b0 : c0.blocks) { b0.off = tot; tot += (int64_t)b0.n * b0.n; Ksum += b0.n; blk.push_back(&b0); } }
+    Ptot = 0; Ksum = 0; tot = 0; gtot = 0; blk.clear();
+    { std::vector<double> wgt; for (auto& c0 : cl) { double w = (double)c0.P * c0.P * c0.P; for (auto& b0 : c0.blocks) { double n3 = (double)b0.n * b0.n * b0.n; w += n3 * (b0.high_rank ? 2.0 * b0.dense_p.size() + 15 : 15); } wgt.push_back(w); }
+      std::vector<int> owner; partition_clusters(wgt, nranks, owner); for (size_t j = 0; j < cl.size(); j++) { cl[j].owner = owner[j]; cl[j].owned = owner[j] == rank; } }
+    for (auto& c0 : cl) { c0.off = Ptot; Ptot += c0.P;
+      for (auto& b0 : c0.blocks) { Ksum += b0.n; b0.goff = gtot; gtot += (int64_t)b0.n * b0.n; if (c0.owned) { b0.off = tot; tot += (int64_t)b0.n * b0.n; blk.push_back(&b0); } } }
     std::vector<int64_t> boff; std::vector<int32_t> bn; for (Block* b0 : blk) { boff.push_back(b0->off); bn.push_back(b0->n); } boff.push_back(tot);
     d_boff = upload(boff); d_bn = upload(bn); bt.off = d_boff; bt.n = d_bn; bt.nblocks = (int)blk.size();
     num** flat[] = {&X, &Y, &Cm, &L, &Minv, &Xi, &R, &P, &dX, &dY, &T1, &TXY, &U};
@@ -400,11 +486,13 @@ template <int NL> struct Solver : SolverBase {
     { std::vector<num> hC(tot); for (Block* b0 : blk) std::copy(b0->hC.begin(), b0->hC.end(), hC.begin() + b0->off); CK(cudaMemcpyAsync(Cm, hC.data(), tot * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
     x = dalloc<num>(Ptot); d = dalloc<num>(Ptot); dx = dalloc<num>(Ptot); tr = dalloc<num>(Ptot);
     y = dalloc<num>(N); p = dalloc<num>(N); dy = dalloc<num>(N); tmpN = dalloc<num>(N); Q = dalloc<num>((size_t)N * N); QMinv = dalloc<num>((size_t)N * N);
-    { std::vector<num> hc; for (auto& c0 : cl) hc.insert(hc.end(), c0.hc.begin(), c0.hc.end()); c = upload(hc); b = upload(hb); }
+    { std::vector<num> hc; num z; mp_zero(z); for (auto& c0 : cl) { if (c0.owned) hc.insert(hc.end(), c0.hc.begin(), c0.hc.end()); else hc.insert(hc.end(), c0.P, z); } c = upload(hc); b = upload(hb); }   // c of clusters owned elsewhere reads as 0
+    tmpU = dalloc<num>(N);
     Td = dalloc<double>(tot); lamX = dalloc<double>(blk.size()); lamY = dalloc<double>(blk.size());
     { std::vector<EigTask> et; size_t vtot = 0; for (Block* b0 : blk) vtot += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); eigV = dalloc<double>(vtot); size_t o = 0;
       for (Block* b0 : blk) { EigTask t; t.T = Td + b0->off; t.n = b0->n; t.V = eigV + o; o += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); et.push_back(t); } eigT = upload(et); }
     for (auto& c0 : cl) {
+      if (!c0.owned) continue;
       c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.LinvB = dalloc<num>((size_t)c0.P * N); c0.t = dalloc<num>(c0.P);
       for (auto& b0 : c0.blocks) if (int rc = finalize_block(c0, b0)) return rc;
     }
@@ -488,6 +576,7 @@ template <int NL> struct Solver : SolverBase {
   // dst_b = sum_p a_p A_p per block  (compute_weighted_A!, src/solver.jl:1410-1470)
   void weighted_A(num* dst, const num* a) {
     for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
+      if (!c0.owned) continue;
       num* M = dst + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; const num* aj = a + c0.off;
       if (b0.high_rank) { nlaunch++, k_weighted_dense<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, aj, M); continue; }
       zero(M, (int64_t)n * n);
@@ -502,6 +591,7 @@ template <int NL> struct Solver : SolverBase {
   void trace_vectors(num* out, const num* Z) {
     zero(out, Ptot);
     for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
+      if (!c0.owned) continue;
       const num* Zb = Z + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; num* oj = out + c0.off;
       if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, Zb, oj); continue; }
       if (b0.nP == 0) continue;
@@ -513,7 +603,7 @@ template <int NL> struct Solver : SolverBase {
   // out[p] = <A_p, Y> from the stored pairings (src/solver.jl:1368-1407)
   void trace_pairings(num* out) {
     zero(out, Ptot);
-    for (auto& c0 : cl) for (auto& b0 : c0.blocks) { num* oj = out + c0.off;
+    for (auto& c0 : cl) for (auto& b0 : c0.blocks) { if (!c0.owned) continue; num* oj = out + c0.off;
       if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)b0.n * b0.n, Y + b0.off, oj); continue; }
       if (b0.nP) nlaunch++, k_trace_pairings<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BY, b0.m, oj); }
   }
@@ -521,16 +611,19 @@ template <int NL> struct Solver : SolverBase {
   void residuals() {
     weighted_A(P, x);
     k_residual_P<NL><<<grid_for(tot), 256, 0, st>>>(tot, P, X, Cm, maximize);
-    // d = c - B y - tr
+    // d = c - B y - tr   (segments of clusters owned by other ranks stay 0)
     addsub(d, c, 1, tr, -1, Ptot);
-    if (N > 0) for (auto& c0 : cl) if (c0.P) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.B, N, y, d + c0.off, -1, 1);
-    // p = +-b - sum_j B_j^T x_j
-    if (N > 0) { addsub(p, b, maximize ? 1 : -1, b, 0, N);
-      for (auto& c0 : cl) if (c0.P) nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1); }
+    if (N > 0) for (auto& c0 : cl) if (c0.owned && c0.P) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.B, N, y, d + c0.off, -1, 1);
+    // p = +-b - sum_j B_j^T x_j   (partial sums over the owned clusters, combined over the ranks)
+    if (N > 0) { zero(p, N);
+      for (auto& c0 : cl) if (c0.owned && c0.P) nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1);
+      allreduce(p, N, 0);
+      addsub(p, p, 1, b, maximize ? 1 : -1, N); }
   }
-  void errors() { reduce(P, nullptr, tot, sc + SC_ERRP, 0); reduce(p, nullptr, N, sc + SC_ERRp, 0); reduce(d, nullptr, Ptot, sc + SC_ERRd, 0); }
+  void errors() { reduce(P, nullptr, tot, sc + SC_ERRP, 0); allreduce(sc + SC_ERRP, 1, 1); reduce(p, nullptr, N, sc + SC_ERRp, 0); reduce(d, nullptr, Ptot, sc + SC_ERRd, 0); allreduce(sc + SC_ERRd, 1, 1); }
   void objectives() {
-    reduce(c, x, Ptot, sc + SC_CX, 0); reduce(Cm, Y, tot, sc + SC_CY, 0); reduce(b, y, N, sc + SC_BY, 0);
+    reduce(c, x, Ptot, sc + SC_CX, 0); reduce(Cm, Y, tot, sc + SC_CY, 0); allreduce(sc + SC_CX, 2, 0);   // SC_CX, SC_CY are adjacent
+    reduce(b, y, N, sc + SC_BY, 0);
     scalar(4);
   }
   void scalar(int phase, const num* M = nullptr, const num* dM = nullptr, const double* lam = nullptr, int which = 0) {
@@ -549,7 +642,7 @@ template <int NL> struct Solver : SolverBase {
     objectives();
     trace_vectors(tr, Y);
     residuals(); errors(); scalar(5);
-    reduce(X, Y, tot, sc + SC_D0, 0);
+    reduce(X, Y, tot, sc + SC_D0, 0); allreduce(sc + SC_D0, 1, 0);
     pull_info();
     h_dobj = hinfo[INFO_DOBJ + 10]; h_pobj = hinfo[INFO_POBJ + 10]; h_gap = hinfo[INFO_GAP + 10];
     h_derr = std::max(hinfo[INFO_ERRP], hinfo[INFO_ERRp]); h_perr = hinfo[INFO_ERRd]; h_pdfeas = hflags[FL_PDFEAS];
@@ -593,20 +686,21 @@ template <int NL> struct Solver : SolverBase {
     nlaunch++, k_scatter_upper<NL><<<(unsigned)(((int64_t)np * np + 127) / 128), 128, 0, st>>>(np, b0.d_plist, b0.Sd, c0.S, c0.P);
   }
   void decomposition(int e0) {
-    for (auto& c0 : cl) { zero(c0.S, (int64_t)c0.P * c0.P);
+    for (auto& c0 : cl) { if (!c0.owned) continue; zero(c0.S, (int64_t)c0.P * c0.P);
       for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_block_dense(c0, b0); else schur_block_lowrank(c0, b0); }
       if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); }
     CK(cudaEventRecord(ev[e0], st));
-    for (auto& c0 : cl) chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S);
+    for (auto& c0 : cl) if (c0.owned) chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S);
     CK(cudaEventRecord(ev[e0 + 1], st));
     if (N > 0) {
-      bool first = true;
-      for (auto& c0 : cl) { if (c0.P == 0) continue;
+      for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
         mm(c0.Minv, c0.P, c0.B, N, c0.P, N, c0.P, c0.LinvB, N); }                                       // LinvB = L^-1 B  (:1258)
       CK(cudaEventRecord(ev[e0 + 2], st));
-      for (auto& c0 : cl) { if (c0.P == 0) continue;
+      zero(Q, (int64_t)N * N);
+      for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
         split_cols(tA, c0.LinvB, N, c0.P, N, use_tc(N, N, c0.P) ? 1 : 0);
-        gemm(tA, 0, tA, 0, N, N, Q, N, first ? 0 : 2, Q, N); first = false; }                            // Q = sum LinvB^T LinvB  (:1268-1269)
+        gemm(tA, 0, tA, 0, N, N, Q, N, 2, Q, N); }                                                       // Q = sum LinvB^T LinvB  (:1268-1269)
+      allreduce(Q, (int64_t)N * N, 0);                                                                  // the only cross-cluster coupling
       CK(cudaEventRecord(ev[e0 + 3], st));
       chol(Q, N, N, QMinv, N, CLRS_ERR_CHOL_Q);
     } else { CK(cudaEventRecord(ev[e0 + 2], st)); CK(cudaEventRecord(ev[e0 + 3], st)); }
@@ -621,13 +715,14 @@ template <int NL> struct Solver : SolverBase {
     trace_vectors(tr, dY);
     if (Ptot) nlaunch++, k_vec_rhs<NL><<<(Ptot + 127) / 128, 128, 0, st>>>(Ptot, dx, d, tr);                                                          // rhs_x = -d - <A_*, Z>
     // block elimination  (:1527-1582)
-    if (N > 0) copy(dy, p, N);
-    for (auto& c0 : cl) { if (c0.P == 0) continue;
+    if (N > 0) zero(tmpU, N);
+    for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
       nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, dx + c0.off, c0.t, 1, 0);                              // t_j = L_j^-1 rhs_j
-      if (N > 0) nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, dy, -1, 1); }                                     // dy -= LinvB_j^T t_j
-    if (N > 0) { nlaunch++, k_gemv_n<NL><<<(N * 32 + 255) / 256, 256, 0, st>>>(N, N, QMinv, N, dy, tmpN, 1, 0);
+      if (N > 0) nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                                     // u += LinvB_j^T t_j
+    if (N > 0) { allreduce(tmpU, N, 0); addsub(dy, p, 1, tmpU, -1, N);                                                                       // dy = p - sum_j u_j
+      nlaunch++, k_gemv_n<NL><<<(N * 32 + 255) / 256, 256, 0, st>>>(N, N, QMinv, N, dy, tmpN, 1, 0);
       nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(N, N, QMinv, N, tmpN, dy, 1, 0); }                                                       // dy = Q^-1 dy
-    for (auto& c0 : cl) { if (c0.P == 0) continue;
+    for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
       if (N > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
       nlaunch++, k_gemv_t<NL><<<(c0.P + 127) / 128, 128, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, c0.t, dx + c0.off, 1, 0); }                                 // dx_j = L_j^-T t_j
     weighted_A(dX, dx); addsub(dX, dX, 1, P, 1, tot);                                                                                       // dX = P + sum dx_p A_p
@@ -643,7 +738,7 @@ template <int NL> struct Solver : SolverBase {
       split_cols(tB, dM + b0->off, n, n, n, b0->lay); gemm(b0->MS, 0, tB, 0, n, n, U + b0->off, n);             // U = L^-1 dM
       split_rows(tA, U + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->MS, 0, n, n, T1 + b0->off, n); }            // T = U L^-T
     nlaunch++, k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, T1, Td);
-    nlaunch++, k_min_eig<<<(unsigned)blk.size(), 256, 0, st>>>(eigT, lam);
+    if (!blk.empty()) nlaunch++, k_min_eig<<<(unsigned)blk.size(), 256, 0, st>>>(eigT, lam);
   }
 
   int check_status() { return hflags[FL_STATUS]; }
@@ -678,7 +773,7 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaEventRecord(ev[8], st));
     direction();                                                      // predictor
     CK(cudaEventRecord(ev[9], st));
-    reduce(X, dY, tot, sc + SC_D1, 0); reduce(dX, Y, tot, sc + SC_D2, 0); reduce(dX, dY, tot, sc + SC_D3, 0);
+    reduce(X, dY, tot, sc + SC_D1, 0); reduce(dX, Y, tot, sc + SC_D2, 0); reduce(dX, dY, tot, sc + SC_D3, 0); allreduce(sc + SC_D1, 3, 0);   // D1..D3 adjacent
     errors(); scalar(1);
     CK(cudaEventRecord(ev[10], st));
     for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); split_cols(tB, dY + b0->off, n, n, n, b0->lay); gemm(tA, 0, tB, 0, n, n, T1 + b0->off, n); }
@@ -687,10 +782,10 @@ template <int NL> struct Solver : SolverBase {
     direction();                                                      // corrector
     CK(cudaEventRecord(ev[12], st));
     // step lengths: X reuses its factor of this iteration (X is unchanged); Y is factored here
-    step_eigs(Minv, dX, lamX, false); scalar(2, X, dX, lamX, SC_ALPHAD);
+    step_eigs(Minv, dX, lamX, false); scalar(2, X, dX, lamX); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAD);
     copy(L, Y, tot);
     for (Block* b0 : blk) { const int n = b0->n; if (n > 1) chol(L + b0->off, n, n, Minv + b0->off, n, CLRS_ERR_CHOL_STEP); }
-    step_eigs(Minv, dY, lamY, false); scalar(2, Y, dY, lamY, SC_ALPHAP);
+    step_eigs(Minv, dY, lamY, false); scalar(2, Y, dY, lamY); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAP);
     scalar(3);
     CK(cudaEventRecord(ev[13], st));
     // the step  (src/solver.jl:485-495)
@@ -699,7 +794,8 @@ template <int NL> struct Solver : SolverBase {
     nlaunch++, k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, X, dX, sc + SC_ALPHAD);
     nlaunch++, k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, Y, dY, sc + SC_ALPHAP);
     objectives();
-    reduce(X, Y, tot, sc + SC_D0, 0);                                  // <X,Y> of the new iterate for the next mu
+    reduce(X, Y, tot, sc + SC_D0, 0); allreduce(sc + SC_D0, 1, 0);     // <X,Y> of the new iterate for the next mu
+    allreduce_flags();                                                 // a failed Cholesky on any rank stops every rank
     CK(cudaEventRecord(ev[14], st));
     pull_info();
     if (int s = check_status()) {
@@ -728,13 +824,21 @@ template <int NL> struct Solver : SolverBase {
     objectives(); num h[SC_COUNT]; CK(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
     mpn_to_wire(d_, h[SC_DOBJ]); mpn_to_wire(p_, h[SC_POBJ]); mpn_to_wire(g_, h[SC_GAP]); return 0;
   }
-  int64_t matrix_count() const override { return tot; }
+  int64_t matrix_count() const override { return gtot; }
+  // x: all constraints; X, Y: all blocks of the SDP in (j,l) order (global layout).  A sharded handle reads/writes the
+  // parts it owns; get_state leaves the others untouched (the host merges the ranks' outputs).
   int set_state(const void* x_, const void* X_, const void* y_, const void* Y_) override {
     auto up = [&](num* dst, const void* w, size_t n) { if (!w || !n) return; std::vector<num> h(n); for (size_t i = 0; i < n; i++) wire_to_mpn(h[i], (const char*)w + i * wire_size()); CK(cudaMemcpyAsync(dst, h.data(), n * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); };
-    up(x, x_, Ptot); up(X, X_, tot); up(y, y_, N); up(Y, Y_, tot); initial_quantities(); return 0;
+    if (x_) for (auto& c0 : cl) if (c0.owned) up(x + c0.off, (const char*)x_ + (size_t)c0.off * wire_size(), c0.P);
+    up(y, y_, N);
+    for (Block* b0 : blk) { size_t nn = (size_t)b0->n * b0->n; if (X_) up(X + b0->off, (const char*)X_ + (size_t)b0->goff * wire_size(), nn); if (Y_) up(Y + b0->off, (const char*)Y_ + (size_t)b0->goff * wire_size(), nn); }
+    initial_quantities(); return 0;
   }
   int get_state(void* x_, void* X_, void* y_, void* Y_) override {
-    if (x_) download_wire(x_, x, Ptot); if (X_) download_wire(X_, X, tot); if (y_ && N) download_wire(y_, y, N); if (Y_) download_wire(Y_, Y, tot); return 0;
+    if (x_) for (auto& c0 : cl) if (c0.owned && c0.P) download_wire((char*)x_ + (size_t)c0.off * wire_size(), x + c0.off, c0.P);
+    if (y_ && N) download_wire(y_, y, N);
+    for (Block* b0 : blk) { size_t nn = (size_t)b0->n * b0->n; if (X_) download_wire((char*)X_ + (size_t)b0->goff * wire_size(), X + b0->off, nn); if (Y_) download_wire((char*)Y_ + (size_t)b0->goff * wire_size(), Y + b0->off, nn); }
+    return 0;
   }
   // ---- standalone kernels -----------------------------------------------------------------
   int mp_gemm(int M, int N_, int K, const void* A, const void* B, void* C, int path, double* ms) override {
@@ -778,10 +882,12 @@ template <int NL> struct Solver : SolverBase {
       tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(3584, sa.Kp); a.k0 = 0; a.BN = BN; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp; a.dbg = nullptr;
       dim3 grid((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1);
       CK(cudaEventRecord(e1, st));
-      for (int r = 0; r < reps; r++) nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
+      const bool ts = getenv("CLRS_TC_TS") != nullptr; if (ts) { const int ntn2 = (N_ + 111) / 112; BN = ((N_ + ntn2 - 1) / ntn2 + 15) & ~15; if (BN > 112) BN = 112; mB = make_map(sb, BN); a.BN = BN; grid = dim3((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1); }
+      tc::ArgsTS pts; pts.g = a; pts.planesA = sa.planes; pts.nvecA = sa.nvec; pts.KpA = sa.Kp;
+      for (int r = 0; r < reps; r++) { if (ts) nlaunch++, tc::k_gemm_ts<<<grid, tc::TS_THREADS, tc::TS_SMEM_BYTES, st>>>(mB, pts); else nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a); }
       CK(cudaEventRecord(e2, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
       cudaEventElapsedTime(&t12, e1, e2); out[2] = t12 / reps;
-      if (getenv("CLRS_TC_TIMELINE")) { long long* dd = dalloc<long long>(128); a.dbg = dd; tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a); long long hh[128]; CK(cudaMemcpyAsync(hh, dd, sizeof(hh), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+      if (getenv("CLRS_TC_TIMELINE") && !ts) { long long* dd = dalloc<long long>(128); a.dbg = dd; tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a); long long hh[128]; CK(cudaMemcpyAsync(hh, dd, sizeof(hh), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
         fprintf(stderr, "group: wait_epi  mma_issue  | epilogue: wait_mma  work   (cycles, CTA 0)\n"); for (int gg = 0; gg < (NS + 3) / 4; gg++) { long long* q = hh + gg * 8; fprintf(stderr, "%2d: %8lld %8lld | %8lld %8lld   t0=%lld\n", gg, q[1] - q[0], q[2] - q[1], q[4] - q[3], q[5] - q[4], q[0] - hh[0]); } }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
@@ -790,6 +896,7 @@ template <int NL> struct Solver : SolverBase {
   }
   int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) override {
     std::string w(what); const num* src = nullptr; int64_t n = 0;
+    if (j >= 0 && j < (int)cl.size() && !cl[j].owned && (w == "S" || w == "LinvB" || w.size() > 2 || w == "X" || w == "Y" || w == "R" || w == "P" || w == "L")) return -1;
     if (w == "S") { src = cl[j].S; n = (int64_t)cl[j].P * cl[j].P; } else if (w == "LinvB") { src = cl[j].LinvB; n = (int64_t)cl[j].P * N; }
     else if (w == "Q") { src = Q; n = (int64_t)N * N; } else if (w == "d") { src = d; n = Ptot; } else if (w == "p") { src = p; n = N; }
     else if (w == "dx") { src = dx; n = Ptot; } else if (w == "dy") { src = dy; n = N; } else if (w == "x") { src = x; n = Ptot; } else if (w == "y") { src = y; n = N; }
@@ -834,8 +941,12 @@ int clrs_get_state(clrs_handle* h, void* x, void* X, void* y, void* Y) { GUARD(h
 int64_t clrs_state_matrix_count(const clrs_handle* h) { return h->s->matrix_count(); }
 int clrs_iterate(clrs_handle* h, clrs_iter_info* info) { GUARD(h, return h->s->iterate(info);) }
 int clrs_get_objectives(clrs_handle* h, void* d, void* p, void* g) { GUARD(h, return h->s->get_objectives(d, p, g);) }
-int clrs_comm_init(clrs_handle* h, int32_t rank, int32_t nranks, const void*) { if (nranks == 1 && rank == 0) return CLRS_OK; h->err = "multi-GPU sharding is not built in this round"; return CLRS_ERR_UNSUPPORTED; }
-int clrs_comm_unique_id(void* out128) { memset(out128, 0, 128); return CLRS_OK; }
+int clrs_comm_init(clrs_handle* h, int32_t rank, int32_t nranks, const void* uid) { GUARD(h, return h->s->comm_init(rank, nranks, uid);) }
+int clrs_comm_unique_id(void* out128) { std::string e; memset(out128, 0, 128); if (!g_nccl.load(e)) return CLRS_ERR_CUDA; return g_nccl.GetUniqueId(out128) == 0 ? CLRS_OK : CLRS_ERR_CUDA; }
+int clrs_cluster_owner(clrs_handle* h, int32_t j) { return h->s->owner_of(j); }
+int clrs_partition_clusters(int32_t J, const double* weight, int32_t nranks, int32_t* owner) {
+  if (J < 0 || nranks < 1) return CLRS_ERR_ARG; std::vector<double> w(weight, weight + J); std::vector<int> o; partition_clusters(w, nranks, o); for (int j = 0; j < J; j++) owner[j] = o[j]; return CLRS_OK;
+}
 int clrs_mp_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, const void* A, const void* B, void* C, int32_t path, double* ms) { GUARD(h, return h->s->mp_gemm(M, N, K, A, B, C, path, ms);) }
 int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L) { GUARD(h, return h->s->mp_cholesky(n, A, L);) }
 void clrs_profile(clrs_handle* h, int32_t enable) { h->s->profile(enable); }

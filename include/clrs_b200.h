@@ -164,8 +164,10 @@ int clrs_add_lowrank_term(clrs_handle* h, int32_t j, int32_t l, int32_t r, int32
 int clrs_finalize(clrs_handle* h);
 
 /* ---- state ------------------------------------------------------------ */
-/* x: sum_j P_j numbers; y: N numbers; X, Y: for every block in (j,l) order an
- * n x n row-major matrix, concatenated.  NULL pointers are skipped. */
+/* x: sum_j P_j numbers; y: N numbers; X, Y: for every block of the SDP in (j,l) order an
+ * n x n row-major matrix, concatenated.  NULL pointers are skipped.  A handle that shares the
+ * SDP with other ranks (clrs_comm_init) reads / writes only the clusters it owns: the caller
+ * passes the full arrays to every rank and merges what the ranks return. */
 int clrs_set_state(clrs_handle* h, const void* x, const void* X, const void* y, const void* Y);
 int clrs_get_state(clrs_handle* h, void* x, void* X, void* y, void* Y);
 /* total count of numbers in X (= in Y): sum over blocks of n^2 */
@@ -184,6 +186,10 @@ int clrs_get_objectives(clrs_handle* h, void* d_obj, void* p_obj, void* gap);
  * by the host program.  Must be called before clrs_finalize. */
 int clrs_comm_init(clrs_handle* h, int32_t rank, int32_t nranks, const void* nccl_unique_id);
 int clrs_comm_unique_id(void* out128);
+/* rank that owns cluster j after clrs_finalize (LPT on P_j^3 + sum n^3, src/threadinginfo.jl:88,97) */
+int clrs_cluster_owner(clrs_handle* h, int32_t j);
+/* the partitioner itself (host only, no GPU needed): owner[j] for J clusters of the given weights */
+int clrs_partition_clusters(int32_t J, const double* weight, int32_t nranks, int32_t* owner);
 
 /* ---- standalone kernels of the path (parity tests / microbenchmarks) ---- */
 /* C = A * B (M x K times K x N) in multi-limb arithmetic on the device,
