@@ -225,8 +225,8 @@ template <int NL> struct Solver : SolverBase {
       nlaunch++, k_split<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0); }
     else if (kfast) { int64_t tot_ = (int64_t)v.nvec * (s.Kp / 4);
       nlaunch++, k_split_tc<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes, 1); }
-    else { dim3 grid((v.nvec + 31) / 32, s.Kp / 32);
-      nlaunch++, k_split_tc_t<NL><<<grid, 256, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes); }
+    else { constexpr int VT = SplitTCfg<NL>::VT; dim3 grid((v.nvec + VT - 1) / VT, s.Kp / 32);
+      nlaunch++, k_split_tc_t<NL><<<grid, VT * 8, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes); }
   }
   void split_rows(Sliced& s, const num* A, int lda, int M, int K, int lay = 0) { split(s, rows_view(A, lda, M, K), true, lay); }
   void split_cols(Sliced& s, const num* B, int ldb, int K, int N, int lay = 0) { split(s, cols_view(B, ldb, K, N), false, lay); }
@@ -277,7 +277,7 @@ template <int NL> struct Solver : SolverBase {
     CUtensorMap mA = make_map(A, tc::BM), mB = make_map(B, BN);
     // K longer than the int32 headroom (35 slices * K * 2^14 < 2^31), or few tiles with a long K: split K over
     // blockIdx.z (partial results summed in k_tc_recombine), sized to fill whole waves of 148 CTAs
-    const int KMAX = 3584; int tiles = 0;
+    const int KMAX = ((1 << 17) / NS / 128) * 128; int tiles = 0;      // int32 headroom: NS * K * 2^14 < 2^31
     for (int by = 0; by < (M + tc::BM - 1) / tc::BM; by++) for (int bx = 0; bx < (N + BN - 1) / BN; bx++) if (!lower_only || bx * BN <= by * tc::BM + tc::BM - 1) tiles++;
     int nch = (A.Kp + KMAX - 1) / KMAX;
     if (batch == 1 && tiles < 148 && A.Kp >= 1024) { const int waves = (tiles * nch + 147) / 148; nch = std::max(nch, std::min(waves * 148 / tiles, A.Kp / 512)); }
@@ -879,7 +879,7 @@ template <int NL> struct Solver : SolverBase {
     out[0] = t01; out[1] = t12 / reps; out[2] = 0;
     if (lay == 1) {      // kernel alone
       CUtensorMap mA = make_map(sa, tc::BM); const int ntn = (N_ + 127) / 128; int BN = ((N_ + ntn - 1) / ntn + 15) & ~15; if (BN > 128) BN = 128; CUtensorMap mB = make_map(sb, BN);
-      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(3584, sa.Kp); a.k0 = 0; a.BN = BN; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp; a.dbg = nullptr;
+      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(((1 << 17) / NS / 128) * 128, sa.Kp); a.k0 = 0; a.BN = BN; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp; a.dbg = nullptr;
       dim3 grid((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1);
       CK(cudaEventRecord(e1, st));
       const bool ts = getenv("CLRS_TC_TS") != nullptr; if (ts) { const int ntn2 = (N_ + 111) / 112; BN = ((N_ + ntn2 - 1) / ntn2 + 15) & ~15; if (BN > 112) BN = 112; mB = make_map(sb, BN); a.BN = BN; grid = dim3((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1); }
@@ -921,8 +921,8 @@ void clrs_default_options(clrs_options* o) {
 int clrs_create(const clrs_options* opt, clrs_handle** out) {
   clrs_handle* h = new clrs_handle(); h->s = nullptr; *out = h;
   try {
-    if (opt->prec <= 0 || opt->prec > 256) { h->err = "this build supports prec <= 256 bits"; return CLRS_ERR_UNSUPPORTED; }
-    h->s = new Solver<8>(*opt);
+    if (opt->prec <= 0 || opt->prec > 320) { h->err = "this build supports prec <= 320 bits (8 or 10 limbs of 32 bits)"; return CLRS_ERR_UNSUPPORTED; }
+    if (opt->prec <= 256) h->s = new Solver<8>(*opt); else h->s = new Solver<10>(*opt);
   } catch (const std::exception& e) { h->err = e.what(); return CLRS_ERR_CUDA; }
   return CLRS_OK;
 }

@@ -524,11 +524,12 @@ template <int NL> __global__ void k_split_tc(VecView v, const int32_t* E, int Kp
 // Same split for vectors whose entries are NOT contiguous (columns of a row-major matrix): consecutive
 // threads take consecutive vectors so the 40-byte reads coalesce, and the digits go through a
 // shared-memory transpose so each plane row receives full 32-byte segments.
+template <int NL> struct SplitTCfg { static constexpr int VT = (I8Cfg<NL>::NS <= 35) ? 32 : 16; };   // vectors per CTA (static smem <= 48 KiB)
 template <int NL> __global__ void __launch_bounds__(256) k_split_tc_t(VecView v, const int32_t* E, int Kp, int64_t nvec_pitch, uint8_t* planes) {
-  constexpr int NS = I8Cfg<NL>::NS;
-  __shared__ uint32_t sm[NS][32][9];
-  const int vl = threadIdx.x & 31, kl = threadIdx.x >> 5;
-  const int vec = blockIdx.x * 32 + vl, k4 = blockIdx.y * 8 + kl;
+  constexpr int NS = I8Cfg<NL>::NS, VT = SplitTCfg<NL>::VT;
+  __shared__ uint32_t sm[NS][VT][9];
+  const int vl = threadIdx.x % VT, kl = threadIdx.x / VT;            // blockDim.x = VT * 8
+  const int vec = blockIdx.x * VT + vl, k4 = blockIdx.y * 8 + kl;
   uint32_t w[NS];
 #pragma unroll
   for (int t = 0; t < NS; t++) w[t] = 0;
@@ -548,8 +549,8 @@ template <int NL> __global__ void __launch_bounds__(256) k_split_tc_t(VecView v,
 #pragma unroll
   for (int t = 0; t < NS; t++) sm[t][vl][kl] = w[t];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < NS * 32; idx += 256) {
-    const int t = idx >> 5, vv = idx & 31, vec2 = blockIdx.x * 32 + vv;
+  for (int idx = threadIdx.x; idx < NS * VT; idx += VT * 8) {
+    const int t = idx / VT, vv = idx % VT, vec2 = blockIdx.x * VT + vv;
     if (vec2 < v.nvec) {
       uint4* dst = (uint4*)(planes + ((int64_t)t * nvec_pitch + vec2) * Kp + 32 * blockIdx.y);
       dst[0] = make_uint4(sm[t][vv][0], sm[t][vv][1], sm[t][vv][2], sm[t][vv][3]);

@@ -280,3 +280,22 @@ def test_dense_schur_equals_hadamard_identity_at_full_size():
             row = [mpmath.fsum(Xinv[i, k] * Xw[k, j] for k in range(n)) for j in range(n)]
             assert max(abs(v - (1 if j == i else 0)) for j, v in enumerate(row)) < mpmath.mpf(10) ** -50
     s.close()
+
+
+def test_prec_300_uses_ten_limbs_and_matches_oracle():
+    """prec = 300 (the reference's setting for the sphere-packing family, test/runtests_solver.jl:21):
+    the 10-limb instantiation; both arms reach gap 1e-30 here."""
+    sdp = workloads.sphere_packing(8, 7, [Fraction(1, 2), Fraction(1, 2)], prec=300)
+    dev = solvesdp(sdp, lib="device", duality_gap_threshold=1e-30)
+    ref = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-30)
+    assert dev.status == ref.status == "Optimal", (dev, ref)
+    with mpmath.workprec(500):
+        assert abs(dev.p_obj - ref.p_obj) <= TOL_OBJ * abs(ref.p_obj)
+        assert abs(dev.d_obj - ref.d_obj) <= TOL_OBJ * abs(ref.d_obj)
+    assert abs(dev.iterations - ref.iterations) <= 1
+
+
+def test_prec_300_dense_path_known_answer():
+    n = 9
+    dev = solvesdp(workloads.maxcut(workloads.laplacian_complete(n), prec=300), lib="device", duality_gap_threshold=1e-40)
+    assert dev.status == "Optimal" and abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -35
