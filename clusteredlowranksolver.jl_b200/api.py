@@ -258,10 +258,13 @@ class Solver:
         fn = self._fn("profile"); fn.restype = None; fn(self.h, C.c_int32(int(enable)))
 
     def profile_get(self):
-        out = (C.c_double * 7)()
+        out = (C.c_double * 10)()
         fn = self._fn("profile_get"); fn.restype = None; fn(self.h, out)
-        return {"dp4a_ms": out[0], "dp4a_mp_flops": out[1], "dp4a_launches": int(out[2]), "tc_ms": out[3],
-                "tc_mp_flops": out[4], "tc_launches": int(out[5]), "kernel_launches": int(out[6])}
+        names = ("dp4a", "tc_small", "tc_large")
+        d = {"kernel_launches": int(out[9])}
+        for i, nm in enumerate(names):
+            d[nm] = {"ms": out[3 * i], "mp_flops": out[3 * i + 1], "launches": int(out[3 * i + 2])}
+        return d
 
     def last_iteration_ms(self) -> float:
         fn = self._fn("last_iteration_ms"); fn.restype = C.c_double

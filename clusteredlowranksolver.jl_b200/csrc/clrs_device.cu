@@ -220,6 +220,7 @@ template <int NL> struct Solver : SolverBase {
   static VecView cols_view(const num* B, int ldb, int K, int N) { VecView v; v.base = B; v.bstride = 0; v.vper = N > 0 ? N : 1; v.sv = 1; v.sk = ldb; v.nvec = N; v.K = K; return v; }
   void split(Sliced& s, const VecView& v, bool kfast, int lay = 0) {
     ensure(s, v.nvec, v.K, lay); if (v.nvec == 0 || v.K == 0) return;
+    if (lay == 0 && v.K <= 512) { nlaunch++, k_split_warp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl); return; }
     nlaunch++, k_vec_exp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 255) / 256), 256, 0, st>>>(v, s.E);
     if (lay == 0) { int64_t tot_ = (int64_t)v.nvec * s.K4;
       nlaunch++, k_split<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0); }
@@ -249,7 +250,7 @@ template <int NL> struct Solver : SolverBase {
       dim3 grid((N + 15) / 16, (M + 15) / 16, batch);
       nlaunch++, k_gemm_dp4a<NL><<<grid, 256, 0, st>>>(g);
     }
-    prof_end(2.0 * M * N * (double)A.K * batch * (lower_only ? 0.5 : 1.0), A.lay);
+    prof_end(2.0 * M * N * (double)A.K * batch * (lower_only ? 0.5 : 1.0), A.lay == 0 ? 0 : ((double)M * N >= 1e6 ? 2 : 1));
   }
   // ---- tensor-core path ---------------------------------------------------------------
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -280,7 +281,7 @@ template <int NL> struct Solver : SolverBase {
     const int KMAX = ((1 << 17) / NS / 128) * 128; int tiles = 0;      // int32 headroom: NS * K * 2^14 < 2^31
     for (int by = 0; by < (M + tc::BM - 1) / tc::BM; by++) for (int bx = 0; bx < (N + BN - 1) / BN; bx++) if (!lower_only || bx * BN <= by * tc::BM + tc::BM - 1) tiles++;
     int nch = (A.Kp + KMAX - 1) / KMAX;
-    if (batch == 1 && tiles < 148 && A.Kp >= 1024) { const int waves = (tiles * nch + 147) / 148; nch = std::max(nch, std::min(waves * 148 / tiles, A.Kp / 512)); }
+    if (batch == 1 && tiles < 148 && A.Kp >= 256) { const int waves = (tiles * nch + 147) / 148; nch = std::max(nch, std::min(waves * 148 / tiles, A.Kp >= 2048 ? A.Kp / 512 : A.Kp / 128)); }
     if (nch > 1 && batch != 1) throw CudaError("gemm_tc: split-K with a batch is not supported");
     int kch = ((A.Kp + nch - 1) / nch + 127) & ~127; nch = (A.Kp + kch - 1) / kch;
     const size_t outs2 = (size_t)std::max(batch, nch) * M * Npitch;
@@ -295,11 +296,17 @@ template <int NL> struct Solver : SolverBase {
     nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1);
   }
   // ---- optional per-launch GEMM profile (bench.py roofline) ------------------------------------
-  bool prof_on = false; cudaEvent_t pe0 = nullptr, pe1 = nullptr; double prof_ms[2] = {0, 0}, prof_flops[2] = {0, 0}; long prof_n[2] = {0, 0};
+  bool prof_on = false; cudaEvent_t pe0 = nullptr, pe1 = nullptr; double prof_ms[3] = {0, 0, 0}, prof_flops[3] = {0, 0, 0}; long prof_n[3] = {0, 0, 0};   // 0: CUDA-core path, 1: tcgen05 small outputs, 2: tcgen05 outputs >= 1e6 numbers
   void prof_begin() { if (prof_on) CK(cudaEventRecord(pe0, st)); }
   void prof_end(double mp_flops, int lay) { if (!prof_on) return; CK(cudaEventRecord(pe1, st)); CK(cudaEventSynchronize(pe1)); float t = 0; cudaEventElapsedTime(&t, pe0, pe1); prof_ms[lay] += t; prof_flops[lay] += mp_flops; prof_n[lay]++; }
   long nlaunch = 0;
   Sliced tA, tB;    // scratch panels
+  // second execution context (stream + scratch) for work that is independent of the main chain: the Cholesky of Y
+  // for the step length only needs the iterate, so it runs beside the Schur assembly.  swap_ctx() exchanges the
+  // members the helpers use; kernels capture their pointers at enqueue time, so swapping while enqueuing is safe.
+  cudaStream_t st2 = nullptr; Sliced tA2, tB2; num* chol_W2 = nullptr; size_t chol_W_cap2 = 0; uint8_t* tc_bytes2 = nullptr; int32_t* tc_top2 = nullptr; size_t tc_cap2 = 0;
+  cudaEvent_t evY0 = nullptr, evY1 = nullptr; num *LY = nullptr, *MinvY = nullptr;
+  void swap_ctx() { std::swap(st, st2); std::swap(tA, tA2); std::swap(tB, tB2); std::swap(chol_W, chol_W2); std::swap(chol_W_cap, chol_W_cap2); std::swap(tc_bytes, tc_bytes2); std::swap(tc_top, tc_top2); std::swap(tc_cap, tc_cap2); }
   // C = op(D, A*B) for plain matrices A (M x K, lda), B (K x N, ldb)
   void mm(const num* A, int lda, const num* B, int ldb, int M, int N, int K, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0) {
     const int lay = use_tc(M, N, K) ? 1 : 0;
@@ -381,7 +388,7 @@ template <int NL> struct Solver : SolverBase {
     std::vector<num> hC;
     // dense
     std::vector<int> dense_p; std::vector<std::vector<num>> dense_A;
-    int np = 0; int32_t* d_plist = nullptr; num* Aall = nullptr; Sliced AallB, AallV; num* T1 = nullptr; num* T2 = nullptr; num* Sd = nullptr; Sliced T1S, T2V;
+    int np = 0; int32_t* d_plist = nullptr; num* Aall = nullptr; int32_t* nz_start = nullptr; int32_t* nz_idx = nullptr; int32_t* nzT_start = nullptr; int32_t* nzT_p = nullptr; int64_t nnz = 0; Sliced AallB, AallV; num* T1 = nullptr; num* T2 = nullptr; num* Sd = nullptr; Sliced T1S, T2V;
     // low rank
     std::vector<HTerm> lr;
     int nP = 0; int32_t* lr_plist = nullptr; int32_t* lr_tstart = nullptr; LRTermDev* lr_terms = nullptr; num* lr_lam = nullptr;
@@ -391,7 +398,7 @@ template <int NL> struct Solver : SolverBase {
     struct RS { int cnt = 0; int32_t* elist = nullptr; num* H = nullptr; Sliced Hs; num* G = nullptr; };
     std::vector<RS> rs;                                                                     // index r*m+s, s <= r
     // per-iteration cached panels (layout `lay`: 1 = tensor-core panels for large blocks)
-    Sliced YS, XiS, MS; int lay = 0;
+    Sliced YS, XiS, MS, MSY; int lay = 0;
   };
   struct Clu { int owner = 0; bool owned = true; int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; int off = 0; };
   std::vector<Clu> cl; std::vector<Block*> blk;   // blk: all blocks in (j,l) order
@@ -414,7 +421,7 @@ template <int NL> struct Solver : SolverBase {
     int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError("no CUDA device: libclrs_b200 has no CPU fallback");
     CK(cudaSetDevice(o.device)); cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, o.device));
     if (pr.major < 10) throw CudaError("an sm_100 device is required");
-    CK(cudaStreamCreate(&st));
+    CK(cudaStreamCreate(&st)); CK(cudaStreamCreate(&st2)); CK(cudaEventCreateWithFlags(&evY0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY1, cudaEventDisableTiming));
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
     CK(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -426,9 +433,10 @@ template <int NL> struct Solver : SolverBase {
     partial = dalloc<num>(256); sc = dalloc<num>(SC_COUNT); flags = dalloc<int>(FL_COUNT); dinfo = dalloc<double>(32);
   }
   ~Solver() {
-    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(st); cudaStreamSynchronize(st2);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-    owned_sliced.push_back(&tA); owned_sliced.push_back(&tB);
+    owned_sliced.push_back(&tA); owned_sliced.push_back(&tB); owned_sliced.push_back(&tA2); owned_sliced.push_back(&tB2);
+    if (tc_bytes2) cudaFree(tc_bytes2); if (tc_top2) cudaFree(tc_top2); cudaEventDestroy(evY0); cudaEventDestroy(evY1); cudaStreamDestroy(st2);
     for (Sliced* s : owned_sliced) { if (s->sl) cudaFree(s->sl); if (s->E) cudaFree(s->E); if (s->planes) cudaFree(s->planes); }
     if (tc_bytes) cudaFree(tc_bytes); if (tc_top) cudaFree(tc_top); if (pe0) cudaEventDestroy(pe0); if (pe1) cudaEventDestroy(pe1);
     for (void* p : allocs) cudaFree(p);
@@ -481,7 +489,7 @@ template <int NL> struct Solver : SolverBase {
       for (auto& b0 : c0.blocks) { Ksum += b0.n; b0.goff = gtot; gtot += (int64_t)b0.n * b0.n; if (c0.owned) { b0.off = tot; tot += (int64_t)b0.n * b0.n; blk.push_back(&b0); } } }
     std::vector<int64_t> boff; std::vector<int32_t> bn; for (Block* b0 : blk) { boff.push_back(b0->off); bn.push_back(b0->n); } boff.push_back(tot);
     d_boff = upload(boff); d_bn = upload(bn); bt.off = d_boff; bt.n = d_bn; bt.nblocks = (int)blk.size();
-    num** flat[] = {&X, &Y, &Cm, &L, &Minv, &Xi, &R, &P, &dX, &dY, &T1, &TXY, &U};
+    num** flat[] = {&X, &Y, &Cm, &L, &Minv, &Xi, &R, &P, &dX, &dY, &T1, &TXY, &U, &LY, &MinvY};
     for (auto f : flat) *f = dalloc<num>(tot);
     { std::vector<num> hC(tot); for (Block* b0 : blk) std::copy(b0->hC.begin(), b0->hC.end(), hC.begin() + b0->off); CK(cudaMemcpyAsync(Cm, hC.data(), tot * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
     x = dalloc<num>(Ptot); d = dalloc<num>(Ptot); dx = dalloc<num>(Ptot); tr = dalloc<num>(Ptot);
@@ -510,11 +518,17 @@ template <int NL> struct Solver : SolverBase {
   }
   int finalize_block(Clu& c0, Block& b0) {
     const int n = b0.n, m = b0.m, dl = b0.delta;
-    own(b0.YS); own(b0.XiS); own(b0.MS); b0.lay = use_tc(n, n, n) ? 1 : 0;
+    own(b0.YS); own(b0.XiS); own(b0.MS); own(b0.MSY); b0.lay = use_tc(n, n, n) ? 1 : 0;
     if (b0.high_rank) {
       b0.np = (int)b0.dense_p.size();
       std::vector<int32_t> pl(b0.dense_p.begin(), b0.dense_p.end()); b0.d_plist = upload(pl);
       std::vector<num> all((size_t)b0.np * n * n); for (int i = 0; i < b0.np; i++) std::copy(b0.dense_A[i].begin(), b0.dense_A[i].end(), all.begin() + (size_t)i * n * n);
+      { // nonzero structure of the A_p (their zero entries contribute exact zeros to <A_p,Z> and sum_p x_p A_p):
+        // per p the list of nonzero positions, and per position the list of p that are nonzero there
+        std::vector<int32_t> st(b0.np + 1, 0), idx; std::vector<std::vector<int32_t>> byel((size_t)n * n);
+        for (int i = 0; i < b0.np; i++) { for (int e = 0; e < n * n; e++) if (all[(size_t)i * n * n + e].sign != 0) { idx.push_back(e); byel[e].push_back(i); } st[i + 1] = (int32_t)idx.size(); }
+        std::vector<int32_t> tst((size_t)n * n + 1, 0), tp; for (int e = 0; e < n * n; e++) { for (int i : byel[e]) tp.push_back(i); tst[e + 1] = (int32_t)tp.size(); }
+        b0.nnz = (int64_t)idx.size(); b0.nz_start = upload(st); b0.nz_idx = upload(idx); b0.nzT_start = upload(tst); b0.nzT_p = upload(tp); }
       b0.Aall = upload(all); b0.dense_A.clear(); b0.dense_A.shrink_to_fit();
       b0.T1 = dalloc<num>((size_t)b0.np * n * n); b0.T2 = dalloc<num>((size_t)b0.np * n * n); b0.Sd = dalloc<num>((size_t)b0.np * b0.np);
       own(b0.AallB); own(b0.AallV); own(b0.T1S); own(b0.T2V);
@@ -578,7 +592,7 @@ template <int NL> struct Solver : SolverBase {
     for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
       if (!c0.owned) continue;
       num* M = dst + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; const num* aj = a + c0.off;
-      if (b0.high_rank) { nlaunch++, k_weighted_dense<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, aj, M); continue; }
+      if (b0.high_rank) { nlaunch++, k_weighted_dense<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(b0.d_plist, b0.Aall, (int64_t)n * n, b0.nzT_start, b0.nzT_p, aj, M); continue; }
       zero(M, (int64_t)n * n);
       for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { auto& q = b0.rs[r * m + s]; if (q.cnt == 0) continue;
         nlaunch++, k_weighted_cols<NL><<<(q.cnt * dl + 127) / 128, 128, 0, st>>>(q.cnt, q.elist, b0.lr_terms, b0.lr_lam, aj, MatRef{b0.V[r], b0.u_r[r]}, dl, q.G, q.cnt);
@@ -593,7 +607,7 @@ template <int NL> struct Solver : SolverBase {
     for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
       if (!c0.owned) continue;
       const num* Zb = Z + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; num* oj = out + c0.off;
-      if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, Zb, oj); continue; }
+      if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, b0.nz_start, b0.nz_idx, Zb, oj); continue; }
       if (b0.nP == 0) continue;
       for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { if (b0.rs[r * m + s].cnt == 0) continue;
         split_rows(tA, Zb + (int64_t)r * dl * n + (int64_t)s * dl, n, dl, dl); gemm(tA, 0, b0.Vs[r], 0, dl, b0.u_r[r], b0.ZV[r * m + s], b0.u_r[r]); }
@@ -604,7 +618,7 @@ template <int NL> struct Solver : SolverBase {
   void trace_pairings(num* out) {
     zero(out, Ptot);
     for (auto& c0 : cl) for (auto& b0 : c0.blocks) { if (!c0.owned) continue; num* oj = out + c0.off;
-      if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)b0.n * b0.n, Y + b0.off, oj); continue; }
+      if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)b0.n * b0.n, b0.nz_start, b0.nz_idx, Y + b0.off, oj); continue; }
       if (b0.nP) nlaunch++, k_trace_pairings<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BY, b0.m, oj); }
   }
   // P, d, p  (compute_residuals!, src/solver.jl:863-918); `tr` must hold <A_*, Y>
@@ -616,7 +630,7 @@ template <int NL> struct Solver : SolverBase {
     if (N > 0) for (auto& c0 : cl) if (c0.owned && c0.P) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.B, N, y, d + c0.off, -1, 1);
     // p = +-b - sum_j B_j^T x_j   (partial sums over the owned clusters, combined over the ranks)
     if (N > 0) { zero(p, N);
-      for (auto& c0 : cl) if (c0.owned && c0.P) nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1);
+      for (auto& c0 : cl) if (c0.owned && c0.P) nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1);
       allreduce(p, N, 0);
       addsub(p, p, 1, b, maximize ? 1 : -1, N); }
   }
@@ -718,13 +732,13 @@ template <int NL> struct Solver : SolverBase {
     if (N > 0) zero(tmpU, N);
     for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
       nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, dx + c0.off, c0.t, 1, 0);                              // t_j = L_j^-1 rhs_j
-      if (N > 0) nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                                     // u += LinvB_j^T t_j
+      if (N > 0) nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                                     // u += LinvB_j^T t_j
     if (N > 0) { allreduce(tmpU, N, 0); addsub(dy, p, 1, tmpU, -1, N);                                                                       // dy = p - sum_j u_j
       nlaunch++, k_gemv_n<NL><<<(N * 32 + 255) / 256, 256, 0, st>>>(N, N, QMinv, N, dy, tmpN, 1, 0);
-      nlaunch++, k_gemv_t<NL><<<(N + 127) / 128, 128, 0, st>>>(N, N, QMinv, N, tmpN, dy, 1, 0); }                                                       // dy = Q^-1 dy
+      nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(N, N, QMinv, N, tmpN, dy, 1, 0); }                                                       // dy = Q^-1 dy
     for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
       if (N > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
-      nlaunch++, k_gemv_t<NL><<<(c0.P + 127) / 128, 128, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, c0.t, dx + c0.off, 1, 0); }                                 // dx_j = L_j^-T t_j
+      nlaunch++, k_gemv_t<NL><<<(c0.P + 31) / 32, 256, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, c0.t, dx + c0.off, 1, 0); }                                 // dx_j = L_j^-T t_j
     weighted_A(dX, dx); addsub(dX, dX, 1, P, 1, tot);                                                                                       // dX = P + sum dx_p A_p
     for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // dX Y
     addsub(T1, R, 1, T1, -1, tot);
@@ -732,13 +746,15 @@ template <int NL> struct Solver : SolverBase {
     nlaunch++, k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
   }
   // lambda_min( L^-1 dM L^-T ) per block in Float64  (compute_step_length, src/solver.jl:1620-1693); Mi holds L^-1
-  void step_eigs(const num* Mi, const num* dM, double* lam, bool have_MS) {
+  void step_eigs(const num* Mi, const num* dM, double* lam, bool forY) {
     for (Block* b0 : blk) { const int n = b0->n; if (n == 1) continue;
-      if (!have_MS) split_rows(b0->MS, Mi + b0->off, n, n, n, b0->lay);
-      split_cols(tB, dM + b0->off, n, n, n, b0->lay); gemm(b0->MS, 0, tB, 0, n, n, U + b0->off, n);             // U = L^-1 dM
-      split_rows(tA, U + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->MS, 0, n, n, T1 + b0->off, n); }            // T = U L^-T
+      Sliced& ms = forY ? b0->MSY : b0->MS;                                                             // rows of L^-1 (Y's are split on the side stream)
+      if (!forY) split_rows(ms, Mi + b0->off, n, n, n, b0->lay);
+      split_cols(tB, dM + b0->off, n, n, n, b0->lay); gemm(ms, 0, tB, 0, n, n, U + b0->off, n);          // U = L^-1 dM
+      split_rows(tA, U + b0->off, n, n, n, b0->lay); gemm(tA, 0, ms, 0, n, n, T1 + b0->off, n); }         // T = U L^-T
     nlaunch++, k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, T1, Td);
-    if (!blk.empty()) nlaunch++, k_min_eig<<<(unsigned)blk.size(), 256, 0, st>>>(eigT, lam);
+    if (!blk.empty()) { int maxn = 1; for (Block* b0 : blk) maxn = std::max(maxn, b0->n);
+      nlaunch++, k_min_eig<<<(unsigned)blk.size(), maxn <= 32 ? 128 : (maxn <= 128 ? 256 : EIG_THREADS), 0, st>>>(eigT, lam); }
   }
 
   int check_status() { return hflags[FL_STATUS]; }
@@ -757,6 +773,11 @@ template <int NL> struct Solver : SolverBase {
     int reason = 0; if (host_terminate(reason)) { info->stop = reason; return 0; }
     CK(cudaMemsetAsync(flags + FL_STOP, 0, 2 * sizeof(int), st));
     CK(cudaEventRecord(ev[0], st));
+    // side stream: Cholesky of Y and L_Y^-1 for the step length (Y does not change until the step at the end)
+    CK(cudaEventRecord(evY0, st)); swap_ctx(); CK(cudaStreamWaitEvent(st, evY0, 0));
+    copy(LY, Y, tot);
+    for (Block* b0 : blk) { const int n = b0->n; if (n > 1) { chol(LY + b0->off, n, n, MinvY + b0->off, n, CLRS_ERR_CHOL_STEP); split_rows(b0->MSY, MinvY + b0->off, n, n, n, b0->lay); } }
+    CK(cudaEventRecord(evY1, st)); swap_ctx();
     scalar(0);                                                        // mu, mu_p  (SC_D0 = <X,Y> is kept current)
     // R = mu_p I - X Y
     for (Block* b0 : blk) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n, b0->lay); split_rows(tA, X + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); }
@@ -783,9 +804,8 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaEventRecord(ev[12], st));
     // step lengths: X reuses its factor of this iteration (X is unchanged); Y is factored here
     step_eigs(Minv, dX, lamX, false); scalar(2, X, dX, lamX); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAD);
-    copy(L, Y, tot);
-    for (Block* b0 : blk) { const int n = b0->n; if (n > 1) chol(L + b0->off, n, n, Minv + b0->off, n, CLRS_ERR_CHOL_STEP); }
-    step_eigs(Minv, dY, lamY, false); scalar(2, Y, dY, lamY); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAP);
+    CK(cudaStreamWaitEvent(st, evY1, 0));
+    step_eigs(MinvY, dY, lamY, true); scalar(2, Y, dY, lamY); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAP);
     scalar(3);
     CK(cudaEventRecord(ev[13], st));
     // the step  (src/solver.jl:485-495)
@@ -860,8 +880,8 @@ template <int NL> struct Solver : SolverBase {
     return 0;
   }
   double last_ms = 0;
-  void profile(int enable) override { prof_on = enable != 0; for (int i = 0; i < 2; i++) { prof_ms[i] = 0; prof_flops[i] = 0; prof_n[i] = 0; } nlaunch = 0; }
-  void profile_get(double* o) override { o[0] = prof_ms[0]; o[1] = prof_flops[0]; o[2] = (double)prof_n[0]; o[3] = prof_ms[1]; o[4] = prof_flops[1]; o[5] = (double)prof_n[1]; o[6] = (double)nlaunch; }
+  void profile(int enable) override { prof_on = enable != 0; for (int i = 0; i < 3; i++) { prof_ms[i] = 0; prof_flops[i] = 0; prof_n[i] = 0; } nlaunch = 0; }
+  void profile_get(double* o) override { for (int i = 0; i < 3; i++) { o[3 * i] = prof_ms[i]; o[3 * i + 1] = prof_flops[i]; o[3 * i + 2] = (double)prof_n[i]; } o[9] = (double)nlaunch; }
   double last_iteration_ms() override { return last_ms; }
   // kernel-only timing of C = A*B on device-generated operands: out = {split ms, gemm ms per rep (kernel + recombine), kernel-only ms per rep}
   int bench_gemm(int M, int N_, int K, int reps, int path, double* out) override {
@@ -950,7 +970,7 @@ int clrs_partition_clusters(int32_t J, const double* weight, int32_t nranks, int
 int clrs_mp_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, const void* A, const void* B, void* C, int32_t path, double* ms) { GUARD(h, return h->s->mp_gemm(M, N, K, A, B, C, path, ms);) }
 int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L) { GUARD(h, return h->s->mp_cholesky(n, A, L);) }
 void clrs_profile(clrs_handle* h, int32_t enable) { h->s->profile(enable); }
-void clrs_profile_get(clrs_handle* h, double* out7) { h->s->profile_get(out7); }
+void clrs_profile_get(clrs_handle* h, double* out10) { h->s->profile_get(out10); }
 double clrs_last_iteration_ms(clrs_handle* h) { return h->s->last_iteration_ms(); }
 int clrs_bench_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, int32_t reps, int32_t path, double* out3) { GUARD(h, return h->s->bench_gemm(M, N, K, reps, path, out3);) }
 int64_t clrs_debug_get(clrs_handle* h, const char* what, int32_t j, int32_t l, void* out, int64_t cap) { try { return h->s->debug_get(what, j, l, out, cap); } catch (const std::exception& e) { h->err = e.what(); return -1; } }

@@ -148,12 +148,15 @@ template <int NL> __global__ void k_gemv_n(int M, int K, const mpn<NL>* A, int l
   }
   if (lane == 0) { acc.sign *= alpha; if (beta) { mpn<NL> o = y[warp]; o.sign *= beta; mp_add(acc, acc, o); } y[warp] = acc; }
 }
-// y[j] = beta*y[j] + alpha * sum_k A[k,j] x[k]; one thread per column, rows in chunks across blockIdx.y is not needed for N <= few thousand
-template <int NL> __global__ void k_gemv_t(int K, int N, const mpn<NL>* A, int lda, const mpn<NL>* x, mpn<NL>* y, int alpha, int beta) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= N) return;
+// y[j] = beta*y[j] + alpha * sum_k A[k,j] x[k]; CTA = 32 columns x 8 row phases (coalesced along j), tree sum over the phases
+template <int NL> __global__ void __launch_bounds__(256) k_gemv_t(int K, int N, const mpn<NL>* A, int lda, const mpn<NL>* x, mpn<NL>* y, int alpha, int beta) {
+  __shared__ mpn<NL> part[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, j = blockIdx.x * 32 + tx;
   mpn<NL> acc; mp_zero(acc);
-  for (int k = 0; k < K; k++) { mpn<NL> a = A[(int64_t)k * lda + j], b = x[k]; mp_mul(a, a, b); mp_add(acc, acc, a); }
-  acc.sign *= alpha; if (beta) { mpn<NL> o = y[j]; o.sign *= beta; mp_add(acc, acc, o); } y[j] = acc;
+  if (j < N) for (int k = ty; k < K; k += 8) { mpn<NL> a = A[(int64_t)k * lda + j], b = x[k]; mp_mul(a, a, b); mp_add(acc, acc, a); }
+  part[ty][tx] = acc; __syncthreads();
+  for (int s2 = 4; s2 > 0; s2 >>= 1) { if (ty < s2) { mpn<NL> a = part[ty][tx], b = part[ty + s2][tx]; mp_add(a, a, b); part[ty][tx] = a; } __syncthreads(); }
+  if (ty == 0 && j < N) { acc = part[0][tx]; acc.sign *= alpha; if (beta) { mpn<NL> o = y[j]; o.sign *= beta; mp_add(acc, acc, o); } y[j] = acc; }
 }
 
 // ---------------------------------------------------------------------------
@@ -267,6 +270,40 @@ template <int NL> __global__ void k_split(VecView v, const int32_t* E, int K4, i
   int4* dst = (int4*)(sl + ((int64_t)vec * K4 + k4) * NSP);
 #pragma unroll
   for (int t = 0; t < NSP / 4; t++) dst[t] = make_int4((int)w[4 * t], (int)w[4 * t + 1], (int)w[4 * t + 2], (int)w[4 * t + 3]);
+}
+
+// Small panels (the Cholesky panels, pairing bases, ...): exponent and split in ONE launch, one warp per vector,
+// one entry per lane; the four digits of a word are gathered with shuffles.
+template <int NL> __global__ void k_split_warp(VecView v, int32_t* E, int K4, int32_t* sl) {
+  constexpr int NS = I8Cfg<NL>::NS, NSP = I8Cfg<NL>::NSP;
+  const int vec = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (vec >= v.nvec) return;
+  const mpn<NL>* p = (const mpn<NL>*)v.base + vec_off(v, vec);
+  int32_t e = I8_EXP_NONE;
+  for (int k = lane; k < v.K; k += 32) { const mpn<NL>* q = p + (int64_t)k * v.sk; if (q->sign != 0) e = max(e, q->exp); }
+  for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+  if (lane == 0) E[vec] = e;
+  for (int kb = 0; kb < 4 * K4; kb += 32) {
+    const int k = kb + lane;
+    int8_t dg[NS];
+    if (k < v.K) { mpn<NL> a = p[(int64_t)k * v.sk]; i8_split<NL>(a, e, dg); }
+    else {
+#pragma unroll
+      for (int t = 0; t < NS; t++) dg[t] = 0;
+    }
+    const int k4 = k >> 2; const bool writer = (lane & 3) == 0 && k4 < K4;
+    int32_t* dst = sl + ((int64_t)vec * K4 + k4) * NSP;
+#pragma unroll
+    for (int t = 0; t < NS; t++) {
+      const uint32_t b = (uint32_t)(uint8_t)dg[t];
+      const uint32_t w = b | (__shfl_down_sync(0xffffffffu, b, 1) << 8) | (__shfl_down_sync(0xffffffffu, b, 2) << 16) | (__shfl_down_sync(0xffffffffu, b, 3) << 24);
+      if (writer) dst[t] = (int32_t)w;
+    }
+    if (writer) {
+#pragma unroll
+      for (int t = NS; t < NSP; t++) dst[t] = 0;
+    }
+  }
 }
 
 struct GemmArgs {
@@ -424,19 +461,20 @@ template <int NL> __global__ void k_weighted_cols(int cnt, const int32_t* elist,
   mpn<NL> c = x[t.p], l = lam[t.lam], v = ((const mpn<NL>*)V.p)[(int64_t)a * V.ld + t.colV];
   mp_mul(c, c, l); mp_mul(c, c, v); G[(int64_t)a * ldg + e] = c;
 }
-// dense constraint matrices: M += sum_p x[p] A_p (zero entries skipped), src/solver.jl:1422-1426
-template <int NL> __global__ void k_weighted_dense(int np, const int32_t* plist, const mpn<NL>* Aall, int64_t nn, const mpn<NL>* x, mpn<NL>* M) {
+// dense constraint matrices: M = sum_p x[p] A_p (src/solver.jl:1422-1426); per entry only the p whose A_p is
+// nonzero there are visited (precomputed lists), in ascending p like the reference
+template <int NL> __global__ void k_weighted_dense(const int32_t* plist, const mpn<NL>* Aall, int64_t nn, const int32_t* tstart, const int32_t* tp, const mpn<NL>* x, mpn<NL>* M) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
     mpn<NL> acc; mp_zero(acc);
-    for (int p = 0; p < np; p++) { const mpn<NL>* a = Aall + (int64_t)p * nn + i; if (a->sign == 0) continue; mpn<NL> v = *a, c = x[plist[p]]; mp_mul(v, v, c); mp_add(acc, acc, v); }
+    for (int q = tstart[i]; q < tstart[i + 1]; q++) { const int p = tp[q]; mpn<NL> v = Aall[(int64_t)p * nn + i], c = x[plist[p]]; mp_mul(v, v, c); mp_add(acc, acc, v); }
     M[i] = acc;
   }
 }
-// out[plist[p]] += <A_p, Z>  (dense trace, src/solver.jl:1303-1305); one CTA per p
-template <int NL> __global__ void k_trace_dense(int np, const int32_t* plist, const mpn<NL>* Aall, int64_t nn, const mpn<NL>* Z, mpn<NL>* out) {
+// out[plist[p]] += <A_p, Z>  (dense trace, src/solver.jl:1303-1305); one CTA per p over the nonzero entries of A_p
+template <int NL> __global__ void k_trace_dense(int np, const int32_t* plist, const mpn<NL>* Aall, int64_t nn, const int32_t* nzstart, const int32_t* nzidx, const mpn<NL>* Z, mpn<NL>* out) {
   extern __shared__ unsigned char smraw[]; mpn<NL>* sh = (mpn<NL>*)smraw;
   const int p = blockIdx.x; mpn<NL> acc; mp_zero(acc);
-  for (int64_t i = threadIdx.x; i < nn; i += blockDim.x) { const mpn<NL>* a = Aall + (int64_t)p * nn + i; if (a->sign == 0) continue; mpn<NL> v = *a, z = Z[i]; mp_mul(v, v, z); mp_add(acc, acc, v); }
+  for (int q = nzstart[p] + threadIdx.x; q < nzstart[p + 1]; q += blockDim.x) { const int e = nzidx[q]; mpn<NL> v = Aall[(int64_t)p * nn + e], z = Z[e]; mp_mul(v, v, z); mp_add(acc, acc, v); }
   block_reduce_sum(acc, sh);
   if (threadIdx.x == 0) { mpn<NL> o = out[plist[p]]; mp_add(o, o, acc); out[plist[p]] = o; }
 }
@@ -466,8 +504,9 @@ __device__ inline double tridiag_min_eig(const double* al, const double* be, int
   return 0.5 * (lo + hi);
 }
 #define EIG_MMAX 320
-__global__ void __launch_bounds__(256) k_min_eig(const EigTask* tasks, double* lam) {
-  __shared__ double sh[256]; __shared__ double al[EIG_MMAX], be[EIG_MMAX]; __shared__ double s_lam, s_prev; __shared__ int s_done, s_close;
+#define EIG_THREADS 1024
+__global__ void __launch_bounds__(EIG_THREADS) k_min_eig(const EigTask* tasks, double* lam) {
+  __shared__ double sh[EIG_THREADS]; __shared__ double al[EIG_MMAX], be[EIG_MMAX]; __shared__ double s_lam, s_prev; __shared__ int s_done, s_close;
   const EigTask t = tasks[blockIdx.x]; const int n = t.n, tid = threadIdx.x;
   if (n == 1) { if (tid == 0) lam[blockIdx.x] = t.T[0]; return; }
   double* V = t.V;                                         // column c at V + c*n
@@ -483,7 +522,12 @@ __global__ void __launch_bounds__(256) k_min_eig(const EigTask* tasks, double* l
     double* v = V + (int64_t)c * n; double* w = V + (int64_t)(c + 1) * n;
     // w = T v  (row per thread; T symmetric so column access is coalesced)
     double a_part = 0;
-    for (int i = tid; i < n; i += blockDim.x) { double s = 0; for (int k = 0; k < n; k++) s += t.T[(int64_t)k * n + i] * v[k]; w[i] = s; a_part += s * v[i]; }
+    for (int i = tid >> 5; i < n; i += (blockDim.x >> 5)) {       // one warp per row (T is symmetric: row i is contiguous)
+      double s = 0; for (int k = tid & 31; k < n; k += 32) s += t.T[(int64_t)i * n + k] * v[k];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if ((tid & 31) == 0) { w[i] = s; a_part += s * v[i]; }
+    }
+    __syncthreads();
     double alpha = block_sum_d(a_part, sh);
     // full reorthogonalisation (twice)
     for (int pass = 0; pass < 2; pass++) for (int q = 0; q <= c; q++) {

@@ -209,9 +209,10 @@ int64_t clrs_debug_get(clrs_handle* h, const char* what, int32_t j, int32_t l, v
 /* enable != 0: time every multi-precision GEMM launch with CUDA events on the
  * library's stream and count kernel launches; resets the counters. */
 void clrs_profile(clrs_handle* h, int32_t enable);
-/* out7 = { ms, mp_flops, launches } of the CUDA-core int8 path, the same three
- * for the tcgen05 path, then the number of kernel launches since clrs_profile. */
-void clrs_profile_get(clrs_handle* h, double* out7);
+/* out10 = { ms, mp_flops (2*M*N*K), launches } for three classes of GEMM launches — CUDA-core
+ * int8 path, tcgen05 with fewer than 1e6 outputs, tcgen05 with at least 1e6 outputs — then
+ * the number of kernel launches since clrs_profile. */
+void clrs_profile_get(clrs_handle* h, double* out10);
 /* Kernel benchmark of C = A*B (M x K times K x N) on device-generated operands.
  * out3 = { split ms, ms per product (kernel + recombine), ms per tcgen05 kernel launch alone }. */
 int clrs_bench_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, int32_t reps, int32_t path, double* out3);
