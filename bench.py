@@ -230,8 +230,8 @@ def main():
     dom = max(classes, key=lambda c: prof[c]["ms"])
     r = rl(dom)
     roofline = {"bound": "tensor", "kernel": r["kernel"], "achieved": r["achieved"], "peak": 2 * bf16,
-                "unit": "TOP/s (int8, canonical 2*M*N*K*528 per 256-bit GEMM)", "frac": r["frac"], "traffic": 2.6e9 if dom == "tc_large" else None,
-                "traffic_note": "dram read+write bytes per launch of the 90000x300x300 product, ncu --set full (profiles/)",
+                "unit": "TOP/s (int8, canonical 2*M*N*K*528 per 256-bit GEMM)", "frac": r["frac"], "traffic": 2.93e9 if dom == "tc_large" else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of the 90000x300x300 product, ncu --set full (profiles/r01_tc_kernel_ncu_full.txt); algorithmic 2.08e9",
                 "peak_source": peak_src, "launches": r["launches"], "avg_launch_ms": r["avg_launch_ms"], "gemm_share_of_step": r["share_of_step"],
                 "other_gemm_classes": {c: rl(c) for c in classes if c != dom}}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K,
