@@ -125,7 +125,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--n", type=int, default=300, help="graph size (300 = the BASELINE config)")
+    ap.add_argument("--size", dest="n", type=int, default=300, help="graph size (300 = the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-path", type=int, default=0)
     args = ap.parse_args()

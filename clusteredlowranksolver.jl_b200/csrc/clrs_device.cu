@@ -188,6 +188,7 @@ struct SolverBase {
   virtual double last_iteration_ms() = 0;
   virtual int bench_gemm(int M, int N, int K, int reps, int path, double* out) = 0;
   virtual int comm_init(int rank, int nranks, const void* uid) = 0;
+  virtual int selftest() = 0;
   virtual int owner_of(int j) = 0;
   size_t wire_size() const { return 16 + 8 * (size_t)((prec + 63) / 64); }
 };
@@ -883,6 +884,13 @@ template <int NL> struct Solver : SolverBase {
   void profile(int enable) override { prof_on = enable != 0; for (int i = 0; i < 3; i++) { prof_ms[i] = 0; prof_flops[i] = 0; prof_n[i] = 0; } nlaunch = 0; }
   void profile_get(double* o) override { for (int i = 0; i < 3; i++) { o[3 * i] = prof_ms[i]; o[3 * i + 1] = prof_flops[i]; o[3 * i + 2] = (double)prof_n[i]; } o[9] = (double)nlaunch; }
   double last_iteration_ms() override { return last_ms; }
+  // device self-test: warp-cooperative arithmetic (mpw.cuh) against the single-thread routines on random operands; returns mismatches
+  int selftest() override {
+    const int n = 4096; mpn<8>* a = dalloc<mpn<8>>(n); mpn<8>* b2 = dalloc<mpn<8>>(n); int* mm = dalloc<int>(1);
+    nlaunch++, k_fill_random<8><<<16, 256, 0, st>>>(n, a, 77, 40); nlaunch++, k_fill_random<8><<<16, 256, 0, st>>>(n, b2, 5, 40);
+    nlaunch++, k_selftest_mpw<<<n * 32 / 256, 256, 0, st>>>(n, a, b2, mm);
+    int h = -1; CK(cudaMemcpyAsync(&h, mm, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); return h;
+  }
   // kernel-only timing of C = A*B on device-generated operands: out = {split ms, gemm ms per rep (kernel + recombine), kernel-only ms per rep}
   int bench_gemm(int M, int N_, int K, int reps, int path, double* out) override {
     num* dA = dalloc<num>((size_t)M * K); num* dB = dalloc<num>((size_t)K * N_); num* dC = dalloc<num>((size_t)M * N_);
@@ -964,6 +972,7 @@ int clrs_get_objectives(clrs_handle* h, void* d, void* p, void* g) { GUARD(h, re
 int clrs_comm_init(clrs_handle* h, int32_t rank, int32_t nranks, const void* uid) { GUARD(h, return h->s->comm_init(rank, nranks, uid);) }
 int clrs_comm_unique_id(void* out128) { std::string e; memset(out128, 0, 128); if (!g_nccl.load(e)) return CLRS_ERR_CUDA; return g_nccl.GetUniqueId(out128) == 0 ? CLRS_OK : CLRS_ERR_CUDA; }
 int clrs_cluster_owner(clrs_handle* h, int32_t j) { return h->s->owner_of(j); }
+int clrs_debug_selftest(clrs_handle* h) { try { return h->s->selftest(); } catch (const std::exception& e) { h->err = e.what(); return -1; } }
 int clrs_partition_clusters(int32_t J, const double* weight, int32_t nranks, int32_t* owner) {
   if (J < 0 || nranks < 1) return CLRS_ERR_ARG; std::vector<double> w(weight, weight + J); std::vector<int> o; partition_clusters(w, nranks, o); for (int j = 0; j < J; j++) owner[j] = o[j]; return CLRS_OK;
 }

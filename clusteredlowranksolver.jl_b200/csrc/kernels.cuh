@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include "mpf.cuh"
 #include "i8split.cuh"
+#include "mpw.cuh"
 
 // ---------------------------------------------------------------------------
 // block table for flat kernels over block-diagonal storage
@@ -176,6 +177,7 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
   mpn<NL>* Ms = Ls + 32 * 32;                             // its inverse
   mpn<NL>* rinv = Ms + 32 * 32;                           // 1/L[c][c]
   mpn<NL>* dpiv = rinv + 32;                              // pivots before the square root
+  mpn<NL>* Pb = dpiv + 32;                                // 32 x 32 products of the inverse rows
   __shared__ int bad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int idx = tid; idx < 32 * 32; idx += POTRF_THREADS) { const int i = idx >> 5, j = idx & 31; mpn<NL> a; mp_zero(a); if (i < nb && j <= i) a = A[(int64_t)i * lda + j]; As[idx] = a; mp_zero(Ls[idx]); mp_zero(Ms[idx]); }
@@ -183,48 +185,86 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
   __syncthreads();
   if (tid == 0) { mpn<NL> a = As[0]; if (a.sign <= 0) { bad = 1; mp_set_i32(a, 1); } dpiv[0] = a; mpn<NL> r; mp_rsqrt(r, a); rinv[0] = r; }
   __syncthreads();
+  // roles by warp: 0-15 inverse rows, 16-22 trailing update, 23 pivot chain (the scheduler favours the highest
+  // warp id on an SM sub-partition, and the pivot chain is the critical path)
   for (int c = 0; c < nb; c++) {
-    if (warp == 0) {
+    if (warp == 23) {
       // ---- pivot chain: d_{c+1} = a_{c+1,c+1} - l_{c+1,c}^2 (columns < c already applied), r_{c+1} = d^-1/2
-      if (lane == 0 && c + 1 < nb) {
-        mpn<NL> l, d; mp_mul(l, As[(c + 1) * 32 + c], rinv[c]); mp_mul(l, l, l); mp_sub(d, As[(c + 1) * 32 + c + 1], l);
-        if (d.sign <= 0) { bad = 1; mp_set_i32(d, 1); }
-        dpiv[c + 1] = d; mpn<NL> r; mp_rsqrt(r, d); rinv[c + 1] = r;
+      if (c + 1 < nb) {
+        if constexpr (NL == 8) {
+          // the whole warp works on one number at a time (mpw.cuh): ~4x shorter critical path than one thread
+          wnum l = w_mul(w_load(&As[(c + 1) * 32 + c]), w_load(&rinv[c]));
+          wnum d = w_sub(w_load(&As[(c + 1) * 32 + c + 1]), w_mul(l, l));
+          if (d.sign <= 0) { if (lane == 0) bad = 1; mpn<8> one; mp_set_i32(one, 1); d = w_from(one); }
+          w_store(&dpiv[c + 1], d);
+          w_store(&rinv[c + 1], w_rsqrt(d));
+        } else if (lane == 0) {
+          mpn<NL> l, d; mp_mul(l, As[(c + 1) * 32 + c], rinv[c]); mp_mul(l, l, l); mp_sub(d, As[(c + 1) * 32 + c + 1], l);
+          if (d.sign <= 0) { bad = 1; mp_set_i32(d, 1); }
+          dpiv[c + 1] = d; mpn<NL> r; mp_rsqrt(r, d); rinv[c + 1] = r;
+        }
       }
-    } else if (warp < 8) {
+    } else if (warp >= 16) {
       // ---- column c of the factor, then the trailing update with it
-      const int ut = tid - 32;                            // 0..223
+      const int ut = tid - 512;                           // 0..223
       if (ut == 0) { mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[c * 32 + c] = sq; }
       for (int i = c + 1 + ut; i < nb; i += 224) { mpn<NL> a; mp_mul(a, As[i * 32 + c], rinv[c]); Ls[i * 32 + c] = a; }
       asm volatile("bar.sync 1, 224;" ::: "memory");
       const int w = nb - c - 1;
-      for (int idx = ut; idx < w * w; idx += 224) {
-        const int i = c + 1 + idx / w, j = c + 1 + idx % w;
-        if (j <= i && !(i == c + 1 && j == c + 1)) { mpn<NL> a = As[i * 32 + j], t; mp_mul(t, Ls[i * 32 + c], Ls[j * 32 + c]); mp_sub(a, a, t); As[i * 32 + j] = a; }
+      for (int idx = ut + 1; idx < w * (w + 1) / 2; idx += 224) {                // lower triangle only; idx 0 = (c+1,c+1) belongs to the pivot chain
+        int ii = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((ii + 1) * (ii + 2) / 2 <= idx) ii++; while (ii * (ii + 1) / 2 > idx) ii--;
+        const int i = c + 1 + ii, j = c + 1 + (idx - ii * (ii + 1) / 2);
+        mpn<NL> a = As[i * 32 + j], t; mp_mul(t, Ls[i * 32 + c], Ls[j * 32 + c]); mp_sub(a, a, t); As[i * 32 + j] = a;
       }
     } else {
-      // ---- row c of the inverse: M[c][c] = r_c, M[c][j] = -r_c sum_{k=j}^{c-1} L[c][k] M[k][j]
-      const int iw = warp - 8;                            // 0..15
-      if (iw == 0 && lane == 0) Ms[c * 32 + c] = rinv[c];
-      for (int j = iw; j < c; j += 16) {
-        mpn<NL> acc; mp_zero(acc);
-        if (lane >= j && lane < c) mp_mul(acc, Ls[c * 32 + lane], Ms[lane * 32 + j]);
-        for (int o = 16; o > 0; o >>= 1) {
-          mpn<NL> other;
-#pragma unroll
-          for (int q = 0; q < NL; q++) other.l[q] = __shfl_down_sync(0xffffffffu, acc.l[q], o);
-          other.exp = __shfl_down_sync(0xffffffffu, acc.exp, o); other.sign = __shfl_down_sync(0xffffffffu, acc.sign, o);
-          mp_add(acc, acc, other);
-        }
-        if (lane == 0) { mp_mul(acc, acc, rinv[c]); acc.sign = -acc.sign; Ms[c * 32 + j] = acc; }
+      // ---- row c of the inverse: M[c][c] = r_c, M[c][j] = -r_c sum_{k=j}^{c-1} L[c][k] M[k][j]   (16 warps)
+      // products packed over the triangle (j <= k < c) one per thread, then a 5-level tree over k per column
+      // through shared memory (named barrier 2 among the 512 threads of this role)
+      if (tid == 0) Ms[c * 32 + c] = rinv[c];
+      const int np = c * (c + 1) / 2;
+      if (tid < np) {
+        int k = (int)((sqrtf(8.0f * tid + 1.0f) - 1.0f) * 0.5f); while ((k + 1) * (k + 2) / 2 <= tid) k++; while (k * (k + 1) / 2 > tid) k--;
+        const int j = tid - k * (k + 1) / 2;                                   // 0 <= j <= k < c
+        mpn<NL> t; mp_mul(t, Ls[c * 32 + k], Ms[k * 32 + j]); Pb[j * 32 + (k - j)] = t;   // column j, position k - j
       }
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      for (int sdist = 16; sdist > 0; sdist >>= 1) {
+        const int j = tid / sdist, kk = tid % sdist;                           // c * sdist <= 496 threads
+        if (j < c && kk + sdist < c - j) { mpn<NL> x = Pb[j * 32 + kk], y = Pb[j * 32 + kk + sdist]; mp_add(x, x, y); Pb[j * 32 + kk] = x; }
+        asm volatile("bar.sync 2, 512;" ::: "memory");
+      }
+      if (tid < c) { mpn<NL> x; mp_mul(x, Pb[tid * 32], rinv[c]); x.sign = -x.sign; Ms[c * 32 + tid] = x; }
     }
     __syncthreads();                                      // (element (c+1,c+1) lives on in dpiv; its As copy is not read again)
   }
   for (int idx = tid; idx < nb * nb; idx += POTRF_THREADS) { const int i = idx / nb, j = idx % nb; A[(int64_t)i * lda + j] = Ls[i * 32 + j]; Minv[(int64_t)i * ldm + j] = Ms[i * 32 + j]; }
   if (tid == 0 && bad) atomicCAS(status, 0, code);
 }
-#define POTRF_SMEM(NL) ((3 * 32 * 32 + 64) * sizeof(mpn<NL>))
+#define POTRF_SMEM(NL) ((4 * 32 * 32 + 64) * sizeof(mpn<NL>))
+
+// self-test of the warp-cooperative arithmetic against the single-thread routines (bit for bit); one warp per sample
+__global__ void k_selftest_mpw(int n, const mpn<8>* a, const mpn<8>* b, int* mismatches) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= n) return;
+  mpn<8> x = a[s], y = b[s], ref, got;
+  mp_mul(ref, x, y); got = w_to(w_mul(w_from(x), w_from(y)));
+  bool bad = got.sign != ref.sign || (ref.sign != 0 && (got.exp != ref.exp));
+  for (int i = 0; i < 8; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
+  mpn<8> ax = x; ax.sign = ax.sign ? 1 : 0;
+  if (ax.sign) { mp_rsqrt(ref, ax); got = w_to(w_rsqrt(w_from(ax))); bad = bad || got.exp != ref.exp; for (int i = 0; i < 8; i++) bad = bad || got.l[i] != ref.l[i]; }
+  mp_sub(ref, x, y); got = w_to(w_sub(w_from(x), w_from(y)));
+  bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < 8; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
+  // cancellation cases: b equal to a except in limb (s mod 8), same exponent, both signs; and a +/- a
+  mpn<8> y2 = x; y2.l[s & 7] ^= (uint32_t)(s * 2654435761u) | 1u; y2.l[7] |= 0x80000000u;
+  for (int sg = -1; sg <= 1; sg += 2) {
+    y2.sign = x.sign * sg; mp_sub(ref, x, y2); got = w_to(w_sub(w_from(x), w_from(y2)));
+    bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < 8; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
+    mp_add(ref, x, y2); got = w_to(w_add(w_from(x), w_from(y2)));
+    bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < 8; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
+  }
+  mp_sub(ref, x, x); got = w_to(w_sub(w_from(x), w_from(x))); bad = bad || got.sign != 0 || ref.sign != 0;
+  if (bad && lane == 0) atomicAdd(mismatches, 1);
+}
 
 // ---------------------------------------------------------------------------
 // int8 slice pipeline on CUDA cores

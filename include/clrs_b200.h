@@ -200,6 +200,9 @@ int clrs_mp_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K,
 /* lower Cholesky factor of an n x n matrix; returns CLRS_ERR_CHOL_X on a
  * non-positive pivot (src/tools.jl:75-107) */
 int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L);
+/* device self-test of the warp-cooperative arithmetic against the single-thread routines; returns the
+ * number of mismatching samples (0 = pass), -1 on a CUDA error */
+int clrs_debug_selftest(clrs_handle* h);
 /* debug / parity access to intermediates of the last iteration.  what:
  * "S" (cluster j, l ignored), "Xinv","R","P","dX","dY","X","Y" (block j,l),
  * "Q","d","p","dx","dy","x","y","LinvB" (cluster j).  Returns count written. */

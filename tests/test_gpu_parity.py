@@ -304,3 +304,11 @@ def test_prec_300_dense_path_known_answer():
     n = 9
     dev = solvesdp(workloads.maxcut(workloads.laplacian_complete(n), prec=300), lib="device", duality_gap_threshold=1e-40)
     assert dev.status == "Optimal" and abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -35
+
+
+def test_warp_cooperative_arithmetic_selftest(tiny):
+    """mpw.cuh (limb-per-lane multiply with ballot carry resolution, used by the Cholesky pivot chain) must give
+    the same bits as the single-thread routines on 4096 random operand pairs."""
+    fn = tiny.lib.clrs_debug_selftest
+    fn.restype = C.c_int
+    assert fn(tiny.h) == 0
