@@ -356,3 +356,129 @@ def sphere_packing(n, d, r, prec=256):
         bvec[fidx["M"]] = mpf(1)
         return ClusteredSDP(prec=prec, maximize=False, constant=_w(0, prec), b=_w(bvec, prec), clusters=clusters,
                             name=f"sphere_packing(n={n},d={d},Nr={Nr})")
+
+
+# ---------------------------------------------------------------------------
+# config 4: three-point bound for spherical codes (examples/ThreePointBound.jl:45-169)
+# ---------------------------------------------------------------------------
+def gegenbauer_coefficients(d, n):
+    """Coefficient lists (low degree first) of the Gegenbauer polynomials of basis_gegenbauer(d, n, x)."""
+    polys = [[mpf(1)]]
+    if d >= 1:
+        polys.append([mpf(0), mpf(1)])
+    for l in range(2, d + 1):
+        a, b = polys[-1], polys[-2]
+        new = [mpf(0)] * (l + 1)
+        for i, c in enumerate(a):
+            new[i + 1] += mpf(2 * l + n - 4) / (l + n - 3) * c
+        for i, c in enumerate(b):
+            new[i] -= mpf(l - 1) / (l + n - 3) * c
+        polys.append(new)
+    return polys
+
+
+def three_point_bound(n, costheta, d2, d3, prec=256, seed=1935):
+    """three_point_spherical_codes(n, costheta, d2, d3).  One cluster (both constraints share the
+    (:F,k) blocks): dense F_k blocks, rank-1 univariate SOS / a_k blocks, rank-1 and rank-2
+    S_3-invariant trivariate SOS blocks.  The trivariate sample subset is drawn with numpy
+    default_rng(seed) (Julia's shuffle stream cannot be reproduced without Julia)."""
+    with mpmath.workprec(prec + 64):
+        ct = mpf(costheta.numerator) / costheta.denominator if isinstance(costheta, Fraction) else mpf(costheta)
+        N2, N3 = max(d2, d3), d3
+        geg = gegenbauer_coefficients(max(d3, 1), n - 1)
+        floor4 = lambda x: mpf(int(mpmath.floor(10 ** 4 * x))) / 10 ** 4
+
+        def Qf(k, u, v, t):
+            cf = geg[k]
+            return mpmath.fsum(cf[i] * ((1 - u * u) * (1 - v * v)) ** ((k - i) // 2) * (t - u * v) ** i for i in range(len(cf)) if cf[i] != 0)
+
+        def mvec(w, d):
+            return [w ** k for k in range(d + 1)]
+
+        def Smat(k, d, u, v, t):
+            mu, mv, mt = mvec(u, d - k), mvec(v, d - k), mvec(t, d - k)
+            q1, q2, q3 = Qf(k, u, v, t), Qf(k, t, u, v), Qf(k, t, v, u)
+            sz = d - k + 1
+            return [[(q1 * (mv[a] * mu[b] + mu[a] * mv[b]) + q2 * (mt[a] * mu[b] + mu[a] * mt[b]) + q3 * (mt[a] * mv[b] + mv[a] * mt[b])) / 6
+                     for b in range(sz)] for a in range(sz)]
+
+        pw = lambda u: (u + 1) * (ct - u)
+        # ---- samples
+        s1 = [floor4(x) for x in sample_points_chebyshev(2 * N2, -1, 1)]
+        ntri = len([1 for deg in range(2 * N3 + 1) for k in range(deg // 3 + 1) for j in range((deg - 3 * k) // 2 + 1)])
+        cheb = [sample_points_chebyshev(2 * N3 + k, -1, 1) for k in range(3)]
+        grid = [(cheb[0][i], cheb[1][j], cheb[2][k]) for i in range(2 * N3 + 1) for j in range(2 * N3 + 2) for k in range(2 * N3 + 3)]
+        rng = np.random.default_rng(seed)
+        pick = sorted(rng.permutation(len(grid))[:ntri].tolist(), key=lambda i: grid[i])
+        s3 = [tuple(floor4(x) for x in grid[i]) for i in pick]
+        P1, P = len(s1), len(s1) + len(s3)
+        blocks = []
+        # ---- (:F, k): dense blocks in both constraints
+        for k in range(d3 + 1):
+            sz = d3 - k + 1
+            Cm = [[mpf(1) if k == 0 else mpf(0)] * sz for _ in range(sz)]
+            blk = PSDBlock(m=1, delta=sz, high_rank=True, C=_w(Cm, prec), name=("F", k))
+            for p, w in enumerate(s1):
+                blk.dense[p] = _w([[3 * v for v in row] for row in Smat(k, d3, w, w, mpf(1))], prec)
+            for p, (u, v, t) in enumerate(s3):
+                blk.dense[P1 + p] = _w(Smat(k, d3, u, v, t), prec)
+            blocks.append(blk)
+        # ---- (:a, k): 1x1 rank-one blocks, univariate constraint only
+        if d2 >= 0:
+            for k in range(2 * d2 + 1):
+                blk = PSDBlock(m=1, delta=1, high_rank=False, C=_w([[1]], prec), name=("a", k))
+                for p, w in enumerate(s1):
+                    blk.lowrank.append(_rank1(0, 0, p, gegenbauer_values(2 * d2, n, w)[k], [1], prec))
+                blocks.append(blk)
+        # ---- univariate SOS blocks
+        if N2 >= 0:
+            b1 = PSDBlock(m=1, delta=N2 + 1, high_rank=False, C=wire.wire_zeros((N2 + 1, N2 + 1), prec), name=("univariatesos", 1))
+            for p, w in enumerate(s1):
+                b1.lowrank.append(_rank1(0, 0, p, 1, chebyshev_values(2 * N2, w)[:N2 + 1], prec))
+            blocks.append(b1)
+        if N2 >= 1:
+            b2 = PSDBlock(m=1, delta=N2, high_rank=False, C=wire.wire_zeros((N2, N2), prec), name=("univariatesos", 2))
+            for p, w in enumerate(s1):
+                b2.lowrank.append(_rank1(0, 0, p, pw(w), chebyshev_values(2 * N2, w)[:N2], prec))
+            blocks.append(b2)
+        # ---- trivariate invariant SOS blocks
+        basis_idx = [(deg, k, j) for deg in range(N3 + 1) for k in range(deg // 3 + 1) for j in range((deg - 3 * k) // 2 + 1)]
+        equivariants = [([lambda u, v, t: mpf(1)], [0]),
+                        ([lambda u, v, t: (u - v) * (v - t) * (t - u)], [3]),
+                        ([lambda u, v, t: 2 * u - v - t, lambda u, v, t: 2 * v * t - u * t - u * v], [1, 2]),      # eqi = 3, r = 1
+                        ([lambda u, v, t: v - t, lambda u, v, t: u * t - u * v], [1, 2])]                          # eqi = 3, r = 2
+        eq_groups = [[0], [1], [2, 3]]
+        factors = [[mpf(1)], [mpf(1)], [mpf(1) / 2, mpf(3) / 2]]
+        weights = [(lambda u, v, t: mpf(1), 0), (lambda u, v, t: pw(u) + pw(v) + pw(t), 2),
+                   (lambda u, v, t: pw(u) * pw(v) + pw(v) * pw(t) + pw(t) * pw(u), 4), (lambda u, v, t: pw(u) * pw(v) * pw(t), 6),
+                   (lambda u, v, t: 2 * u * v * t + 1 - u * u - v * v - t * t, 3)]
+        for wi, (wf, wdeg) in enumerate(weights):
+            if wdeg > 2 * N3:
+                continue
+            for eqi, rows in enumerate(eq_groups):
+                # which (eq, basis) pairs enter row r
+                sel = [[(e, bi) for e in range(len(equivariants[r][0])) for bi, (deg, _, _) in enumerate(basis_idx)
+                        if wdeg + 2 * equivariants[r][1][e] + 2 * deg <= 2 * N3] for r in rows]
+                sel = [s for s in sel if s]
+                if not sel:
+                    continue
+                rows_used = [r for r, s in zip(rows, [[(e, bi) for e in range(len(equivariants[r][0])) for bi, (deg, _, _) in enumerate(basis_idx)
+                                                      if wdeg + 2 * equivariants[r][1][e] + 2 * deg <= 2 * N3] for r in rows]) if s]
+                delta = len(sel[0])
+                assert all(len(s) == delta for s in sel)
+                blk = PSDBlock(m=1, delta=delta, high_rank=False, C=wire.wire_zeros((delta, delta), prec), name=("trivariatesos", wi, eqi))
+                for p, (u, v, t) in enumerate(s3):
+                    s1v, s2v, s3v = u + v + t, u * v + v * t + u * t, u * v * t
+                    bas = [s1v ** (deg - 3 * k - 2 * j) * s2v ** j * s3v ** k for (deg, k, j) in basis_idx]
+                    wv = wf(u, v, t)
+                    lam, vecs = [], []
+                    for r, s in zip(rows_used, sel):
+                        eqv = [f(u, v, t) for f in equivariants[r][0]]
+                        lam.append(wv * factors[eqi][rows.index(r)])
+                        vecs.append([eqv[e] * bas[bi] for (e, bi) in s])
+                    blk.lowrank.append(LowRankTerm(0, 0, P1 + p, _w(lam, prec), _w(vecs, prec), _w(vecs, prec)))
+                blocks.append(blk)
+        c = _w([-1] * P1 + [0] * len(s3), prec)
+        cl = Cluster(B=wire.wire_zeros((P, 0), prec), c=c, blocks=blocks)
+        return ClusteredSDP(prec=prec, maximize=False, constant=_w(1, prec), b=wire.wire_zeros((0,), prec), clusters=[cl],
+                            name=f"three_point_bound(n={n},d2={d2},d3={d3})")

@@ -312,3 +312,15 @@ def test_warp_cooperative_arithmetic_selftest(tiny):
     fn = tiny.lib.clrs_debug_selftest
     fn.restype = C.c_int
     assert fn(tiny.h) == 0
+
+
+def test_three_point_bound_config4():
+    """BASELINE config 4 at the reference's test size: dense F_k blocks, rank-1 and rank-2 invariant SOS blocks."""
+    sdp = workloads.three_point_bound(4, Fraction(1, 6), -1, 4)
+    dev, _ = _compare(sdp, omega_p=10 ** 3, omega_d=10 ** 3)
+    assert abs(dev.p_obj - 10) < mpmath.mpf(10) ** -24           # test/runtests_solver.jl:26-27
+
+
+def test_three_point_bound_with_univariate_part():
+    """d2 >= 0 adds the 1x1 a_k blocks with sample-dependent eigenvalues."""
+    _compare(workloads.three_point_bound(4, Fraction(1, 6), 3, 3), omega_p=10 ** 3, omega_d=10 ** 3)

@@ -63,3 +63,10 @@ def test_status_codes_and_iteration_limit():
     assert r.error_code == 2 and r.iterations == 5 and r.status != "Optimal"     # src/solver.jl:362-366
     r = solvesdp(workloads.maxcut(workloads.laplacian_cycle(3)), lib="oracle", need_primal_feasible=True)
     assert r.status in ("PrimalFeasible", "Feasible", "NearOptimal", "Optimal") and r.iterations < 30
+
+
+def test_three_point_bound_n4_is_10():                       # test/runtests_solver.jl:26-27, 89-93
+    sdp = workloads.three_point_bound(4, Fraction(1, 6), -1, 4)
+    assert sdp.num_constraints == 50 and len(sdp.clusters[0].blocks) == 19      # P=50, 19 blocks, K=79
+    r = solve(sdp, omega_p=10 ** 3, omega_d=10 ** 3)
+    assert abs(r.p_obj - 10) < mpmath.mpf(10) ** -25
