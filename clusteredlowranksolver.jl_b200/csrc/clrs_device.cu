@@ -354,9 +354,10 @@ template <int NL> struct Solver : SolverBase {
   // ---- blocked Cholesky with explicit factor inverse -----------------------------------
   // A (n x n, lower part read) -> L in place (strict upper zeroed); Minv = L^-1 (lower triangular, full n x n buffer)
   num* chol_W = nullptr; size_t chol_W_cap = 0;
-  void chol(num* A, int lda, int n, num* Minv, int ldm, int code) {
+  // full_inverse: also assemble L^-1 below the diagonal blocks (X and Y blocks: products with L^-1 and X^-1 follow);
+  // otherwise only the inverses of the 32 x 32 diagonal blocks are formed and solves go by block substitution.
+  void chol(num* A, int lda, int n, num* Minv, int ldm, int code, bool full_inverse = true) {
     if (n == 0) return;
-    for (int r = 0; r < n; r++) { (void)r; }
     if (ldm == n) zero(Minv, (int64_t)n * n); else for (int r = 0; r < n; r++) zero(Minv + (int64_t)r * ldm, n);
     for (int k0 = 0; k0 < n; k0 += 32) {
       const int nb = std::min(32, n - k0), rem = n - k0 - nb;
@@ -371,7 +372,7 @@ template <int NL> struct Solver : SolverBase {
     }
     nlaunch++, k_zero_upper<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, A, lda);
     // rows of the inverse below the diagonal blocks: M[i,0:k0] = -inv(L_ii) * (L[i,0:k0] * M[0:k0,0:k0])
-    if (n > 32) {
+    if (full_inverse && n > 32) {
       size_t need = (size_t)32 * n; if (need > chol_W_cap) { chol_W = dalloc<num>(need); chol_W_cap = need; }
       for (int k0 = 32; k0 < n; k0 += 32) {
         const int nb = std::min(32, n - k0);
@@ -379,6 +380,21 @@ template <int NL> struct Solver : SolverBase {
         mm(Minv + (int64_t)k0 * ldm + k0, ldm, chol_W, k0, nb, k0, nb, Minv + (int64_t)k0 * ldm, ldm, 3);
       }
     }
+  }
+  // X = L^-1 B by block forward substitution (approx_solve_tril!, src/solver.jl:1258): X_k = inv(L_kk) (B_k - L[k,0:k0] X[0:k0])
+  num* trsm_R = nullptr; size_t trsm_cap = 0;
+  void trsm_lower(const num* Lf, int ldl, int n, const num* Minv, int ldm, const num* B, int ldb, int ncols, num* Xo, int ldx) {
+    if (n == 0 || ncols == 0) return;
+    size_t need = (size_t)32 * ncols; if (need > trsm_cap) { trsm_R = dalloc<num>(need); trsm_cap = need; }
+    for (int k0 = 0; k0 < n; k0 += 32) {
+      const int nb = std::min(32, n - k0);
+      const num* rhs = B + (int64_t)k0 * ldb; int ldr = ldb;
+      if (k0 > 0) { mm(Lf + (int64_t)k0 * ldl, ldl, Xo, ldx, nb, ncols, k0, trsm_R, ncols, 1, B + (int64_t)k0 * ldb, ldb); rhs = trsm_R; ldr = ncols; }
+      mm(Minv + (int64_t)k0 * ldm + k0, ldm, rhs, ldr, nb, ncols, nb, Xo + (int64_t)k0 * ldx, ldx);
+    }
+  }
+  void trsv(const num* Lf, int ldl, int n, const num* Minv, int ldm, num* xv, bool transposed) {
+    if (n > 0) nlaunch++, k_trsv<NL><<<1, 1024, 0, st>>>(n, Lf, ldl, Minv, ldm, xv, transposed ? 1 : 0);
   }
 
   // ---- problem description -------------------------------------------------------------
@@ -705,11 +721,11 @@ template <int NL> struct Solver : SolverBase {
       for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_block_dense(c0, b0); else schur_block_lowrank(c0, b0); }
       if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); }
     CK(cudaEventRecord(ev[e0], st));
-    for (auto& c0 : cl) if (c0.owned) chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S);
+    for (auto& c0 : cl) if (c0.owned) chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S, false);
     CK(cudaEventRecord(ev[e0 + 1], st));
     if (N > 0) {
       for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
-        mm(c0.Minv, c0.P, c0.B, N, c0.P, N, c0.P, c0.LinvB, N); }                                       // LinvB = L^-1 B  (:1258)
+        trsm_lower(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.B, N, N, c0.LinvB, N); }                             // LinvB = L^-1 B  (:1258)
       CK(cudaEventRecord(ev[e0 + 2], st));
       zero(Q, (int64_t)N * N);
       for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
@@ -717,7 +733,7 @@ template <int NL> struct Solver : SolverBase {
         gemm(tA, 0, tA, 0, N, N, Q, N, 2, Q, N); }                                                       // Q = sum LinvB^T LinvB  (:1268-1269)
       allreduce(Q, (int64_t)N * N, 0);                                                                  // the only cross-cluster coupling
       CK(cudaEventRecord(ev[e0 + 3], st));
-      chol(Q, N, N, QMinv, N, CLRS_ERR_CHOL_Q);
+      chol(Q, N, N, QMinv, N, CLRS_ERR_CHOL_Q, false);
     } else { CK(cudaEventRecord(ev[e0 + 2], st)); CK(cudaEventRecord(ev[e0 + 3], st)); }
     CK(cudaEventRecord(ev[e0 + 4], st));
   }
@@ -732,14 +748,13 @@ template <int NL> struct Solver : SolverBase {
     // block elimination  (:1527-1582)
     if (N > 0) zero(tmpU, N);
     for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
-      nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, dx + c0.off, c0.t, 1, 0);                              // t_j = L_j^-1 rhs_j
-      if (N > 0) nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                                     // u += LinvB_j^T t_j
+      copy(c0.t, dx + c0.off, c0.P); trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, false);                                                    // t_j = L_j^-1 rhs_j
+      if (N > 0) nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                             // u += LinvB_j^T t_j
     if (N > 0) { allreduce(tmpU, N, 0); addsub(dy, p, 1, tmpU, -1, N);                                                                       // dy = p - sum_j u_j
-      nlaunch++, k_gemv_n<NL><<<(N * 32 + 255) / 256, 256, 0, st>>>(N, N, QMinv, N, dy, tmpN, 1, 0);
-      nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(N, N, QMinv, N, tmpN, dy, 1, 0); }                                                       // dy = Q^-1 dy
+      trsv(Q, N, N, QMinv, N, dy, false); trsv(Q, N, N, QMinv, N, dy, true); }                                                              // dy = Q^-1 dy
     for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
       if (N > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
-      nlaunch++, k_gemv_t<NL><<<(c0.P + 31) / 32, 256, 0, st>>>(c0.P, c0.P, c0.Minv, c0.P, c0.t, dx + c0.off, 1, 0); }                                 // dx_j = L_j^-T t_j
+      trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, true); copy(dx + c0.off, c0.t, c0.P); }                                                   // dx_j = L_j^-T t_j
     weighted_A(dX, dx); addsub(dX, dX, 1, P, 1, tot);                                                                                       // dX = P + sum dx_p A_p
     for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // dX Y
     addsub(T1, R, 1, T1, -1, tot);

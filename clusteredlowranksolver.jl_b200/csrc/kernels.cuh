@@ -160,6 +160,47 @@ template <int NL> __global__ void __launch_bounds__(256) k_gemv_t(int K, int N, 
   if (ty == 0 && j < N) { acc = part[0][tx]; acc.sign *= alpha; if (beta) { mpn<NL> o = y[j]; o.sign *= beta; mp_add(acc, acc, o); } y[j] = acc; }
 }
 
+// Blocked triangular solve with ONE right-hand side, in place: x <- L^-1 x (transposed = 0, forward) or
+// x <- L^-T x (transposed = 1, backward).  L is the n x n lower Cholesky factor, Minv holds the inverses of
+// its 32 x 32 diagonal blocks (from k_potrf_diag).  Substitution is kept at the block level because the Schur
+// complement and Q become extremely ill-conditioned (explicit full inverses lose kappa(L) more bits).
+// One CTA of 32 warps: warp i owns row i of the current block; dots are lane-strided + shuffle-reduced.
+template <int NL> __device__ __forceinline__ void warp_reduce_add(mpn<NL>& acc) {
+  for (int o = 16; o > 0; o >>= 1) {
+    mpn<NL> other;
+#pragma unroll
+    for (int q = 0; q < NL; q++) other.l[q] = __shfl_down_sync(0xffffffffu, acc.l[q], o);
+    other.exp = __shfl_down_sync(0xffffffffu, acc.exp, o); other.sign = __shfl_down_sync(0xffffffffu, acc.sign, o);
+    mp_add(acc, acc, other);
+  }
+}
+template <int NL> __global__ void __launch_bounds__(1024) k_trsv(int n, const mpn<NL>* L, int ldl, const mpn<NL>* Minv, int ldm, mpn<NL>* x, int transposed) {
+  __shared__ mpn<NL> rs[32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = (n + 31) / 32;
+  for (int bi = 0; bi < nblk; bi++) {
+    const int b = transposed ? nblk - 1 - bi : bi, k0 = b * 32, nb = min(32, n - k0);
+    if (w < nb) {
+      mpn<NL> acc; mp_zero(acc);
+      if (!transposed) { for (int c = lane; c < k0; c += 32) { mpn<NL> a = L[(int64_t)(k0 + w) * ldl + c], v = x[c]; mp_mul(a, a, v); mp_add(acc, acc, a); } }
+      else { for (int c = k0 + nb + lane; c < n; c += 32) { mpn<NL> a = L[(int64_t)c * ldl + k0 + w], v = x[c]; mp_mul(a, a, v); mp_add(acc, acc, a); } }
+      warp_reduce_add(acc);
+      if (lane == 0) { mpn<NL> r = x[k0 + w]; mp_sub(r, r, acc); rs[w] = r; }
+    }
+    __syncthreads();
+    if (w < nb) {
+      mpn<NL> acc; mp_zero(acc);
+      if (lane < nb) {
+        if (!transposed) { if (lane <= w) mp_mul(acc, Minv[(int64_t)(k0 + w) * ldm + k0 + lane], rs[lane]); }
+        else { if (lane >= w) mp_mul(acc, Minv[(int64_t)(k0 + lane) * ldm + k0 + w], rs[lane]); }
+      }
+      warp_reduce_add(acc);
+      if (lane == 0) x[k0 + w] = acc;
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------
 // panel kernel: Cholesky of one diagonal block (nb <= 32) and the inverse of its
 // factor, one CTA, the block in shared memory.
