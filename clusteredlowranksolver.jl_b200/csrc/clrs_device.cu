@@ -364,8 +364,9 @@ template <int NL> struct Solver : SolverBase {
       nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code);
       if (rem > 0) {
         num* A21 = A + (int64_t)(k0 + nb) * lda + k0; num* A22 = A + (int64_t)(k0 + nb) * lda + k0 + nb;
-        split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);
-        gemm(tA, 0, tB, 0, rem, nb, A21, lda);                       // L21 = A21 * inv(L11)^T
+        if (full_inverse) { split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);
+          gemm(tA, 0, tB, 0, rem, nb, A21, lda); }                    // L21 = A21 * inv(L11)^T
+        else nlaunch++, k_trsm32<NL><<<(rem + 7) / 8, 256, 0, st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, A21, lda, 1, rem, A21, lda, 1);   // rows of L21 by substitution
         split_rows(tA, A21, lda, rem, nb);
         gemm(tA, 0, tA, 0, rem, rem, A22, lda, 1, A22, lda, 1, 0, 0, 0, 0, 1);   // A22 -= L21 L21^T (lower)
       }
@@ -381,7 +382,7 @@ template <int NL> struct Solver : SolverBase {
       }
     }
   }
-  // X = L^-1 B by block forward substitution (approx_solve_tril!, src/solver.jl:1258): X_k = inv(L_kk) (B_k - L[k,0:k0] X[0:k0])
+  // X = L^-1 B by block forward substitution (approx_solve_tril!, src/solver.jl:1258): L_kk X_k = B_k - L[k,0:k0] X[0:k0]
   num* trsm_R = nullptr; size_t trsm_cap = 0;
   void trsm_lower(const num* Lf, int ldl, int n, const num* Minv, int ldm, const num* B, int ldb, int ncols, num* Xo, int ldx) {
     if (n == 0 || ncols == 0) return;
@@ -390,7 +391,7 @@ template <int NL> struct Solver : SolverBase {
       const int nb = std::min(32, n - k0);
       const num* rhs = B + (int64_t)k0 * ldb; int ldr = ldb;
       if (k0 > 0) { mm(Lf + (int64_t)k0 * ldl, ldl, Xo, ldx, nb, ncols, k0, trsm_R, ncols, 1, B + (int64_t)k0 * ldb, ldb); rhs = trsm_R; ldr = ncols; }
-      mm(Minv + (int64_t)k0 * ldm + k0, ldm, rhs, ldr, nb, ncols, nb, Xo + (int64_t)k0 * ldx, ldx);
+      nlaunch++, k_trsm32<NL><<<(ncols + 7) / 8, 256, 0, st>>>(nb, Lf + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, Xo + (int64_t)k0 * ldx, 1, ldx, ncols, rhs, 1, ldr);
     }
   }
   void trsv(const num* Lf, int ldl, int n, const num* Minv, int ldm, num* xv, bool transposed) {
@@ -964,8 +965,8 @@ void clrs_default_options(clrs_options* o) {
 int clrs_create(const clrs_options* opt, clrs_handle** out) {
   clrs_handle* h = new clrs_handle(); h->s = nullptr; *out = h;
   try {
-    if (opt->prec <= 0 || opt->prec > 320) { h->err = "this build supports prec <= 320 bits (8 or 10 limbs of 32 bits)"; return CLRS_ERR_UNSUPPORTED; }
-    if (opt->prec <= 256) h->s = new Solver<8>(*opt); else h->s = new Solver<10>(*opt);
+    if (opt->prec <= 0 || opt->prec > 512) { h->err = "this build supports prec <= 512 bits (8, 10 or 16 limbs of 32 bits)"; return CLRS_ERR_UNSUPPORTED; }
+    if (opt->prec <= 256) h->s = new Solver<8>(*opt); else if (opt->prec <= 320) h->s = new Solver<10>(*opt); else h->s = new Solver<16>(*opt);
   } catch (const std::exception& e) { h->err = e.what(); return CLRS_ERR_CUDA; }
   return CLRS_OK;
 }

@@ -161,9 +161,9 @@ template <int NL> __global__ void __launch_bounds__(256) k_gemv_t(int K, int N, 
 }
 
 // Blocked triangular solve with ONE right-hand side, in place: x <- L^-1 x (transposed = 0, forward) or
-// x <- L^-T x (transposed = 1, backward).  L is the n x n lower Cholesky factor, Minv holds the inverses of
-// its 32 x 32 diagonal blocks (from k_potrf_diag).  Substitution is kept at the block level because the Schur
-// complement and Q become extremely ill-conditioned (explicit full inverses lose kappa(L) more bits).
+// x <- L^-T x (transposed = 1, backward).  L is the n x n lower Cholesky factor; of Minv (the inverses of the
+// 32 x 32 diagonal blocks from k_potrf_diag) only the diagonal, 1/L_cc, is used.  Everything is substitution:
+// the Schur complement and Q become extremely ill-conditioned and explicit inverses lose kappa(L) more bits.
 // One CTA of 32 warps: warp i owns row i of the current block; dots are lane-strided + shuffle-reduced.
 template <int NL> __device__ __forceinline__ void warp_reduce_add(mpn<NL>& acc) {
   for (int o = 16; o > 0; o >>= 1) {
@@ -174,12 +174,53 @@ template <int NL> __device__ __forceinline__ void warp_reduce_add(mpn<NL>& acc) 
     mp_add(acc, acc, other);
   }
 }
+// ---- substitution inside one 32 x 32 diagonal block -----------------------------------------------------------
+// The block's lower triangle is staged in shared memory (packed, tri(i,j) = i(i+1)/2 + j) with the reciprocals of
+// its diagonal; one warp solves one right-hand side, lane i owning element i (column-oriented: x_c is broadcast,
+// the lanes below it update their residuals).  No explicit inverse is applied: products with inv(L_kk) are not
+// backward stable when the block is ill-conditioned (kernel-like Schur blocks of neighbouring samples).
+template <int NL> __device__ __forceinline__ void stage_tri32(mpn<NL>* Ls, mpn<NL>* rinv, int nb, const mpn<NL>* Lkk, int ldl, const mpn<NL>* Mkk, int ldm) {
+  for (int idx = threadIdx.x; idx < 528; idx += blockDim.x) {
+    int i = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((i + 1) * (i + 2) / 2 <= idx) i++; while (i * (i + 1) / 2 > idx) i--;
+    const int j = idx - i * (i + 1) / 2;
+    mpn<NL> v; if (i < nb) v = Lkk[(int64_t)i * ldl + j]; else mp_zero(v);
+    Ls[idx] = v;
+  }
+  for (int c = threadIdx.x; c < 32; c += blockDim.x) { mpn<NL> v; if (c < nb) v = Mkk[(int64_t)c * ldm + c]; else mp_zero(v); rinv[c] = v; }
+}
+template <int NL> __device__ __forceinline__ void warp_trisolve32(int nb, const mpn<NL>* Ls, const mpn<NL>* rinv, mpn<NL>& r, int transposed) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int s = 0; s < nb; s++) {
+    const int c = transposed ? nb - 1 - s : s;
+    mpn<NL> x = r;
+    if (lane == c) { mp_mul(x, r, rinv[c]); r = x; }
+#pragma unroll
+    for (int q = 0; q < NL; q++) x.l[q] = __shfl_sync(0xffffffffu, x.l[q], c);
+    x.exp = __shfl_sync(0xffffffffu, x.exp, c); x.sign = __shfl_sync(0xffffffffu, x.sign, c);
+    const bool upd = transposed ? lane < c : (lane > c && lane < nb);
+    if (upd) { mpn<NL> t; mp_mul(t, transposed ? Ls[c * (c + 1) / 2 + lane] : Ls[lane * (lane + 1) / 2 + c], x); mp_sub(r, r, t); }
+  }
+}
+// nvec right-hand sides against one diagonal block: V[v*vs + e*es] <- (L_kk^-1 Src_v)[e].  8 warps per CTA.
+template <int NL> __global__ void __launch_bounds__(256) k_trsm32(int nb, const mpn<NL>* Lkk, int ldl, const mpn<NL>* Mkk, int ldm, mpn<NL>* V, int64_t vs, int64_t es, int nvec, const mpn<NL>* Src, int64_t svs, int64_t ses) {
+  __shared__ mpn<NL> Ls[528]; __shared__ mpn<NL> rinv[32];
+  stage_tri32<NL>(Ls, rinv, nb, Lkk, ldl, Mkk, ldm);
+  __syncthreads();
+  const int v = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (v >= nvec) return;
+  mpn<NL> r; if (lane < nb) r = Src[(int64_t)v * svs + (int64_t)lane * ses]; else mp_zero(r);
+  warp_trisolve32<NL>(nb, Ls, rinv, r, 0);
+  if (lane < nb) V[(int64_t)v * vs + (int64_t)lane * es] = r;
+}
+
 template <int NL> __global__ void __launch_bounds__(1024) k_trsv(int n, const mpn<NL>* L, int ldl, const mpn<NL>* Minv, int ldm, mpn<NL>* x, int transposed) {
-  __shared__ mpn<NL> rs[32];
+  __shared__ mpn<NL> Ls[528]; __shared__ mpn<NL> rinv[32]; __shared__ mpn<NL> rs[32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = (n + 31) / 32;
   for (int bi = 0; bi < nblk; bi++) {
     const int b = transposed ? nblk - 1 - bi : bi, k0 = b * 32, nb = min(32, n - k0);
+    stage_tri32<NL>(Ls, rinv, nb, L + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm);
     if (w < nb) {
       mpn<NL> acc; mp_zero(acc);
       if (!transposed) { for (int c = lane; c < k0; c += 32) { mpn<NL> a = L[(int64_t)(k0 + w) * ldl + c], v = x[c]; mp_mul(a, a, v); mp_add(acc, acc, a); } }
@@ -188,14 +229,10 @@ template <int NL> __global__ void __launch_bounds__(1024) k_trsv(int n, const mp
       if (lane == 0) { mpn<NL> r = x[k0 + w]; mp_sub(r, r, acc); rs[w] = r; }
     }
     __syncthreads();
-    if (w < nb) {
-      mpn<NL> acc; mp_zero(acc);
-      if (lane < nb) {
-        if (!transposed) { if (lane <= w) mp_mul(acc, Minv[(int64_t)(k0 + w) * ldm + k0 + lane], rs[lane]); }
-        else { if (lane >= w) mp_mul(acc, Minv[(int64_t)(k0 + lane) * ldm + k0 + w], rs[lane]); }
-      }
-      warp_reduce_add(acc);
-      if (lane == 0) x[k0 + w] = acc;
+    if (w == 0) {
+      mpn<NL> r; if (lane < nb) r = rs[lane]; else mp_zero(r);
+      warp_trisolve32<NL>(nb, Ls, rinv, r, transposed);
+      if (lane < nb) x[k0 + lane] = r;
     }
     __syncthreads();
   }
@@ -213,15 +250,19 @@ template <int NL> __global__ void __launch_bounds__(1024) k_trsv(int n, const mp
 #define POTRF_THREADS 768
 template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(int nb, mpn<NL>* A, int lda, mpn<NL>* Minv, int ldm, int* status, int code) {
   extern __shared__ unsigned char smraw[];
+  // beyond 10 limbs four full 32 x 32 arrays do not fit in shared memory: keep the lower triangles only
+  constexpr bool PACK = NL > 10; constexpr int SZ = PACK ? 528 : 1024;
+  auto ix = [](int i, int j) { return PACK ? i * (i + 1) / 2 + j : i * 32 + j; };          // j <= i
+  auto px = [](int j, int kk) { return PACK ? j * 32 - j * (j - 1) / 2 + kk : j * 32 + kk; };  // kk < 32 - j
   mpn<NL>* As = (mpn<NL>*)smraw;                          // 32 x 32 working block (updated lower part)
-  mpn<NL>* Ls = As + 32 * 32;                             // the factor
-  mpn<NL>* Ms = Ls + 32 * 32;                             // its inverse
-  mpn<NL>* rinv = Ms + 32 * 32;                           // 1/L[c][c]
+  mpn<NL>* Ls = As + SZ;                                  // the factor
+  mpn<NL>* Ms = Ls + SZ;                                  // its inverse
+  mpn<NL>* rinv = Ms + SZ;                                // 1/L[c][c]
   mpn<NL>* dpiv = rinv + 32;                              // pivots before the square root
   mpn<NL>* Pb = dpiv + 32;                                // 32 x 32 products of the inverse rows
   __shared__ int bad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int idx = tid; idx < 32 * 32; idx += POTRF_THREADS) { const int i = idx >> 5, j = idx & 31; mpn<NL> a; mp_zero(a); if (i < nb && j <= i) a = A[(int64_t)i * lda + j]; As[idx] = a; mp_zero(Ls[idx]); mp_zero(Ms[idx]); }
+  for (int idx = tid; idx < 32 * 32; idx += POTRF_THREADS) { const int i = idx >> 5, j = idx & 31; if (PACK && j > i) continue; mpn<NL> a; mp_zero(a); if (i < nb && j <= i) a = A[(int64_t)i * lda + j]; const int o = PACK ? ix(i, j) : idx; As[o] = a; mp_zero(Ls[o]); mp_zero(Ms[o]); }
   if (tid == 0) bad = 0;
   __syncthreads();
   if (tid == 0) { mpn<NL> a = As[0]; if (a.sign <= 0) { bad = 1; mp_set_i32(a, 1); } dpiv[0] = a; mpn<NL> r; mp_rsqrt(r, a); rinv[0] = r; }
@@ -234,13 +275,13 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
       if (c + 1 < nb) {
         if constexpr (NL == 8) {
           // the whole warp works on one number at a time (mpw.cuh): ~4x shorter critical path than one thread
-          wnum l = w_mul(w_load(&As[(c + 1) * 32 + c]), w_load(&rinv[c]));
-          wnum d = w_sub(w_load(&As[(c + 1) * 32 + c + 1]), w_mul(l, l));
+          wnum l = w_mul(w_load(&As[ix(c + 1, c)]), w_load(&rinv[c]));
+          wnum d = w_sub(w_load(&As[ix(c + 1, c + 1)]), w_mul(l, l));
           if (d.sign <= 0) { if (lane == 0) bad = 1; mpn<8> one; mp_set_i32(one, 1); d = w_from(one); }
           w_store(&dpiv[c + 1], d);
           w_store(&rinv[c + 1], w_rsqrt(d));
         } else if (lane == 0) {
-          mpn<NL> l, d; mp_mul(l, As[(c + 1) * 32 + c], rinv[c]); mp_mul(l, l, l); mp_sub(d, As[(c + 1) * 32 + c + 1], l);
+          mpn<NL> l, d; mp_mul(l, As[ix(c + 1, c)], rinv[c]); mp_mul(l, l, l); mp_sub(d, As[ix(c + 1, c + 1)], l);
           if (d.sign <= 0) { bad = 1; mp_set_i32(d, 1); }
           dpiv[c + 1] = d; mpn<NL> r; mp_rsqrt(r, d); rinv[c + 1] = r;
         }
@@ -248,40 +289,40 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
     } else if (warp >= 16) {
       // ---- column c of the factor, then the trailing update with it
       const int ut = tid - 512;                           // 0..223
-      if (ut == 0) { mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[c * 32 + c] = sq; }
-      for (int i = c + 1 + ut; i < nb; i += 224) { mpn<NL> a; mp_mul(a, As[i * 32 + c], rinv[c]); Ls[i * 32 + c] = a; }
+      if (ut == 0) { mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[ix(c, c)] = sq; }
+      for (int i = c + 1 + ut; i < nb; i += 224) { mpn<NL> a; mp_mul(a, As[ix(i, c)], rinv[c]); Ls[ix(i, c)] = a; }
       asm volatile("bar.sync 1, 224;" ::: "memory");
       const int w = nb - c - 1;
       for (int idx = ut + 1; idx < w * (w + 1) / 2; idx += 224) {                // lower triangle only; idx 0 = (c+1,c+1) belongs to the pivot chain
         int ii = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((ii + 1) * (ii + 2) / 2 <= idx) ii++; while (ii * (ii + 1) / 2 > idx) ii--;
         const int i = c + 1 + ii, j = c + 1 + (idx - ii * (ii + 1) / 2);
-        mpn<NL> a = As[i * 32 + j], t; mp_mul(t, Ls[i * 32 + c], Ls[j * 32 + c]); mp_sub(a, a, t); As[i * 32 + j] = a;
+        mpn<NL> a = As[ix(i, j)], t; mp_mul(t, Ls[ix(i, c)], Ls[ix(j, c)]); mp_sub(a, a, t); As[ix(i, j)] = a;
       }
     } else {
       // ---- row c of the inverse: M[c][c] = r_c, M[c][j] = -r_c sum_{k=j}^{c-1} L[c][k] M[k][j]   (16 warps)
       // products packed over the triangle (j <= k < c) one per thread, then a 5-level tree over k per column
       // through shared memory (named barrier 2 among the 512 threads of this role)
-      if (tid == 0) Ms[c * 32 + c] = rinv[c];
+      if (tid == 0) Ms[ix(c, c)] = rinv[c];
       const int np = c * (c + 1) / 2;
       if (tid < np) {
         int k = (int)((sqrtf(8.0f * tid + 1.0f) - 1.0f) * 0.5f); while ((k + 1) * (k + 2) / 2 <= tid) k++; while (k * (k + 1) / 2 > tid) k--;
         const int j = tid - k * (k + 1) / 2;                                   // 0 <= j <= k < c
-        mpn<NL> t; mp_mul(t, Ls[c * 32 + k], Ms[k * 32 + j]); Pb[j * 32 + (k - j)] = t;   // column j, position k - j
+        mpn<NL> t; mp_mul(t, Ls[ix(c, k)], Ms[ix(k, j)]); Pb[px(j, k - j)] = t;   // column j, position k - j
       }
       asm volatile("bar.sync 2, 512;" ::: "memory");
       for (int sdist = 16; sdist > 0; sdist >>= 1) {
         const int j = tid / sdist, kk = tid % sdist;                           // c * sdist <= 496 threads
-        if (j < c && kk + sdist < c - j) { mpn<NL> x = Pb[j * 32 + kk], y = Pb[j * 32 + kk + sdist]; mp_add(x, x, y); Pb[j * 32 + kk] = x; }
+        if (j < c && kk + sdist < c - j) { mpn<NL> x = Pb[px(j, kk)], y = Pb[px(j, kk + sdist)]; mp_add(x, x, y); Pb[px(j, kk)] = x; }
         asm volatile("bar.sync 2, 512;" ::: "memory");
       }
-      if (tid < c) { mpn<NL> x; mp_mul(x, Pb[tid * 32], rinv[c]); x.sign = -x.sign; Ms[c * 32 + tid] = x; }
+      if (tid < c) { mpn<NL> x; mp_mul(x, Pb[px(tid, 0)], rinv[c]); x.sign = -x.sign; Ms[ix(c, tid)] = x; }
     }
     __syncthreads();                                      // (element (c+1,c+1) lives on in dpiv; its As copy is not read again)
   }
-  for (int idx = tid; idx < nb * nb; idx += POTRF_THREADS) { const int i = idx / nb, j = idx % nb; A[(int64_t)i * lda + j] = Ls[i * 32 + j]; Minv[(int64_t)i * ldm + j] = Ms[i * 32 + j]; }
+  for (int idx = tid; idx < nb * nb; idx += POTRF_THREADS) { const int i = idx / nb, j = idx % nb; mpn<NL> lv, mv; if (j <= i) { lv = Ls[ix(i, j)]; mv = Ms[ix(i, j)]; } else { mp_zero(lv); mp_zero(mv); } A[(int64_t)i * lda + j] = lv; Minv[(int64_t)i * ldm + j] = mv; }
   if (tid == 0 && bad) atomicCAS(status, 0, code);
 }
-#define POTRF_SMEM(NL) ((4 * 32 * 32 + 64) * sizeof(mpn<NL>))
+#define POTRF_SMEM(NL) ((4 * ((NL) > 10 ? 528 : 1024) + 64) * sizeof(mpn<NL>))
 
 // self-test of the warp-cooperative arithmetic against the single-thread routines (bit for bit); one warp per sample
 __global__ void k_selftest_mpw(int n, const mpn<8>* a, const mpn<8>* b, int* mismatches) {

@@ -306,6 +306,25 @@ def test_prec_300_dense_path_known_answer():
     assert dev.status == "Optimal" and abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -35
 
 
+def test_prec_512_sixteen_limbs_sphere_packing():
+    """prec = 512 is the default of the reference's examples/SpherePacking.jl:13 (16-limb instantiation).  Degree 15 with
+    two radii; both arms reach gap 1e-30 and must agree far below it."""
+    sdp = workloads.sphere_packing(8, 15, [Fraction(1, 2), Fraction(1, 2)], prec=512)
+    dev = solvesdp(sdp, lib="device", duality_gap_threshold=1e-30)
+    ref = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-30)
+    assert dev.status == ref.status == "Optimal", (dev, ref)
+    with mpmath.workprec(700):
+        assert abs(dev.p_obj - ref.p_obj) <= mpmath.mpf(10) ** -40 * abs(ref.p_obj)
+        assert abs(dev.d_obj - ref.d_obj) <= mpmath.mpf(10) ** -40 * abs(ref.d_obj)
+    assert abs(dev.iterations - ref.iterations) <= 1
+
+
+def test_prec_512_dense_path_known_answer():
+    n = 40                                                  # > 32: blocked Cholesky and the tensor-core split at 67 slices
+    dev = solvesdp(workloads.maxcut(workloads.laplacian_complete(n), prec=512), lib="device", duality_gap_threshold=1e-60)
+    assert dev.status == "Optimal" and abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -55
+
+
 def test_warp_cooperative_arithmetic_selftest(tiny):
     """mpw.cuh (limb-per-lane multiply with ballot carry resolution, used by the Cholesky pivot chain) must give
     the same bits as the single-thread routines on 4096 random operand pairs."""
