@@ -305,9 +305,33 @@ template <int NL> struct Solver : SolverBase {
   // second execution context (stream + scratch) for work that is independent of the main chain: the Cholesky of Y
   // for the step length only needs the iterate, so it runs beside the Schur assembly.  swap_ctx() exchanges the
   // members the helpers use; kernels capture their pointers at enqueue time, so swapping while enqueuing is safe.
-  cudaStream_t st2 = nullptr; Sliced tA2, tB2; num* chol_W2 = nullptr; size_t chol_W_cap2 = 0; uint8_t* tc_bytes2 = nullptr; int32_t* tc_top2 = nullptr; size_t tc_cap2 = 0;
+  struct Ctx { cudaStream_t st = nullptr; Sliced tA, tB; num* chol_W = nullptr; size_t chol_W_cap = 0; uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0;
+               num* trsm_R = nullptr; size_t trsm_cap = 0; cudaEvent_t ev = nullptr; };
+  Ctx side;
   cudaEvent_t evY0 = nullptr, evY1 = nullptr; num *LY = nullptr, *MinvY = nullptr;
-  void swap_ctx() { std::swap(st, st2); std::swap(tA, tA2); std::swap(tB, tB2); std::swap(chol_W, chol_W2); std::swap(chol_W_cap, chol_W_cap2); std::swap(tc_bytes, tc_bytes2); std::swap(tc_top, tc_top2); std::swap(tc_cap, tc_cap2); }
+  void swap_with(Ctx& c) { std::swap(st, c.st); std::swap(tA, c.tA); std::swap(tB, c.tB); std::swap(chol_W, c.chol_W); std::swap(chol_W_cap, c.chol_W_cap);
+    std::swap(tc_bytes, c.tc_bytes); std::swap(tc_top, c.tc_top); std::swap(tc_cap, c.tc_cap); std::swap(trsm_R, c.trsm_R); std::swap(trsm_cap, c.trsm_cap); }
+  void swap_ctx() { swap_with(side); }
+  // Independent items (PSD blocks, clusters) are enqueued round-robin on NCTX execution contexts, so that the many small
+  // kernels of a many-block problem (one diagonal-block Cholesky CTA, 16-CTA GEMMs) overlap instead of queueing on one
+  // stream.  Item i runs on context i mod NCTX (context 0 = the caller's); fork and join are events.
+  static constexpr int NCTX = 8;
+  Ctx pctx[NCTX]; cudaEvent_t evFork = nullptr; int par_depth = 0;
+  template <class F> void par_clusters(F&& f) { std::vector<Clu*> o; for (auto& c0 : cl) if (c0.owned) o.push_back(&c0); par_for((int)o.size(), [&](int i) { f(*o[i]); }); }
+  template <class F> void par_blocks(F&& f) { par_for((int)blk.size(), [&](int i) { f(blk[i]); }); }
+  template <class F> void par_for(int n, F&& f) {
+    const int nc = std::min(n, NCTX);
+    if (nc <= 1 || par_depth > 0 || prof_on) { for (int i = 0; i < n; i++) f(i); return; }
+    par_depth++;
+    CK(cudaEventRecord(evFork, st));
+    for (int k = 1; k < nc; k++) CK(cudaStreamWaitEvent(pctx[k].st, evFork, 0));
+    for (int i = 0; i < n; i++) { const int k = i % nc;
+      if (k) swap_with(pctx[k]);
+      try { f(i); } catch (...) { if (k) swap_with(pctx[k]); par_depth--; throw; }
+      if (k) swap_with(pctx[k]); }
+    for (int k = 1; k < nc; k++) { CK(cudaEventRecord(pctx[k].ev, pctx[k].st)); CK(cudaStreamWaitEvent(st, pctx[k].ev, 0)); }
+    par_depth--;
+  }
   // C = op(D, A*B) for plain matrices A (M x K, lda), B (K x N, ldb)
   void mm(const num* A, int lda, const num* B, int ldb, int M, int N, int K, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0) {
     const int lay = use_tc(M, N, K) ? 1 : 0;
@@ -439,7 +463,8 @@ template <int NL> struct Solver : SolverBase {
     int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError("no CUDA device: libclrs_b200 has no CPU fallback");
     CK(cudaSetDevice(o.device)); cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, o.device));
     if (pr.major < 10) throw CudaError("an sm_100 device is required");
-    CK(cudaStreamCreate(&st)); CK(cudaStreamCreate(&st2)); CK(cudaEventCreateWithFlags(&evY0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY1, cudaEventDisableTiming));
+    CK(cudaStreamCreate(&st)); CK(cudaStreamCreate(&side.st)); CK(cudaEventCreateWithFlags(&evY0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY1, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming)); for (int k = 1; k < NCTX; k++) { CK(cudaStreamCreate(&pctx[k].st)); CK(cudaEventCreateWithFlags(&pctx[k].ev, cudaEventDisableTiming)); }
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
     CK(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -451,10 +476,13 @@ template <int NL> struct Solver : SolverBase {
     partial = dalloc<num>(256); sc = dalloc<num>(SC_COUNT); flags = dalloc<int>(FL_COUNT); dinfo = dalloc<double>(32);
   }
   ~Solver() {
-    cudaStreamSynchronize(st); cudaStreamSynchronize(st2);
+    cudaSetDevice(opt.device); cudaDeviceSynchronize();
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-    owned_sliced.push_back(&tA); owned_sliced.push_back(&tB); owned_sliced.push_back(&tA2); owned_sliced.push_back(&tB2);
-    if (tc_bytes2) cudaFree(tc_bytes2); if (tc_top2) cudaFree(tc_top2); cudaEventDestroy(evY0); cudaEventDestroy(evY1); cudaStreamDestroy(st2);
+    owned_sliced.push_back(&tA); owned_sliced.push_back(&tB); owned_sliced.push_back(&side.tA); owned_sliced.push_back(&side.tB);
+    if (side.tc_bytes) cudaFree(side.tc_bytes); if (side.tc_top) cudaFree(side.tc_top); cudaEventDestroy(evY0); cudaEventDestroy(evY1); cudaStreamDestroy(side.st);
+    for (int k = 1; k < NCTX; k++) { Ctx& c = pctx[k]; owned_sliced.push_back(&c.tA); owned_sliced.push_back(&c.tB); if (c.tc_bytes) cudaFree(c.tc_bytes); if (c.tc_top) cudaFree(c.tc_top);
+      if (c.ev) cudaEventDestroy(c.ev); if (c.st) cudaStreamDestroy(c.st); }
+    if (evFork) cudaEventDestroy(evFork);
     for (Sliced* s : owned_sliced) { if (s->sl) cudaFree(s->sl); if (s->E) cudaFree(s->E); if (s->planes) cudaFree(s->planes); }
     if (tc_bytes) cudaFree(tc_bytes); if (tc_top) cudaFree(tc_top); if (pe0) cudaEventDestroy(pe0); if (pe1) cudaEventDestroy(pe1);
     for (void* p : allocs) cudaFree(p);
@@ -607,37 +635,38 @@ template <int NL> struct Solver : SolverBase {
   // ---- pieces of the iteration ---------------------------------------------------------
   // dst_b = sum_p a_p A_p per block  (compute_weighted_A!, src/solver.jl:1410-1470)
   void weighted_A(num* dst, const num* a) {
-    for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
-      if (!c0.owned) continue;
+    par_blocks([&](Block* bp) { Block& b0 = *bp; Clu& c0 = cl[b0.j];
       num* M = dst + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; const num* aj = a + c0.off;
-      if (b0.high_rank) { nlaunch++, k_weighted_dense<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(b0.d_plist, b0.Aall, (int64_t)n * n, b0.nzT_start, b0.nzT_p, aj, M); continue; }
+      if (b0.high_rank) { nlaunch++, k_weighted_dense<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(b0.d_plist, b0.Aall, (int64_t)n * n, b0.nzT_start, b0.nzT_p, aj, M); return; }
       zero(M, (int64_t)n * n);
       for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { auto& q = b0.rs[r * m + s]; if (q.cnt == 0) continue;
         nlaunch++, k_weighted_cols<NL><<<(q.cnt * dl + 127) / 128, 128, 0, st>>>(q.cnt, q.elist, b0.lr_terms, b0.lr_lam, aj, MatRef{b0.V[r], b0.u_r[r]}, dl, q.G, q.cnt);
         split_rows(tA, q.G, q.cnt, dl, q.cnt);
         gemm(tA, 0, q.Hs, 0, dl, dl, M + (int64_t)r * dl * n + (int64_t)s * dl, n); }
       if (m > 1) nlaunch++, k_mirror<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, M, n, 0);
-    }
+    });
   }
   // out[p] = <A_p, Z>  (trace_A with vectors, src/solver.jl:1290-1366)
   void trace_vectors(num* out, const num* Z) {
     zero(out, Ptot);
-    for (auto& c0 : cl) for (auto& b0 : c0.blocks) {
-      if (!c0.owned) continue;
+    par_blocks([&](Block* bp) { Block& b0 = *bp;                                                   // the products Z V_r of all blocks side by side
+      const num* Zb = Z + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta;
+      if (b0.high_rank || b0.nP == 0) return;
+      for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { if (b0.rs[r * m + s].cnt == 0) continue;
+        split_rows(tA, Zb + (int64_t)r * dl * n + (int64_t)s * dl, n, dl, dl); gemm(tA, 0, b0.Vs[r], 0, dl, b0.u_r[r], b0.ZV[r * m + s], b0.u_r[r]); } });
+    par_clusters([&](Clu& c0) { for (auto& b0 : c0.blocks) {                                        // blocks of one cluster add into the same rows: in order
       const num* Zb = Z + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; num* oj = out + c0.off;
       if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, b0.nz_start, b0.nz_idx, Zb, oj); continue; }
       if (b0.nP == 0) continue;
-      for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { if (b0.rs[r * m + s].cnt == 0) continue;
-        split_rows(tA, Zb + (int64_t)r * dl * n + (int64_t)s * dl, n, dl, dl); gemm(tA, 0, b0.Vs[r], 0, dl, b0.u_r[r], b0.ZV[r * m + s], b0.u_r[r]); }
       nlaunch++, k_trace_vectors<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_W, b0.d_ZV, m, dl, oj);
-    }
+    } });
   }
   // out[p] = <A_p, Y> from the stored pairings (src/solver.jl:1368-1407)
   void trace_pairings(num* out) {
     zero(out, Ptot);
-    for (auto& c0 : cl) for (auto& b0 : c0.blocks) { if (!c0.owned) continue; num* oj = out + c0.off;
+    par_clusters([&](Clu& c0) { for (auto& b0 : c0.blocks) { num* oj = out + c0.off;
       if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)b0.n * b0.n, b0.nz_start, b0.nz_idx, Y + b0.off, oj); continue; }
-      if (b0.nP) nlaunch++, k_trace_pairings<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BY, b0.m, oj); }
+      if (b0.nP) nlaunch++, k_trace_pairings<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BY, b0.m, oj); } });
   }
   // P, d, p  (compute_residuals!, src/solver.jl:863-918); `tr` must hold <A_*, Y>
   void residuals() {
@@ -690,7 +719,7 @@ template <int NL> struct Solver : SolverBase {
   }
 
   // Schur complement S_j and its factorisation  (compute_T_decomposition!, src/solver.jl:1229-1287)
-  void schur_block_lowrank(Clu& c0, Block& b0) {
+  void pairings_lowrank(Block& b0) {
     const int n = b0.n, m = b0.m, dl = b0.delta;
     if (b0.nP == 0) return;
     for (int pass = 0; pass < 2; pass++) {
@@ -702,10 +731,13 @@ template <int NL> struct Solver : SolverBase {
           split_cols(tB, b0.part + (int64_t)s * dl * b0.u_r[r], b0.u_r[r], dl, b0.u_r[r]);
           gemm(b0.Ws[s], 0, tB, 0, b0.ul_r[s], b0.u_r[r], Bout[s * m + r], b0.u_r[r]); } }                // W_s part[s-rows]            (:1131,:1143)
     }
+  }
+  void schur_add_lowrank(Clu& c0, Block& b0) {
+    if (b0.nP == 0) return; const int m = b0.m;
     int64_t np2 = (int64_t)b0.nP * b0.nP;
     nlaunch++, k_schur_lowrank<NL><<<(unsigned)((np2 + 127) / 128), 128, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BX, b0.d_BY, m, c0.S, c0.P);
   }
-  void schur_block_dense(Clu& c0, Block& b0) {        // T = X^-1 A_p Y, S[p,q] += <A_q, T>   (src/solver.jl:1089-1104)
+  void pairings_dense(Block& b0) {                    // T = X^-1 A_p Y, S[p,q] += <A_q, T>   (src/solver.jl:1089-1104)
     const int n = b0.n, np = b0.np; if (np == 0) return; const int64_t nn = (int64_t)n * n;
     // T1t[(p,j)][i] = sum_k A_p[k][j] X^-1[i][k]   (= (X^-1 A_p)^T; the 90000-row operand sits on the 128-lane M side)
     gemm(b0.AallB, 0, b0.XiS, 0, np * n, n, b0.T1, n);
@@ -715,18 +747,21 @@ template <int NL> struct Solver : SolverBase {
     // S[p,q] += sum_ab T2_p[ab] A_q[ab]
     { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true, b0.AallV.lay); }
     gemm(b0.AallV, 0, b0.T2V, 0, np, np, b0.Sd, np, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);          // Sd[q][p], q >= p only
+  }
+  void schur_add_dense(Clu& c0, Block& b0) {
+    const int np = b0.np; if (np == 0) return;
     nlaunch++, k_scatter_upper<NL><<<(unsigned)(((int64_t)np * np + 127) / 128), 128, 0, st>>>(np, b0.d_plist, b0.Sd, c0.S, c0.P);
   }
   void decomposition(int e0) {
-    for (auto& c0 : cl) { if (!c0.owned) continue; zero(c0.S, (int64_t)c0.P * c0.P);
-      for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_block_dense(c0, b0); else schur_block_lowrank(c0, b0); }
-      if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); }
+    par_blocks([&](Block* b0) { if (b0->high_rank) pairings_dense(*b0); else pairings_lowrank(*b0); });
+    par_clusters([&](Clu& c0) { zero(c0.S, (int64_t)c0.P * c0.P);
+      for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_add_dense(c0, b0); else schur_add_lowrank(c0, b0); }
+      if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); });
     CK(cudaEventRecord(ev[e0], st));
-    for (auto& c0 : cl) if (c0.owned) chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S, false);
+    par_clusters([&](Clu& c0) { chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S, false); });
     CK(cudaEventRecord(ev[e0 + 1], st));
     if (N > 0) {
-      for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
-        trsm_lower(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.B, N, N, c0.LinvB, N); }                             // LinvB = L^-1 B  (:1258)
+      par_clusters([&](Clu& c0) { if (c0.P) trsm_lower(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.B, N, N, c0.LinvB, N); });     // LinvB = L^-1 B  (:1258)
       CK(cudaEventRecord(ev[e0 + 2], st));
       zero(Q, (int64_t)N * N);
       for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
@@ -740,35 +775,35 @@ template <int NL> struct Solver : SolverBase {
   }
   // search direction  (compute_search_direction!, src/solver.jl:1474-1616)
   void direction() {
-    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, P + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // P Y
+    par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, P + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); });     // P Y
     addsub(T1, T1, 1, R, -1, tot);
-    for (Block* b0 : blk) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n, b0->lay); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); }    // Z = X^-1 (P Y - R)
+    par_blocks([&](Block* b0) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n, b0->lay); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); });    // Z = X^-1 (P Y - R)
     nlaunch++, k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
     trace_vectors(tr, dY);
     if (Ptot) nlaunch++, k_vec_rhs<NL><<<(Ptot + 127) / 128, 128, 0, st>>>(Ptot, dx, d, tr);                                                          // rhs_x = -d - <A_*, Z>
     // block elimination  (:1527-1582)
     if (N > 0) zero(tmpU, N);
-    for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
-      copy(c0.t, dx + c0.off, c0.P); trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, false);                                                    // t_j = L_j^-1 rhs_j
-      if (N > 0) nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                             // u += LinvB_j^T t_j
+    par_clusters([&](Clu& c0) { if (c0.P) { copy(c0.t, dx + c0.off, c0.P); trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, false); } });                 // t_j = L_j^-1 rhs_j
+    if (N > 0) for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
+      nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                                        // u += LinvB_j^T t_j
     if (N > 0) { allreduce(tmpU, N, 0); addsub(dy, p, 1, tmpU, -1, N);                                                                       // dy = p - sum_j u_j
       trsv(Q, N, N, QMinv, N, dy, false); trsv(Q, N, N, QMinv, N, dy, true); }                                                              // dy = Q^-1 dy
-    for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
+    par_clusters([&](Clu& c0) { if (c0.P == 0) return;
       if (N > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
-      trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, true); copy(dx + c0.off, c0.t, c0.P); }                                                   // dx_j = L_j^-T t_j
+      trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, true); copy(dx + c0.off, c0.t, c0.P); });                                                 // dx_j = L_j^-T t_j
     weighted_A(dX, dx); addsub(dX, dX, 1, P, 1, tot);                                                                                       // dX = P + sum dx_p A_p
-    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); }     // dX Y
+    par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); });     // dX Y
     addsub(T1, R, 1, T1, -1, tot);
-    for (Block* b0 : blk) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n, b0->lay); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); }    // dY = X^-1 (R - dX Y)
+    par_blocks([&](Block* b0) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n, b0->lay); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); });    // dY = X^-1 (R - dX Y)
     nlaunch++, k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
   }
   // lambda_min( L^-1 dM L^-T ) per block in Float64  (compute_step_length, src/solver.jl:1620-1693); Mi holds L^-1
   void step_eigs(const num* Mi, const num* dM, double* lam, bool forY) {
-    for (Block* b0 : blk) { const int n = b0->n; if (n == 1) continue;
+    par_blocks([&](Block* b0) { const int n = b0->n; if (n == 1) return;
       Sliced& ms = forY ? b0->MSY : b0->MS;                                                             // rows of L^-1 (Y's are split on the side stream)
       if (!forY) split_rows(ms, Mi + b0->off, n, n, n, b0->lay);
       split_cols(tB, dM + b0->off, n, n, n, b0->lay); gemm(ms, 0, tB, 0, n, n, U + b0->off, n);          // U = L^-1 dM
-      split_rows(tA, U + b0->off, n, n, n, b0->lay); gemm(tA, 0, ms, 0, n, n, T1 + b0->off, n); }         // T = U L^-T
+      split_rows(tA, U + b0->off, n, n, n, b0->lay); gemm(tA, 0, ms, 0, n, n, T1 + b0->off, n); });        // T = U L^-T
     nlaunch++, k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, T1, Td);
     if (!blk.empty()) { int maxn = 1; for (Block* b0 : blk) maxn = std::max(maxn, b0->n);
       nlaunch++, k_min_eig<<<(unsigned)blk.size(), maxn <= 32 ? 128 : (maxn <= 128 ? 256 : EIG_THREADS), 0, st>>>(eigT, lam); }
@@ -793,18 +828,18 @@ template <int NL> struct Solver : SolverBase {
     // side stream: Cholesky of Y and L_Y^-1 for the step length (Y does not change until the step at the end)
     CK(cudaEventRecord(evY0, st)); swap_ctx(); CK(cudaStreamWaitEvent(st, evY0, 0));
     copy(LY, Y, tot);
-    for (Block* b0 : blk) { const int n = b0->n; if (n > 1) { chol(LY + b0->off, n, n, MinvY + b0->off, n, CLRS_ERR_CHOL_STEP); split_rows(b0->MSY, MinvY + b0->off, n, n, n, b0->lay); } }
+    par_blocks([&](Block* b0) { const int n = b0->n; if (n > 1) { chol(LY + b0->off, n, n, MinvY + b0->off, n, CLRS_ERR_CHOL_STEP); split_rows(b0->MSY, MinvY + b0->off, n, n, n, b0->lay); } });
     CK(cudaEventRecord(evY1, st)); swap_ctx();
     scalar(0);                                                        // mu, mu_p  (SC_D0 = <X,Y> is kept current)
     // R = mu_p I - X Y
-    for (Block* b0 : blk) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n, b0->lay); split_rows(tA, X + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); }
+    par_blocks([&](Block* b0) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n, b0->lay); split_rows(tA, X + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); });
     k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, (const num*)nullptr, sc + SC_MUP);
     CK(cudaEventRecord(ev[1], st));
     // Cholesky of X, L^-1, X^-1  (src/solver.jl:388-399, 1117)
     copy(L, X, tot);
-    for (Block* b0 : blk) { const int n = b0->n; chol(L + b0->off, n, n, Minv + b0->off, n, CLRS_ERR_CHOL_X);
+    par_blocks([&](Block* b0) { const int n = b0->n; chol(L + b0->off, n, n, Minv + b0->off, n, CLRS_ERR_CHOL_X);
       split_cols(tA, Minv + b0->off, n, n, n, b0->lay); gemm(tA, 0, tA, 0, n, n, Xi + b0->off, n);               // X^-1 = L^-T L^-1
-      split_rows(b0->XiS, Xi + b0->off, n, n, n, b0->lay); }
+      split_rows(b0->XiS, Xi + b0->off, n, n, n, b0->lay); });
     CK(cudaEventRecord(ev[2], st));
     decomposition(3);                                                 // events 3..7
     trace_pairings(tr); residuals();
@@ -814,7 +849,7 @@ template <int NL> struct Solver : SolverBase {
     reduce(X, dY, tot, sc + SC_D1, 0); reduce(dX, Y, tot, sc + SC_D2, 0); reduce(dX, dY, tot, sc + SC_D3, 0); allreduce(sc + SC_D1, 3, 0);   // D1..D3 adjacent
     errors(); scalar(1);
     CK(cudaEventRecord(ev[10], st));
-    for (Block* b0 : blk) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); split_cols(tB, dY + b0->off, n, n, n, b0->lay); gemm(tA, 0, tB, 0, n, n, T1 + b0->off, n); }
+    par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); split_cols(tB, dY + b0->off, n, n, n, b0->lay); gemm(tA, 0, tB, 0, n, n, T1 + b0->off, n); });
     k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, T1, sc + SC_MUC);                     // R = mu_c I - XY - dXdY
     CK(cudaEventRecord(ev[11], st));
     direction();                                                      // corrector

@@ -23,15 +23,19 @@ CASES = {
     "maxcut130_seed1": lambda: workloads.maxcut(workloads.laplacian_random(130, 0.5, 1)),
     "polyopt20_seed0": lambda: workloads.polyopt_random(20, 0),
     "delsarte_8_16": lambda: workloads.delsarte(8, 16, Fraction(1, 2)),
+    "delsarte_8_32": lambda: workloads.delsarte(8, 32, Fraction(1, 2)),                               # BASELINE config 3 at full size
+    "sphere_2_31_prec512": lambda: workloads.sphere_packing(8, 31, [Fraction(1, 2), Fraction(1, 2)], prec=512),   # config 5, examples/SpherePacking.jl:13 default precision
+    "threepoint_4_10_10": lambda: workloads.three_point_bound(4, Fraction(1, 6), 10, 10),             # config 4 (examples/ThreePointBound.jl)
 }
+KW = {"threepoint_4_10_10": dict(omega_p=10 ** 3, omega_d=10 ** 3)}
 
 for name in (sys.argv[1:] or list(CASES)):
     sdp = CASES[name]()
     t = time.time()
-    r = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-30, oracle_skip_zeros=True)
+    r = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-30, oracle_skip_zeros=True, **KW.get(name, {}))
     out = {"name": name, "describe": sdp.describe(), "status": r.status, "iterations": r.iterations,
            "d_obj": mpmath.nstr(r.d_obj, 70), "p_obj": mpmath.nstr(r.p_obj, 70), "gap": mpmath.nstr(r.gap, 20),
-           "options": {"prec": 256, "duality_gap_threshold": 1e-30}, "oracle_seconds": round(time.time() - t, 1)}
+           "options": {"prec": sdp.prec, "duality_gap_threshold": 1e-30, **{k: str(v) for k, v in KW.get(name, {}).items()}}, "oracle_seconds": round(time.time() - t, 1)}
     with open(os.path.join(HERE, name + ".json"), "w") as f:
         json.dump(out, f, indent=1)
     print(out, flush=True)

@@ -245,14 +245,18 @@ def _golden(name):
     ("maxcut130_seed1", lambda: workloads.maxcut(workloads.laplacian_random(130, 0.5, 1))),
     ("polyopt20_seed0", lambda: workloads.polyopt_random(20, 0)),                                # config 1
     ("delsarte_8_16", lambda: workloads.delsarte(8, 16, Fraction(1, 2))),                        # config 3
+    ("delsarte_8_32", lambda: workloads.delsarte(8, 32, Fraction(1, 2))),                        # config 3 at full size (dimension 8, degree 32)
+    ("sphere_2_31_prec512", lambda: workloads.sphere_packing(8, 31, [Fraction(1, 2), Fraction(1, 2)], prec=512)),   # config 5, reference default precision
+    ("threepoint_4_10_10", lambda: workloads.three_point_bound(4, Fraction(1, 6), 10, 10)),      # config 4
 ])
 def test_full_size_configs_against_golden_oracle_values(name, make):
     """Objectives and gap to a relative 1e-25, iteration count within +-1 (the north-star parity bar);
     the golden values come from the CPU oracle (tests/golden/make_golden.py)."""
     g = _golden(name)
-    dev = solvesdp(make(), lib="device", duality_gap_threshold=1e-30)
+    kw = {k: int(v) for k, v in g["options"].items() if k.startswith("omega")}
+    dev = solvesdp(make(), lib="device", duality_gap_threshold=1e-30, **kw)
     assert dev.status == g["status"] == "Optimal"
-    with mpmath.workprec(400):
+    with mpmath.workprec(700):
         for key, val in (("p_obj", dev.p_obj), ("d_obj", dev.d_obj)):
             ref = mpmath.mpf(g[key])
             assert abs(val - ref) <= TOL_OBJ * max(1, abs(ref)), (key, val, ref)
