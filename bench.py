@@ -35,13 +35,22 @@ METRIC = "ipm_iterations_per_sec"
 UNIT = "iterations/s"
 
 
-def workload(n):
+def workload(n, kind="maxcut"):
     import clrs_b200
     from clrs_b200 import workloads
+    from fractions import Fraction as F
+    if kind == "sphere":        # BASELINE.json configs[4]: many clusters coupled through the free variables; shards by cluster
+        return workloads.sphere_packing(8, n if n != 300 else 23, [F(1, 2), F(1, 2), F(3, 4), F(1)], prec=512)
+    if kind == "threepoint":    # configs[3] at the size of examples/ThreePointBound.jl (one cluster: the dense F_k blocks are shared)
+        return workloads.three_point_bound(4, F(1, 6), n if n != 300 else 10, n if n != 300 else 10, prec=256)
     return workloads.maxcut(workloads.laplacian_random(n, 0.5, 0), prec=256)
 
 
-def config(n, n_gpus):
+def config(n, n_gpus, kind="maxcut", sdp=None):
+    if kind != "maxcut":
+        return {"workload": f"{sdp.describe() if sdp is not None else kind} (BASELINE.json configs[{4 if kind == 'sphere' else 3}])",
+                "step": "one predictor-corrector IPM iteration", "l2": "L2 flushed by the iteration's own temporaries only; latency-bound small blocks",
+                "parallelism": ("clusters sharded over ranks (LPT), NCCL all-gather of Q, u, p and scalars" if kind == "sphere" else "replicas only") if n_gpus > 1 else "single GPU"}
     return {"workload": f"GW MAX-CUT relaxation, G({n},0.5) numpy default_rng(0), dense constraint path "
                         f"(BASELINE.json configs[1]), prec=256, J=1 P={n} one dense block {n}x{n}, N=0",
             "step": "one predictor-corrector IPM iteration", "l2": "working set (~7 GB of slices/temporaries) exceeds the 126 MB L2",
@@ -86,11 +95,11 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows)}
 
 
-def cpu_arm(n, steps, warmup, target_seconds=12.0):
+def cpu_arm(n, steps, warmup, target_seconds=12.0, kind="maxcut"):
     """The oracle on the host cores, bounded sample.  Returns (it/s, description, seconds per step list)."""
     import ctypes as C
     from clrs_b200 import Solver
-    sdp = workload(n)
+    sdp = workload(n, kind)
     S = Solver(sdp, lib="oracle", oracle_skip_zeros=True)
     lib = S.lib
     lib.clrs_oracle_set_sample_limit.restype = None
@@ -107,6 +116,11 @@ def cpu_arm(n, steps, warmup, target_seconds=12.0):
         out = (C.c_double * 3)()
         lib.clrs_oracle_get_sample_times(S.h, out)
         t_plain, t_skip, np_ = out[0], out[1], int(out[2])
+        if np_ == 0:            # no dense Schur rows (low-rank workloads): the iteration ran in full
+            if it >= warmup:
+                times.append(wall)
+            desc = f"full iterations of {sdp.describe()}"
+            continue
         est = (wall - t_plain - t_skip) + t_plain * np_ / max(limit, 1)
         if it >= warmup:
             times.append(est)
@@ -128,6 +142,8 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=300, help="graph size (300 = the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-path", type=int, default=0)
+    ap.add_argument("--workload", default="maxcut", choices=["maxcut", "sphere", "threepoint"],
+                    help="maxcut = BASELINE configs[1] (default, the metric's config); sphere = configs[4], sharded by cluster when N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -136,10 +152,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        its, cores, desc = cpu_arm(args.n, max(1, args.steps), max(0, min(args.warmup, 1)))
+        its, cores, desc = cpu_arm(args.n, max(1, args.steps), max(0, min(args.warmup, 1)), kind=args.workload)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "mpfr256 (cpu)", "data": "synthetic", "config": config(args.n, args.gpus),
+                          "dtype": "mpfr (cpu)", "data": "synthetic", "config": config(args.n, args.gpus, args.workload, workload(args.n, args.workload) if args.workload != "maxcut" else None),
                           "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
                           "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -158,8 +174,17 @@ def main():
         dist.barrier()
     import clrs_b200
     from clrs_b200 import Solver, wire
-    sdp = workload(args.n)
-    S = Solver(sdp, lib="device", device=local_rank, gemm_path=args.gemm_path)
+    sdp = workload(args.n, args.workload)
+    sharded = world > 1 and args.workload == "sphere"
+    comm = None
+    if sharded:                 # one communicator over the ranks; the id travels through torch.distributed
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(clrs_b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        comm = (rank, world, bytes(uid.cpu().tolist()))
+    S = Solver(sdp, lib="device", device=local_rank, gemm_path=args.gemm_path, comm=comm)
+    reps = 1 if sharded else world
     W, K = max(args.warmup, 3), args.steps
 
     def sync():
@@ -188,7 +213,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
-    value = world * K / (dev_ms_max / 1e3)
+    value = reps * K / (dev_ms_max / 1e3)
 
     # ---- end to end through the C ABI with host buffers every step ----
     x, X, y, Y = S.get_state()
@@ -204,7 +229,7 @@ def main():
     te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * K / float(te.item())
+    e2e_value = reps * K / float(te.item())
 
     # ---- roofline of the dominant kernel: per-launch CUDA-event timing of every GEMM ----
     S.profile(True)
@@ -235,14 +260,14 @@ def main():
                 "peak_source": peak_src, "launches": r["launches"], "avg_launch_ms": r["avg_launch_ms"], "gemm_share_of_step": r["share_of_step"],
                 "other_gemm_classes": {c: rl(c) for c in classes if c != dom}}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 slices of 256-bit mantissas (exact int32 accumulation)",
-           "data": "synthetic", "config": config(args.n, world), "wall_ms_per_step": 1e3 * wall / K,
+           "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": f"int8 slices of {sdp.prec}-bit mantissas (exact int32 accumulation)",
+           "data": "synthetic", "config": config(args.n, world, args.workload, sdp), "wall_ms_per_step": 1e3 * wall / K,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
                    "path": "clrs_set_state + clrs_iterate + clrs_get_state with host wire buffers"},
            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            its, cores, desc = cpu_arm(args.n, 1, 1)
+            its, cores, desc = cpu_arm(args.n, 1, 1, kind=args.workload)
             out["cpu_baseline"] = {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         except Exception as e:      # the baseline must never take the GPU number down
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}

@@ -269,7 +269,7 @@ template <int NL> struct Solver : SolverBase {
     return m;
   }
   void gemm_tc(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode, const num* D, int ldd,
-               int batch, int64_t a_bvec, int64_t b_bvec, int64_t c_bs, int64_t d_bs, int lower_only) {
+               int batch, int64_t a_bvec, int64_t b_bvec, int64_t c_bs, int64_t d_bs, int lower_only, int trans = 0) {
     if (a0 != 0 || b0 != 0) throw CudaError("gemm_tc: panel offsets are not supported");
     // default: both operands in shared memory (k_gemm_tc); CLRS_TC_TS=1 selects the variant with the left
     // operand chunk in TMEM (k_gemm_ts, tiles of at most 112 columns) — measured slower once four warps issue MMAs
@@ -294,7 +294,7 @@ template <int NL> struct Solver : SolverBase {
     if (ts) { tc::ArgsTS p; p.g = a; p.planesA = A.planes; p.nvecA = A.nvec; p.KpA = A.Kp; nlaunch++, tc::k_gemm_ts<<<grid, tc::TS_THREADS, tc::TS_SMEM_BYTES, st>>>(mB, p); }
     else nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
     const int64_t tot_ = (int64_t)batch * M * N;
-    nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1);
+    nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1, trans);
   }
   // ---- optional per-launch GEMM profile (bench.py roofline) ------------------------------------
   bool prof_on = false; cudaEvent_t pe0 = nullptr, pe1 = nullptr; double prof_ms[3] = {0, 0, 0}, prof_flops[3] = {0, 0, 0}; long prof_n[3] = {0, 0, 0};   // 0: CUDA-core path, 1: tcgen05 small outputs, 2: tcgen05 outputs >= 1e6 numbers
@@ -335,6 +335,12 @@ template <int NL> struct Solver : SolverBase {
   // C = op(D, A*B) for plain matrices A (M x K, lda), B (K x N, ldb)
   void mm(const num* A, int lda, const num* B, int ldb, int M, int N, int K, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0) {
     const int lay = use_tc(M, N, K) ? 1 : 0;
+    // a short left operand (a 32-row panel against a long right-hand side): swap the operands so that the long
+    // dimension fills the 128 TMEM lanes and the short one becomes a narrow N tile; the result is written transposed
+    if (!lay && opt.gemm_path != 1 && M >= 16 && M < 128 && N >= 128 && K >= 96) {
+      split_cols(tA, B, ldb, K, N, 1); split_rows(tB, A, lda, M, K, 1);
+      prof_begin(); gemm_tc(tA, 0, tB, 0, N, M, C, ldc, mode, D, ldd, 1, 0, 0, 0, 0, 0, 1); prof_end(2.0 * M * N * (double)K, 1);
+      return; }
     split_rows(tA, A, lda, M, K, lay); split_cols(tB, B, ldb, K, N, lay); gemm(tA, 0, tB, 0, M, N, C, ldc, mode, D, ldd);
   }
 

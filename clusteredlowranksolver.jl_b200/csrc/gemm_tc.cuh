@@ -562,8 +562,9 @@ template <int NL> __global__ void __launch_bounds__(256) k_split_tc_t(VecView v,
 // byte planes + top -> multi-limb C (op with D), one thread per output
 template <int NL> __global__ void k_tc_recombine(int M, int N, int Npitch, int batch, const uint8_t* obytes, const int32_t* otop,
                                                  const int32_t* EA, int64_t a_bvec, const int32_t* EB, int64_t b_bvec,
-                                                 mpn<NL>* C, int ldc, int64_t c_bs, const mpn<NL>* D, int ldd, int64_t d_bs, int mode, int lower_only, int nsum) {
+                                                 mpn<NL>* C, int ldc, int64_t c_bs, const mpn<NL>* D, int ldd, int64_t d_bs, int mode, int lower_only, int nsum, int trans) {
   constexpr int NS = I8Cfg<NL>::NS;
+  // trans: the product was formed with the operands swapped (small left operand on the N side); element (m,n) goes to C[n][m]
   // nsum > 1: the `batch` planes are split-K partial results of ONE product and are summed here
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int nb = nsum > 1 ? 1 : batch;
@@ -583,7 +584,8 @@ template <int NL> __global__ void k_tc_recombine(int M, int N, int Npitch, int b
     if (ea == I8_EXP_NONE || eb == I8_EXP_NONE) mp_zero(t); else i8_recombine<NL>(t, top, dg, ea + eb);
     if (z == 0) r = t; else mp_add(r, r, t);
   }
-  if (mode == 1 || mode == 2) { mpn<NL> d = D[(int64_t)bz * d_bs + (int64_t)m * ldd + n]; if (mode == 1) mp_sub(r, d, r); else mp_add(r, d, r); }
+  const int cr = trans ? n : m, cc = trans ? m : n;
+  if (mode == 1 || mode == 2) { mpn<NL> d = D[(int64_t)bz * d_bs + (int64_t)cr * ldd + cc]; if (mode == 1) mp_sub(r, d, r); else mp_add(r, d, r); }
   else if (mode == 3) r.sign = -r.sign;
-  C[(int64_t)bz * c_bs + (int64_t)m * ldc + n] = r;
+  C[(int64_t)bz * c_bs + (int64_t)cr * ldc + cc] = r;
 }

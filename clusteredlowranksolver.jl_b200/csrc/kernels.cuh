@@ -441,10 +441,22 @@ struct GemmArgs {
 // C tile 16x16 per CTA, one output per thread, all NS slice-pair sums of that
 // output in registers (NS(NS+1)/2 dp4a per 4 k).  Exact: the int32 sums are
 // carry-normalised every FLUSH steps.
+// acc[t+u] += a[t] . b[u] for all t + u < NS, unrolled by template recursion (the 2278 products of the 512-bit
+// configuration exceed what "#pragma unroll" expands, and a rolled loop would put acc[] in local memory)
+template <int NS, int NSP, int U> struct Dp4aSweep {
+  static __device__ __forceinline__ void run(int32_t (&acc)[NS], const int32_t (&a)[NSP], const int32_t* bp) {
+    const int32_t bu = bp[U];
+#pragma unroll
+    for (int t = 0; t + U < NS; t++) acc[t + U] = __dp4a(a[t], bu, acc[t + U]);
+    Dp4aSweep<NS, NSP, U + 1>::run(acc, a, bp);
+  }
+};
+template <int NS, int NSP> struct Dp4aSweep<NS, NSP, NS> { static __device__ __forceinline__ void run(int32_t (&)[NS], const int32_t (&)[NSP], const int32_t*) {} };
 template <int NL> __global__ void __launch_bounds__(256) k_gemm_dp4a(GemmArgs g) {
   constexpr int NS = I8Cfg<NL>::NS, NSP = I8Cfg<NL>::NSP, KC = 4, FLUSH = 512;
+  constexpr int BST = KC * NSP + 1;                      // odd row pitch: the 16 columns of a warp hit 16 different banks
   __shared__ __align__(16) int32_t As[16][KC][NSP];
-  __shared__ __align__(16) int32_t Bs[16][KC][NSP];
+  __shared__ int32_t Bs[16][BST];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16, bz = blockIdx.z;
   if (g.lower_only && j0 > i0 + 15) return;
@@ -463,22 +475,19 @@ template <int NL> __global__ void __launch_bounds__(256) k_gemm_dp4a(GemmArgs g)
         if (i0 + v < g.M) za = *(const int4*)(Ab + ((int64_t)v * g.K4 + k0 + kk) * NSP + 4 * q);
         if (j0 + v < g.N) zb = *(const int4*)(Bb + ((int64_t)v * g.K4 + k0 + kk) * NSP + 4 * q);
       }
-      *(int4*)&As[v][kk][4 * q] = za; *(int4*)&Bs[v][kk][4 * q] = zb;
+      *(int4*)&As[v][kk][4 * q] = za;
+      int32_t* bd = &Bs[v][kk * NSP + 4 * q]; bd[0] = zb.x; bd[1] = zb.y; bd[2] = zb.z; bd[3] = zb.w;
     }
     __syncthreads();
 #pragma unroll 1
     for (int kk = 0; kk < KC; kk++) {
-      int32_t a[NSP], b[NSP];
+      // the row's digits stay in registers (broadcast reads); the column's digits stream from shared memory one
+      // slice at a time, each feeding one anti-diagonal sweep: acc[t+u] += a[t] . b[u]
+      int32_t a[NSP];
 #pragma unroll
-      for (int q = 0; q < NSP / 4; q++) {
-        int4 va = *(const int4*)&As[ty][kk][4 * q]; a[4 * q] = va.x; a[4 * q + 1] = va.y; a[4 * q + 2] = va.z; a[4 * q + 3] = va.w;
-        int4 vb = *(const int4*)&Bs[tx][kk][4 * q]; b[4 * q] = vb.x; b[4 * q + 1] = vb.y; b[4 * q + 2] = vb.z; b[4 * q + 3] = vb.w;
-      }
-#pragma unroll
-      for (int s = 0; s < NS; s++) {
-#pragma unroll
-        for (int t = 0; t <= s; t++) acc[s] = __dp4a(a[t], b[s - t], acc[s]);
-      }
+      for (int q = 0; q < NSP / 4; q++) { int4 va = *(const int4*)&As[ty][kk][4 * q]; a[4 * q] = va.x; a[4 * q + 1] = va.y; a[4 * q + 2] = va.z; a[4 * q + 3] = va.w; }
+      const int32_t* bp = &Bs[tx][kk * NSP];
+      Dp4aSweep<NS, NSP, 0>::run(acc, a, bp);
     }
     __syncthreads();
     since += KC;

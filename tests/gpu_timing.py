@@ -41,3 +41,4 @@ if "gemm512" in which:
             dev = clrs_b200.mp_gemm(A, B, M, K, N, prec=prec, lib="device"); ora = clrs_b200.mp_gemm(A, B, M, K, N, prec=prec, lib="oracle")
             err = max(abs(a - b) for a, b in zip(dev, ora)) / max(abs(b) for b in ora)
             print(f"gemm prec {prec}: rel diff 2^{float(mpmath.log(err, 2)) if err else -9999:.1f}")
+if "sp4" in which: run("sphere(4,23) prec512", workloads.sphere_packing(8, 23, [Fraction(1, 2), Fraction(1, 2), Fraction(3, 4), Fraction(1)], prec=512), iters=6)

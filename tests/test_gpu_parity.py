@@ -208,6 +208,16 @@ def test_gemm_tcgen05_equals_cuda_core_path(tiny, M, N, K, spread):
     assert C1.tobytes() == C2.tobytes()
 
 
+@pytest.mark.parametrize("M,N,K,spread", [(32, 300, 200, 5), (17, 129, 96, 50), (64, 481, 224, 3)])
+def test_gemm_short_left_operand_runs_swapped_on_tensor_cores(tiny, M, N, K, spread):
+    """A short panel against a long right-hand side (block rows of the triangular solves) is routed to the tcgen05
+    kernel with the operands swapped and the result written transposed: same bits as the CUDA-core path."""
+    A = rand_wire(3, (M, K), spread); B = rand_wire(4, (K, N), spread)
+    C0, _ = tiny.mp_gemm(A, B, path=0)
+    C1, _ = tiny.mp_gemm(A, B, path=1)
+    assert C0.tobytes() == C1.tobytes()
+
+
 @pytest.mark.parametrize("M,N,K,spread", [(300, 300, 300, 5), (512, 304, 300, 200), (256, 48, 3800, 10)])
 def test_gemm_tcgen05_k_split(tiny, M, N, K, spread):
     """Products with few output tiles or K beyond the int32 headroom (35 K 2^14 < 2^31) run as split-K over
