@@ -179,25 +179,28 @@ template <int NL> __device__ __forceinline__ void warp_reduce_add(mpn<NL>& acc) 
 // its diagonal; one warp solves one right-hand side, lane i owning element i (column-oriented: x_c is broadcast,
 // the lanes below it update their residuals).  No explicit inverse is applied: products with inv(L_kk) are not
 // backward stable when the block is ill-conditioned (kernel-like Schur blocks of neighbouring samples).
-template <int NL> __device__ __forceinline__ void stage_tri32(mpn<NL>* Ls, mpn<NL>* rinv, int nb, const mpn<NL>* Lkk, int ldl, const mpn<NL>* Mkk, int ldm) {
+template <int NL> __device__ __forceinline__ void stage_tri32(mpn<NL>* Ls, mpn<NL>* rinv, int nb, const mpn<NL>* Lkk, int ldl, const mpn<NL>* Mkk, int ldm, int transposed) {
+  for (int c = threadIdx.x; c < 32; c += blockDim.x) { mpn<NL> v; if (c < nb) v = Mkk[(int64_t)c * ldm + c]; else mp_zero(v); rinv[c] = v; }
+  __syncthreads();
+  // the triangle is stored scaled to a unit diagonal (rows by 1/L_ii for L x = r, columns by 1/L_jj for L^T x = r),
+  // which takes the multiplication by the reciprocal pivot out of the sequential chain of the substitution
   for (int idx = threadIdx.x; idx < 528; idx += blockDim.x) {
     int i = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((i + 1) * (i + 2) / 2 <= idx) i++; while (i * (i + 1) / 2 > idx) i--;
     const int j = idx - i * (i + 1) / 2;
-    mpn<NL> v; if (i < nb) v = Lkk[(int64_t)i * ldl + j]; else mp_zero(v);
+    mpn<NL> v; if (i < nb && j < i) { v = Lkk[(int64_t)i * ldl + j]; mp_mul(v, v, rinv[transposed ? j : i]); } else mp_zero(v);
     Ls[idx] = v;
   }
-  for (int c = threadIdx.x; c < 32; c += blockDim.x) { mpn<NL> v; if (c < nb) v = Mkk[(int64_t)c * ldm + c]; else mp_zero(v); rinv[c] = v; }
 }
 template <int NL> __device__ __forceinline__ void warp_trisolve32(int nb, const mpn<NL>* Ls, const mpn<NL>* rinv, mpn<NL>& r, int transposed) {
   const int lane = threadIdx.x & 31;
+  if (lane < nb) mp_mul(r, r, rinv[lane]);
 #pragma unroll 1
   for (int s = 0; s < nb; s++) {
     const int c = transposed ? nb - 1 - s : s;
-    mpn<NL> x = r;
-    if (lane == c) { mp_mul(x, r, rinv[c]); r = x; }
+    mpn<NL> x;
 #pragma unroll
-    for (int q = 0; q < NL; q++) x.l[q] = __shfl_sync(0xffffffffu, x.l[q], c);
-    x.exp = __shfl_sync(0xffffffffu, x.exp, c); x.sign = __shfl_sync(0xffffffffu, x.sign, c);
+    for (int q = 0; q < NL; q++) x.l[q] = __shfl_sync(0xffffffffu, r.l[q], c);
+    x.exp = __shfl_sync(0xffffffffu, r.exp, c); x.sign = __shfl_sync(0xffffffffu, r.sign, c);
     const bool upd = transposed ? lane < c : (lane > c && lane < nb);
     if (upd) { mpn<NL> t; mp_mul(t, transposed ? Ls[c * (c + 1) / 2 + lane] : Ls[lane * (lane + 1) / 2 + c], x); mp_sub(r, r, t); }
   }
@@ -205,7 +208,7 @@ template <int NL> __device__ __forceinline__ void warp_trisolve32(int nb, const 
 // nvec right-hand sides against one diagonal block: V[v*vs + e*es] <- (L_kk^-1 Src_v)[e].  8 warps per CTA.
 template <int NL> __global__ void __launch_bounds__(256) k_trsm32(int nb, const mpn<NL>* Lkk, int ldl, const mpn<NL>* Mkk, int ldm, mpn<NL>* V, int64_t vs, int64_t es, int nvec, const mpn<NL>* Src, int64_t svs, int64_t ses) {
   __shared__ mpn<NL> Ls[528]; __shared__ mpn<NL> rinv[32];
-  stage_tri32<NL>(Ls, rinv, nb, Lkk, ldl, Mkk, ldm);
+  stage_tri32<NL>(Ls, rinv, nb, Lkk, ldl, Mkk, ldm, 0);
   __syncthreads();
   const int v = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (v >= nvec) return;
@@ -220,7 +223,7 @@ template <int NL> __global__ void __launch_bounds__(1024) k_trsv(int n, const mp
   const int nblk = (n + 31) / 32;
   for (int bi = 0; bi < nblk; bi++) {
     const int b = transposed ? nblk - 1 - bi : bi, k0 = b * 32, nb = min(32, n - k0);
-    stage_tri32<NL>(Ls, rinv, nb, L + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm);
+    stage_tri32<NL>(Ls, rinv, nb, L + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, transposed);
     if (w < nb) {
       mpn<NL> acc; mp_zero(acc);
       if (!transposed) { for (int c = lane; c < k0; c += 32) { mpn<NL> a = L[(int64_t)(k0 + w) * ldl + c], v = x[c]; mp_mul(a, a, v); mp_add(acc, acc, a); } }
@@ -273,13 +276,13 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
     if (warp == 23) {
       // ---- pivot chain: d_{c+1} = a_{c+1,c+1} - l_{c+1,c}^2 (columns < c already applied), r_{c+1} = d^-1/2
       if (c + 1 < nb) {
-        if constexpr (NL == 8) {
+        if constexpr (NL == 8 || NL == 16) {
           // the whole warp works on one number at a time (mpw.cuh): ~4x shorter critical path than one thread
-          wnum l = w_mul(w_load(&As[ix(c + 1, c)]), w_load(&rinv[c]));
-          wnum d = w_sub(w_load(&As[ix(c + 1, c + 1)]), w_mul(l, l));
-          if (d.sign <= 0) { if (lane == 0) bad = 1; mpn<8> one; mp_set_i32(one, 1); d = w_from(one); }
-          w_store(&dpiv[c + 1], d);
-          w_store(&rinv[c + 1], w_rsqrt(d));
+          wnum l = w_mul<NL>(w_load<NL>(&As[ix(c + 1, c)]), w_load<NL>(&rinv[c]));
+          wnum d = w_sub<NL>(w_load<NL>(&As[ix(c + 1, c + 1)]), w_mul<NL>(l, l));
+          if (d.sign <= 0) { if (lane == 0) bad = 1; mpn<NL> one; mp_set_i32(one, 1); d = w_from<NL>(one); }
+          w_store<NL>(&dpiv[c + 1], d);
+          w_store<NL>(&rinv[c + 1], w_rsqrt<NL>(d));
         } else if (lane == 0) {
           mpn<NL> l, d; mp_mul(l, As[ix(c + 1, c)], rinv[c]); mp_mul(l, l, l); mp_sub(d, As[ix(c + 1, c + 1)], l);
           if (d.sign <= 0) { bad = 1; mp_set_i32(d, 1); }
@@ -325,26 +328,26 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
 #define POTRF_SMEM(NL) ((4 * ((NL) > 10 ? 528 : 1024) + 64) * sizeof(mpn<NL>))
 
 // self-test of the warp-cooperative arithmetic against the single-thread routines (bit for bit); one warp per sample
-__global__ void k_selftest_mpw(int n, const mpn<8>* a, const mpn<8>* b, int* mismatches) {
+template <int NL> __global__ void k_selftest_mpw(int n, const mpn<NL>* a, const mpn<NL>* b, int* mismatches) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= n) return;
-  mpn<8> x = a[s], y = b[s], ref, got;
-  mp_mul(ref, x, y); got = w_to(w_mul(w_from(x), w_from(y)));
+  mpn<NL> x = a[s], y = b[s], ref, got;
+  mp_mul(ref, x, y); got = w_to<NL>(w_mul<NL>(w_from<NL>(x), w_from<NL>(y)));
   bool bad = got.sign != ref.sign || (ref.sign != 0 && (got.exp != ref.exp));
-  for (int i = 0; i < 8; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
-  mpn<8> ax = x; ax.sign = ax.sign ? 1 : 0;
-  if (ax.sign) { mp_rsqrt(ref, ax); got = w_to(w_rsqrt(w_from(ax))); bad = bad || got.exp != ref.exp; for (int i = 0; i < 8; i++) bad = bad || got.l[i] != ref.l[i]; }
-  mp_sub(ref, x, y); got = w_to(w_sub(w_from(x), w_from(y)));
-  bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < 8; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
+  for (int i = 0; i < NL; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
+  mpn<NL> ax = x; ax.sign = ax.sign ? 1 : 0;
+  if (ax.sign) { mp_rsqrt(ref, ax); got = w_to<NL>(w_rsqrt<NL>(w_from<NL>(ax))); bad = bad || got.exp != ref.exp; for (int i = 0; i < NL; i++) bad = bad || got.l[i] != ref.l[i]; }
+  mp_sub(ref, x, y); got = w_to<NL>(w_sub<NL>(w_from<NL>(x), w_from<NL>(y)));
+  bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < NL; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
   // cancellation cases: b equal to a except in limb (s mod 8), same exponent, both signs; and a +/- a
-  mpn<8> y2 = x; y2.l[s & 7] ^= (uint32_t)(s * 2654435761u) | 1u; y2.l[7] |= 0x80000000u;
+  mpn<NL> y2 = x; y2.l[s & (NL - 1)] ^= (uint32_t)(s * 2654435761u) | 1u; y2.l[NL - 1] |= 0x80000000u;
   for (int sg = -1; sg <= 1; sg += 2) {
-    y2.sign = x.sign * sg; mp_sub(ref, x, y2); got = w_to(w_sub(w_from(x), w_from(y2)));
-    bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < 8; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
-    mp_add(ref, x, y2); got = w_to(w_add(w_from(x), w_from(y2)));
-    bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < 8; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
+    y2.sign = x.sign * sg; mp_sub(ref, x, y2); got = w_to<NL>(w_sub<NL>(w_from<NL>(x), w_from<NL>(y2)));
+    bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < NL; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
+    mp_add(ref, x, y2); got = w_to<NL>(w_add<NL>(w_from<NL>(x), w_from<NL>(y2)));
+    bad = bad || got.sign != ref.sign || (ref.sign != 0 && got.exp != ref.exp); for (int i = 0; i < NL; i++) bad = bad || (ref.sign != 0 && got.l[i] != ref.l[i]);
   }
-  mp_sub(ref, x, x); got = w_to(w_sub(w_from(x), w_from(x))); bad = bad || got.sign != 0 || ref.sign != 0;
+  mp_sub(ref, x, x); got = w_to<NL>(w_sub<NL>(w_from<NL>(x), w_from<NL>(x))); bad = bad || got.sign != 0 || ref.sign != 0;
   if (bad && lane == 0) atomicAdd(mismatches, 1);
 }
 

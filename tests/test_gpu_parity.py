@@ -345,6 +345,11 @@ def test_warp_cooperative_arithmetic_selftest(tiny):
     fn = tiny.lib.clrs_debug_selftest
     fn.restype = C.c_int
     assert fn(tiny.h) == 0
+    s16 = Solver(workloads.maxcut(workloads.laplacian_cycle(3), prec=512), lib="device")      # 16 limbs: 32 product columns fill the warp
+    try:
+        assert fn(s16.h) == 0
+    finally:
+        s16.close()
 
 
 def test_three_point_bound_config4():
