@@ -134,6 +134,10 @@ def cpu_arm(n, steps, warmup, target_seconds=12.0, kind="maxcut"):
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (build commands, NCCL's version
+    # banner, library chatter) is sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -153,11 +157,11 @@ def main():
         if rank != 0:
             return
         its, cores, desc = cpu_arm(args.n, max(1, args.steps), max(0, min(args.warmup, 1)), kind=args.workload)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        print(file=real_stdout, flush=True, *[json.dumps({"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "mpfr (cpu)", "data": "synthetic", "config": config(args.n, args.gpus, args.workload, workload(args.n, args.workload) if args.workload != "maxcut" else None),
                           "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
-                          "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
         return
 
     import torch
@@ -273,7 +277,7 @@ def main():
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     S.close()
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), file=real_stdout, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
