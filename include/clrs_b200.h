@@ -87,7 +87,7 @@ enum {
  * reference converts rationals such as gamma = 9//10 at full precision,
  * src/solver.jl:138-139). */
 typedef struct clrs_options {
-  int32_t prec;                      /* bits; 256 default (precision(BigFloat)) */
+  int32_t prec;                      /* bits; 256 default (precision(BigFloat)); <= 512 in this build (8, 10 or 16 limbs) */
   int32_t matmul_prec;               /* bits for pairings/S GEMMs; 0 = prec     */
   double  beta_infeasible;           /* 3//10 */
   double  beta_feasible;             /* 1//10 */
