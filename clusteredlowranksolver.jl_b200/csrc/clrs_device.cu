@@ -233,7 +233,7 @@ template <int NL> struct Solver : SolverBase {
   void split_rows(Sliced& s, const num* A, int lda, int M, int K, int lay = 0) { split(s, rows_view(A, lda, M, K), true, lay); }
   void split_cols(Sliced& s, const num* B, int ldb, int K, int N, int lay = 0) { split(s, cols_view(B, ldb, K, N), false, lay); }
   // does a product of this shape go to the tensor cores?
-  bool use_tc(int M, int N, int K) const { if (opt.gemm_path == 1) return false; if (opt.gemm_path == 2) return M >= 1 && N >= 1 && K >= 1; return M >= 128 && N >= 32 && K >= 96; }
+  bool use_tc(int M, int N, int K) const { if (opt.gemm_path == 1) return false; if (opt.gemm_path == 2) return M >= 1 && N >= 1 && K >= 1; return M >= 128 && N >= 32 && K >= 96 && ((int64_t)M * N > 256 * 256 || K > 512); }   // up to ~256^3 the CUDA-core kernel wins (measured: 130^3 0.06 vs 0.20 ms, 200^3 0.16 vs 0.24, 300^3 0.34 vs 0.25)
 
   // C (M x N) = op(D, A*B);  A, B sliced with vector offsets a0, b0
   void gemm(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode = 0, const num* D = nullptr, int ldd = 0,

@@ -566,6 +566,9 @@ template <int NL> __global__ void k_tc_recombine(int M, int N, int Npitch, int b
   constexpr int NS = I8Cfg<NL>::NS;
   // trans: the product was formed with the operands swapped (small left operand on the N side); element (m,n) goes to C[n][m]
   // nsum > 1: the `batch` planes are split-K partial results of ONE product and are summed here
+  // (measured alternatives that were slower or no faster than this one-output-per-thread form: four outputs per thread
+  //  with 32-bit plane loads - register count 47 -> 168; results staged in shared memory for 128-byte stores - 0.7 -> 1.1 ms
+  //  on 27e6 outputs: the kernel is bound by load/store instruction issue, not by sectors; profiles/r01_hbm_kernels_ncu.txt)
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int nb = nsum > 1 ? 1 : batch;
   if (idx >= (int64_t)nb * M * N) return;
