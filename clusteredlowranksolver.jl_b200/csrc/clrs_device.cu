@@ -307,7 +307,8 @@ template <int NL> struct Solver : SolverBase {
   // members the helpers use; kernels capture their pointers at enqueue time, so swapping while enqueuing is safe.
   struct Ctx { cudaStream_t st = nullptr; Sliced tA, tB; num* chol_W = nullptr; size_t chol_W_cap = 0; uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0;
                num* trsm_R = nullptr; size_t trsm_cap = 0; cudaEvent_t ev = nullptr; };
-  Ctx side;
+  Ctx side, side2;                                   // side: Cholesky of Y; side2: R = mu I - XY beside chol(X), and Y's step-length eigenvalue beside X's
+  cudaEvent_t evR0 = nullptr, evR1 = nullptr, evE0 = nullptr, evE1 = nullptr; num *U2 = nullptr, *T1b = nullptr; double* Td2 = nullptr; double* eigV2 = nullptr; EigTask* eigT2 = nullptr;
   cudaEvent_t evY0 = nullptr, evY1 = nullptr; num *LY = nullptr, *MinvY = nullptr;
   void swap_with(Ctx& c) { std::swap(st, c.st); std::swap(tA, c.tA); std::swap(tB, c.tB); std::swap(chol_W, c.chol_W); std::swap(chol_W_cap, c.chol_W_cap);
     std::swap(tc_bytes, c.tc_bytes); std::swap(tc_top, c.tc_top); std::swap(tc_cap, c.tc_cap); std::swap(trsm_R, c.trsm_R); std::swap(trsm_cap, c.trsm_cap); }
@@ -469,7 +470,7 @@ template <int NL> struct Solver : SolverBase {
     int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError("no CUDA device: libclrs_b200 has no CPU fallback");
     CK(cudaSetDevice(o.device)); cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, o.device));
     if (pr.major < 10) throw CudaError("an sm_100 device is required");
-    CK(cudaStreamCreate(&st)); CK(cudaStreamCreate(&side.st)); CK(cudaEventCreateWithFlags(&evY0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY1, cudaEventDisableTiming));
+    CK(cudaStreamCreate(&st)); CK(cudaStreamCreate(&side.st)); CK(cudaStreamCreate(&side2.st)); for (cudaEvent_t* e : {&evR0, &evR1, &evE0, &evE1}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY1, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming)); for (int k = 1; k < NCTX; k++) { CK(cudaStreamCreate(&pctx[k].st)); CK(cudaEventCreateWithFlags(&pctx[k].ev, cudaEventDisableTiming)); }
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
@@ -484,7 +485,8 @@ template <int NL> struct Solver : SolverBase {
   ~Solver() {
     cudaSetDevice(opt.device); cudaDeviceSynchronize();
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-    owned_sliced.push_back(&tA); owned_sliced.push_back(&tB); owned_sliced.push_back(&side.tA); owned_sliced.push_back(&side.tB);
+    owned_sliced.push_back(&tA); owned_sliced.push_back(&tB); owned_sliced.push_back(&side.tA); owned_sliced.push_back(&side.tB); owned_sliced.push_back(&side2.tA); owned_sliced.push_back(&side2.tB);
+    if (side2.tc_bytes) cudaFree(side2.tc_bytes); if (side2.tc_top) cudaFree(side2.tc_top); cudaStreamDestroy(side2.st); for (cudaEvent_t e : {evR0, evR1, evE0, evE1}) if (e) cudaEventDestroy(e);
     if (side.tc_bytes) cudaFree(side.tc_bytes); if (side.tc_top) cudaFree(side.tc_top); cudaEventDestroy(evY0); cudaEventDestroy(evY1); cudaStreamDestroy(side.st);
     for (int k = 1; k < NCTX; k++) { Ctx& c = pctx[k]; owned_sliced.push_back(&c.tA); owned_sliced.push_back(&c.tB); if (c.tc_bytes) cudaFree(c.tc_bytes); if (c.tc_top) cudaFree(c.tc_top);
       if (c.ev) cudaEventDestroy(c.ev); if (c.st) cudaStreamDestroy(c.st); }
@@ -550,7 +552,9 @@ template <int NL> struct Solver : SolverBase {
     tmpU = dalloc<num>(N);
     Td = dalloc<double>(tot); lamX = dalloc<double>(blk.size()); lamY = dalloc<double>(blk.size());
     { std::vector<EigTask> et; size_t vtot = 0; for (Block* b0 : blk) vtot += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); eigV = dalloc<double>(vtot); size_t o = 0;
-      for (Block* b0 : blk) { EigTask t; t.T = Td + b0->off; t.n = b0->n; t.V = eigV + o; o += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); et.push_back(t); } eigT = upload(et); }
+      for (Block* b0 : blk) { EigTask t; t.T = Td + b0->off; t.n = b0->n; t.V = eigV + o; o += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); et.push_back(t); } eigT = upload(et);
+      Td2 = dalloc<double>(tot); eigV2 = dalloc<double>(vtot); U2 = dalloc<num>(tot); T1b = dalloc<num>(tot);
+      for (auto& t : et) { t.T = Td2 + (t.T - Td); t.V = eigV2 + (t.V - eigV); } eigT2 = upload(et); }
     for (auto& c0 : cl) {
       if (!c0.owned) continue;
       c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.LinvB = dalloc<num>((size_t)c0.P * N); c0.t = dalloc<num>(c0.P);
@@ -805,14 +809,15 @@ template <int NL> struct Solver : SolverBase {
   }
   // lambda_min( L^-1 dM L^-T ) per block in Float64  (compute_step_length, src/solver.jl:1620-1693); Mi holds L^-1
   void step_eigs(const num* Mi, const num* dM, double* lam, bool forY) {
+    num* Ub = forY ? U2 : U; num* Tb = forY ? T1b : T1; double* Tdb = forY ? Td2 : Td; EigTask* et = forY ? eigT2 : eigT;    // own buffers: the two run side by side
     par_blocks([&](Block* b0) { const int n = b0->n; if (n == 1) return;
       Sliced& ms = forY ? b0->MSY : b0->MS;                                                             // rows of L^-1 (Y's are split on the side stream)
       if (!forY) split_rows(ms, Mi + b0->off, n, n, n, b0->lay);
-      split_cols(tB, dM + b0->off, n, n, n, b0->lay); gemm(ms, 0, tB, 0, n, n, U + b0->off, n);          // U = L^-1 dM
-      split_rows(tA, U + b0->off, n, n, n, b0->lay); gemm(tA, 0, ms, 0, n, n, T1 + b0->off, n); });        // T = U L^-T
-    nlaunch++, k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, T1, Td);
+      split_cols(tB, dM + b0->off, n, n, n, b0->lay); gemm(ms, 0, tB, 0, n, n, Ub + b0->off, n);         // U = L^-1 dM
+      split_rows(tA, Ub + b0->off, n, n, n, b0->lay); gemm(tA, 0, ms, 0, n, n, Tb + b0->off, n); });       // T = U L^-T
+    nlaunch++, k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, Tb, Tdb);
     if (!blk.empty()) { int maxn = 1; for (Block* b0 : blk) maxn = std::max(maxn, b0->n);
-      nlaunch++, k_min_eig<<<(unsigned)blk.size(), maxn <= 32 ? 128 : (maxn <= 128 ? 256 : EIG_THREADS), 0, st>>>(eigT, lam); }
+      nlaunch++, k_min_eig<<<(unsigned)blk.size(), maxn <= 32 ? 128 : (maxn <= 128 ? 256 : EIG_THREADS), 0, st>>>(et, lam); }
   }
 
   int check_status() { return hflags[FL_STATUS]; }
@@ -838,8 +843,11 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaEventRecord(evY1, st)); swap_ctx();
     scalar(0);                                                        // mu, mu_p  (SC_D0 = <X,Y> is kept current)
     // R = mu_p I - X Y
-    par_blocks([&](Block* b0) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n, b0->lay); split_rows(tA, X + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); });
+    par_blocks([&](Block* b0) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n, b0->lay); });      // Y panels: used by R, the Schur products and the directions
+    CK(cudaEventRecord(evR0, st)); swap_with(side2); CK(cudaStreamWaitEvent(st, evR0, 0));                      // R is first needed by the predictor: beside chol(X) and the Schur assembly
+    par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, X + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); });
     k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, (const num*)nullptr, sc + SC_MUP);
+    CK(cudaEventRecord(evR1, st)); swap_with(side2);
     CK(cudaEventRecord(ev[1], st));
     // Cholesky of X, L^-1, X^-1  (src/solver.jl:388-399, 1117)
     copy(L, X, tot);
@@ -849,6 +857,7 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaEventRecord(ev[2], st));
     decomposition(3);                                                 // events 3..7
     trace_pairings(tr); residuals();
+    CK(cudaStreamWaitEvent(st, evR1, 0));
     CK(cudaEventRecord(ev[8], st));
     direction();                                                      // predictor
     CK(cudaEventRecord(ev[9], st));
@@ -861,9 +870,12 @@ template <int NL> struct Solver : SolverBase {
     direction();                                                      // corrector
     CK(cudaEventRecord(ev[12], st));
     // step lengths: X reuses its factor of this iteration (X is unchanged); Y is factored here
+    CK(cudaEventRecord(evE0, st)); swap_with(side2); CK(cudaStreamWaitEvent(st, evE0, 0)); CK(cudaStreamWaitEvent(st, evY1, 0));
+    step_eigs(MinvY, dY, lamY, true);                                                                           // Y's eigenvalue beside X's
+    CK(cudaEventRecord(evE1, st)); swap_with(side2);
     step_eigs(Minv, dX, lamX, false); scalar(2, X, dX, lamX); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAD);
-    CK(cudaStreamWaitEvent(st, evY1, 0));
-    step_eigs(MinvY, dY, lamY, true); scalar(2, Y, dY, lamY); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAP);
+    CK(cudaStreamWaitEvent(st, evY1, 0)); CK(cudaStreamWaitEvent(st, evE1, 0));
+    scalar(2, Y, dY, lamY); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAP);
     scalar(3);
     CK(cudaEventRecord(ev[13], st));
     // the step  (src/solver.jl:485-495)
