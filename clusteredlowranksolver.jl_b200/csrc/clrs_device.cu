@@ -274,7 +274,8 @@ template <int NL> struct Solver : SolverBase {
     // default: both operands in shared memory (k_gemm_tc); CLRS_TC_TS=1 selects the variant with the left
     // operand chunk in TMEM (k_gemm_ts, tiles of at most 112 columns) — measured slower once four warps issue MMAs
     static const bool ts = getenv("CLRS_TC_TS") != nullptr;
-    const int bnmax = ts ? 112 : 128; const int ntn = (N + bnmax - 1) / bnmax; int BN = ((N + ntn - 1) / ntn + 15) & ~15; if (BN > bnmax) BN = bnmax;
+    // column tiles: full 128-column tiles with a narrower last one (k_gemm_tc issues N = 16..128 per tile); the TS variant keeps balanced tiles <= 112
+    const int bnmax = ts ? 112 : 128; const int ntn = (N + bnmax - 1) / bnmax; int BN = ts ? (((N + ntn - 1) / ntn + 15) & ~15) : std::min(128, (N + 15) & ~15); if (BN > bnmax) BN = bnmax;
     const int Npitch = (N + 15) & ~15;
     CUtensorMap mA = make_map(A, tc::BM), mB = make_map(B, BN);
     // K longer than the int32 headroom (35 slices * K * 2^14 < 2^31), or few tiles with a long K: split K over

@@ -109,6 +109,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int n0 = blockIdx.x * a.BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
   if (a.lower_only && n0 > m0 + BM - 1) return;
   const int NS = a.NS, BN = a.BN;
+  const int bn = min(BN, ((a.N - n0) + 15) & ~15);            // the last column tile may be narrower: MMAs and epilogue cover bn columns (TMA still fills BN rows, zeros beyond N)
   const int ngroups = (NS + GROUP - 1) / GROUP;
   const int kbase = a.kz_stride > 0 ? a.k0 + bz * a.kz_stride : a.k0;
   const int Kp = a.kz_stride > 0 ? min(a.kz_stride, a.Kp_total - bz * a.kz_stride) : a.Kp;
@@ -170,7 +171,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // counts are constant.
     static_assert(NA == 4 && NB == 8, "ring phase shifts below assume NA = 4, NB = 8");
     const int koff = warp - 1;
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint64_t descA0 = make_desc(smem_u32(ringA)), descB0 = make_desc(smem_u32(ringB));   // slot s: + s * (SLOT_BYTES >> 4)
     const bool leader = (lane == 0);
     const bool dbgon = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 1;
@@ -233,7 +234,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(tmem_full, full_parity); full_parity ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 4] = clock64();
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = 0; c0 < bn; c0 += 16) {
         int32_t carry[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) carry[q] = 0;

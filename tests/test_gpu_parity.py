@@ -362,3 +362,71 @@ def test_three_point_bound_config4():
 def test_three_point_bound_with_univariate_part():
     """d2 >= 0 adds the 1x1 a_k blocks with sample-dependent eigenvalues."""
     _compare(workloads.three_point_bound(4, Fraction(1, 6), 3, 3), omega_p=10 ** 3, omega_d=10 ** 3)
+
+
+# ---- solver options and stop reasons (src/solver.jl:100-137 keyword arguments, terminate() :921-950) ----
+
+def _hist(r):
+    return [(h["iter"], h["alpha_p"], h["alpha_d"], h["beta_c"]) for h in r.history]
+
+
+@pytest.mark.parametrize("kw", [
+    dict(need_dual_feasible=True),
+    dict(need_primal_feasible=True),
+    dict(correctoronly=True),
+    dict(safe_step=False),
+    dict(gamma=Fraction(7, 10), beta_feasible=Fraction(1, 5), beta_infeasible=Fraction(2, 5)),
+    dict(omega_p=10 ** 4, omega_d=10 ** 6),
+    dict(maxiterations=7),
+])
+def test_solver_options_take_the_same_path_as_the_oracle(kw):
+    """Every keyword of solvesdp that changes the iteration must change it the same way in both arms: same status,
+    same error code, same iteration count, same step lengths and centering parameters (to double rounding)."""
+    sdp = workloads.polyopt_random(8, 3)
+    dev = solvesdp(sdp, lib="device", duality_gap_threshold=1e-30, **kw)
+    ref = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-30, **kw)
+    assert (dev.status, dev.error_code, dev.iterations) == (ref.status, ref.error_code, ref.iterations), (dev, ref)
+    for a, b in zip(_hist(dev), _hist(ref)):
+        assert a[0] == b[0] and all(abs(x - y) <= 1e-9 * max(1.0, abs(y)) for x, y in zip(a[1:], b[1:])), (a, b)
+    # converged runs agree far below the gap; runs stopped early differ by the Float64 step lengths (alpha comes from a
+    # double-precision eigenvalue, so the iterates agree to ~1e-16 relative until the optimum pulls them together)
+    tol = mpmath.mpf(10) ** -20 if ref.status == "Optimal" else mpmath.mpf(10) ** -8
+    with mpmath.workprec(400):
+        assert abs(dev.p_obj - ref.p_obj) <= tol * max(1, abs(ref.p_obj))
+
+
+def test_duplicate_constraint_fails_in_the_same_place_as_the_oracle():
+    """Two copies of one constraint make S singular: both arms must raise the reference's SolverFailure for the Schur
+    complement (src/solver.jl:1246-1250) instead of returning numbers."""
+    import copy
+    sdp = copy.deepcopy(workloads.maxcut(workloads.laplacian_cycle(5)))
+    c2 = sdp.clusters[0]
+    P = c2.P
+    c2.c = np.concatenate([c2.c, c2.c[:1]])                       # a copy of constraint 0: same matrix, same right-hand side
+    c2.B = np.concatenate([c2.B, c2.B[:1]], axis=0)
+    c2.blocks[0].dense[P] = c2.blocks[0].dense[0]               # (lazy dense matrices: the same object serves both keys)
+    outs = []
+    for lib in ("device", "oracle"):
+        r = solvesdp(sdp, lib=lib, duality_gap_threshold=1e-30, maxiterations=60)
+        outs.append(r)
+    dev, ref = outs
+    assert dev.error_code == ref.error_code and dev.status == ref.status, (dev, ref)
+    assert abs(dev.iterations - ref.iterations) <= 1
+
+
+def test_warm_start_continues_identically_on_the_device():
+    """clrs_get_state / clrs_set_state (src/solver.jl:202-239): a solver restarted from a saved iterate takes the same
+    iterations as the uninterrupted one (the state crosses the ABI as exact wire numbers)."""
+    sdp = workloads.sphere_packing(8, 5, [Fraction(1, 2), Fraction(1, 2)])
+    a = Solver(sdp, lib="device")
+    for _ in range(6):
+        a.iterate()
+    x, X, y, Y = a.get_state()
+    b = Solver(sdp, lib="device")
+    b.set_state(x, X, y, Y)
+    for _ in range(5):
+        ia, ib = a.iterate(), b.iterate()
+        assert ia.p_obj == ib.p_obj and ia.d_obj == ib.d_obj and ia.alpha_p == ib.alpha_p and ia.mu == ib.mu
+    xa, Xa, ya, Ya = a.get_state(); xb, Xb, yb, Yb = b.get_state()
+    assert Xa.tobytes() == Xb.tobytes() and xa.tobytes() == xb.tobytes() and Ya.tobytes() == Yb.tobytes()
+    a.close(); b.close()
