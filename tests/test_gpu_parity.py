@@ -395,23 +395,21 @@ def test_solver_options_take_the_same_path_as_the_oracle(kw):
         assert abs(dev.p_obj - ref.p_obj) <= tol * max(1, abs(ref.p_obj))
 
 
-def test_duplicate_constraint_fails_in_the_same_place_as_the_oracle():
-    """Two copies of one constraint make S singular: both arms must raise the reference's SolverFailure for the Schur
-    complement (src/solver.jl:1246-1250) instead of returning numbers."""
-    import copy
-    sdp = copy.deepcopy(workloads.maxcut(workloads.laplacian_cycle(5)))
-    c2 = sdp.clusters[0]
-    P = c2.P
-    c2.c = np.concatenate([c2.c, c2.c[:1]])                       # a copy of constraint 0: same matrix, same right-hand side
-    c2.B = np.concatenate([c2.B, c2.B[:1]], axis=0)
-    c2.blocks[0].dense[P] = c2.blocks[0].dense[0]               # (lazy dense matrices: the same object serves both keys)
-    outs = []
+def test_indefinite_iterate_raises_the_same_solver_failure_as_the_oracle():
+    """A warm start whose X is not positive definite must stop in the Cholesky factorisation of X with the reference's
+    SolverFailure (src/solver.jl:389-392, src/tools.jl:92-95) in both arms, not return numbers."""
+    sdp = workloads.polyopt_random(6, 1)
+    msgs = []
     for lib in ("device", "oracle"):
-        r = solvesdp(sdp, lib=lib, duality_gap_threshold=1e-30, maxiterations=60)
-        outs.append(r)
-    dev, ref = outs
-    assert dev.error_code == ref.error_code and dev.status == ref.status, (dev, ref)
-    assert abs(dev.iterations - ref.iterations) <= 1
+        s = Solver(sdp, lib=lib)
+        x, X, y, Y = s.get_state()
+        X = X.copy(); X["sign"] = -X["sign"]                      # X = -omega_p I
+        s.set_state(x, X, y, Y)
+        with pytest.raises(clrs_b200.SolverFailure) as e:
+            s.iterate()
+        msgs.append(str(e.value))
+        s.close()
+    assert msgs[0][:4] == msgs[1][:4] and msgs[0].startswith("[1"), msgs      # same failure site code
 
 
 def test_warm_start_continues_identically_on_the_device():
