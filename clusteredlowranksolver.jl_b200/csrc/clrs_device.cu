@@ -206,7 +206,11 @@ template <int NL> struct Solver : SolverBase {
 
   // ---- sliced panels -------------------------------------------------------
   // lay 0: dp4a words sl[vec][K4][NSP];  lay 1: tc planes planes[t][vec][Kp] (gemm_tc.cuh)
-  struct Sliced { int32_t* sl = nullptr; int32_t* E = nullptr; uint8_t* planes = nullptr; int nvec = 0, K = 0, K4 = 0, Kp = 0, lay = 0; size_t cap_w = 0, cap_v = 0, cap_b = 0; };
+  struct Sliced { int32_t* sl = nullptr; int32_t* E = nullptr; uint8_t* planes = nullptr; int nvec = 0, K = 0, K4 = 0, Kp = 0, lay = 0; size_t cap_w = 0, cap_v = 0, cap_b = 0;
+                  int64_t vpitch = 0;   /* vectors per plane when this is a view of a larger panel (0: nvec) */
+                  int64_t pitch() const { return vpitch ? vpitch : nvec; } };
+  // vectors [v0, v0 + cnt) of a tensor-core panel as a panel of their own (no ownership)
+  static Sliced view(const Sliced& f, int v0, int cnt) { Sliced s = f; s.planes = f.planes + (size_t)v0 * f.Kp; s.E = f.E + v0; s.nvec = cnt; s.vpitch = f.pitch(); s.cap_w = s.cap_v = s.cap_b = 0; return s; }
   void ensure(Sliced& s, int nvec, int K, int lay) {
     int K4 = (K + 3) / 4; int Kp = (K + 31) & ~31;
     if ((size_t)nvec > s.cap_v) { if (s.E) CK(cudaFreeAsync(s.E, st)); s.cap_v = nvec; CK(cudaMallocAsync((void**)&s.E, std::max<size_t>(s.cap_v, 1) * sizeof(int32_t), st)); }
@@ -214,21 +218,22 @@ template <int NL> struct Solver : SolverBase {
       if (need > s.cap_w) { if (s.sl) CK(cudaFreeAsync(s.sl, st)); s.cap_w = need; CK(cudaMallocAsync((void**)&s.sl, std::max<size_t>(s.cap_w, 4) * sizeof(int32_t), st)); } }
     else { size_t need = (size_t)NS * nvec * Kp;
       if (need > s.cap_b) { if (s.planes) CK(cudaFreeAsync(s.planes, st)); s.cap_b = need; CK(cudaMallocAsync((void**)&s.planes, std::max<size_t>(s.cap_b, 16), st)); } }
-    s.nvec = nvec; s.K = K; s.K4 = K4; s.Kp = Kp; s.lay = lay;
+    s.nvec = nvec; s.K = K; s.K4 = K4; s.Kp = Kp; s.lay = lay; s.vpitch = 0;
   }
   std::vector<Sliced*> owned_sliced;
   static VecView rows_view(const num* A, int lda, int M, int K) { VecView v; v.base = A; v.bstride = 0; v.vper = M > 0 ? M : 1; v.sv = lda; v.sk = 1; v.nvec = M; v.K = K; return v; }
   static VecView cols_view(const num* B, int ldb, int K, int N) { VecView v; v.base = B; v.bstride = 0; v.vper = N > 0 ? N : 1; v.sv = 1; v.sk = ldb; v.nvec = N; v.K = K; return v; }
-  void split(Sliced& s, const VecView& v, bool kfast, int lay = 0) {
-    ensure(s, v.nvec, v.K, lay); if (v.nvec == 0 || v.K == 0) return;
+  void split(Sliced& s, const VecView& v, bool kfast, int lay = 0, bool is_view = false) {
+    if (!is_view) ensure(s, v.nvec, v.K, lay);
+    if (v.nvec == 0 || v.K == 0) return;
     if (lay == 0 && v.K <= 512) { nlaunch++, k_split_warp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl); return; }
     nlaunch++, k_vec_exp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 255) / 256), 256, 0, st>>>(v, s.E);
     if (lay == 0) { int64_t tot_ = (int64_t)v.nvec * s.K4;
       nlaunch++, k_split<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0); }
     else if (kfast) { int64_t tot_ = (int64_t)v.nvec * (s.Kp / 4);
-      nlaunch++, k_split_tc<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes, 1); }
+      nlaunch++, k_split_tc<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.Kp, s.pitch(), s.planes, 1); }
     else { constexpr int VT = SplitTCfg<NL>::VT; dim3 grid((v.nvec + VT - 1) / VT, s.Kp / 32);
-      nlaunch++, k_split_tc_t<NL><<<grid, VT * 8, 0, st>>>(v, s.E, s.Kp, (int64_t)v.nvec, s.planes); }
+      nlaunch++, k_split_tc_t<NL><<<grid, VT * 8, 0, st>>>(v, s.E, s.Kp, s.pitch(), s.planes); }
   }
   void split_rows(Sliced& s, const num* A, int lda, int M, int K, int lay = 0) { split(s, rows_view(A, lda, M, K), true, lay); }
   void split_cols(Sliced& s, const num* B, int ldb, int K, int N, int lay = 0) { split(s, cols_view(B, ldb, K, N), false, lay); }
@@ -261,7 +266,7 @@ template <int NL> struct Solver : SolverBase {
   CUtensorMap make_map(const Sliced& P, int box_rows) {
     if (!encode_fn) { void* fn = nullptr; cudaDriverEntryPointQueryResult q; CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q)); if (!fn) throw CudaError("cuTensorMapEncodeTiled not available"); encode_fn = (EncodeFn)fn; }
     CUtensorMap m; cuuint64_t dims[3] = {(cuuint64_t)P.Kp, (cuuint64_t)P.nvec, (cuuint64_t)NS};
-    cuuint64_t strides[2] = {(cuuint64_t)P.Kp, (cuuint64_t)P.Kp * (cuuint64_t)P.nvec};
+    cuuint64_t strides[2] = {(cuuint64_t)P.Kp, (cuuint64_t)P.Kp * (cuuint64_t)P.pitch()};
     cuuint32_t box[3] = {(cuuint32_t)tc::KC, (cuuint32_t)box_rows, 1}; cuuint32_t es[3] = {1, 1, 1};
     CUresult r = encode_fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, P.planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -750,13 +755,30 @@ template <int NL> struct Solver : SolverBase {
   }
   void pairings_dense(Block& b0) {                    // T = X^-1 A_p Y, S[p,q] += <A_q, T>   (src/solver.jl:1089-1104)
     const int n = b0.n, np = b0.np; if (np == 0) return; const int64_t nn = (int64_t)n * n;
+    static const int nchunk_env = getenv("CLRS_SCHUR_CHUNKS") ? atoi(getenv("CLRS_SCHUR_CHUNKS")) : 4;   // measured on n = P = 300: 16.6 / 16.4 / 16.2 / 16.0 ms for 1 / 2 / 3 / 4 chunks
+    const int nchunk = (b0.lay == 1 && b0.AallV.lay == 1 && (int64_t)np * n >= 32768) ? std::max(1, std::min(nchunk_env, NCTX)) : 1;
+    if (nchunk > 1) {
+      // the constraints are processed in chunks on different execution contexts: while one chunk's products occupy the
+      // tensor pipe, the other's recombination / exponent / split kernels (HBM and load-store bound) run beside them
+      ensure(b0.T1S, np * n, n, 1); ensure(b0.T2V, np, n * n, 1);
+      par_for(nchunk, [&](int c) {
+        const int p0 = (int)((int64_t)np * c / nchunk), cnt = (int)((int64_t)np * (c + 1) / nchunk) - p0; if (cnt == 0) return;
+        Sliced Ac = view(b0.AallB, p0 * n, cnt * n), T1c = view(b0.T1S, p0 * n, cnt * n), T2c = view(b0.T2V, p0, cnt);
+        num* T1p = b0.T1 + (int64_t)p0 * nn; num* T2p = b0.T2 + (int64_t)p0 * nn;
+        gemm(Ac, 0, b0.XiS, 0, cnt * n, n, T1p, n);
+        { VecView v; v.base = T1p; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = cnt * n; v.K = n; split(T1c, v, false, 1, true); }
+        gemm(T1c, 0, b0.YS, 0, cnt * n, n, T2p, n);
+        { VecView v; v.base = T2p; v.bstride = 0; v.vper = cnt; v.sv = nn; v.sk = 1; v.nvec = cnt; v.K = n * n; split(T2c, v, true, 1, true); }
+      });
+    } else {
     // T1t[(p,j)][i] = sum_k A_p[k][j] X^-1[i][k]   (= (X^-1 A_p)^T; the 90000-row operand sits on the 128-lane M side)
     gemm(b0.AallB, 0, b0.XiS, 0, np * n, n, b0.T1, n);
     // T2[(p,i)][b] = sum_j T1_p[i][j] Y[j][b]
     { VecView v; v.base = b0.T1; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = np * n; v.K = n; split(b0.T1S, v, false, b0.lay); }
     gemm(b0.T1S, 0, b0.YS, 0, np * n, n, b0.T2, n);
-    // S[p,q] += sum_ab T2_p[ab] A_q[ab]
     { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true, b0.AallV.lay); }
+    }
+    // S[p,q] += sum_ab T2_p[ab] A_q[ab]
     gemm(b0.AallV, 0, b0.T2V, 0, np, np, b0.Sd, np, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);          // Sd[q][p], q >= p only
   }
   void schur_add_dense(Clu& c0, Block& b0) {
