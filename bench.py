@@ -40,7 +40,7 @@ def workload(n, kind="maxcut"):
     from clrs_b200 import workloads
     from fractions import Fraction as F
     if kind == "sphere":        # BASELINE.json configs[4]: many clusters coupled through the free variables; shards by cluster
-        return workloads.sphere_packing(8, n if n != 300 else 23, [F(1, 2), F(1, 2), F(3, 4), F(1)], prec=512)
+        return workloads.sphere_packing(8, n if n != 300 else 31, [F(1, 2), F(1, 2), F(3, 4), F(1)], prec=512)   # SURVEY.md §8(d) size (4,31): J=16, N=641, P=1294
     if kind == "threepoint":    # configs[3] at the size of examples/ThreePointBound.jl (one cluster: the dense F_k blocks are shared)
         return workloads.three_point_bound(4, F(1, 6), n if n != 300 else 10, n if n != 300 else 10, prec=256)
     return workloads.maxcut(workloads.laplacian_random(n, 0.5, 0), prec=256)

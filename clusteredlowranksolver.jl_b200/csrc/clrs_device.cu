@@ -462,7 +462,7 @@ template <int NL> struct Solver : SolverBase {
   int64_t gtot = 0;  // numbers in all blocks of the SDP
   // device state
   num *X = nullptr, *Y = nullptr, *Cm = nullptr, *L = nullptr, *Minv = nullptr, *Xi = nullptr, *R = nullptr, *P = nullptr, *dX = nullptr, *dY = nullptr, *T1 = nullptr, *TXY = nullptr, *U = nullptr;
-  num* tmpU = nullptr;
+  num* tmpU = nullptr; num* LinvBall = nullptr; int Pown = 0;
   num *x = nullptr, *y = nullptr, *c = nullptr, *b = nullptr, *d = nullptr, *p = nullptr, *dx = nullptr, *dy = nullptr, *tr = nullptr, *Q = nullptr, *QMinv = nullptr, *tmpN = nullptr;
   num* sc = nullptr; int* flags = nullptr; double* dinfo = nullptr; double* Td = nullptr; double* lamX = nullptr; double* lamY = nullptr; double* eigV = nullptr; EigTask* eigT = nullptr;
   int64_t* d_boff = nullptr; int32_t* d_bn = nullptr; BlockTab bt;
@@ -561,9 +561,13 @@ template <int NL> struct Solver : SolverBase {
       for (Block* b0 : blk) { EigTask t; t.T = Td + b0->off; t.n = b0->n; t.V = eigV + o; o += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); et.push_back(t); } eigT = upload(et);
       Td2 = dalloc<double>(tot); eigV2 = dalloc<double>(vtot); U2 = dalloc<num>(tot); T1b = dalloc<num>(tot);
       for (auto& t : et) { t.T = Td2 + (t.T - Td); t.V = eigV2 + (t.V - eigV); } eigT2 = upload(et); }
+    // the L_j^-1 B_j of the owned clusters are the row blocks of ONE matrix, so Q = (vcat LinvB)^T (vcat LinvB) is one product (:1268-1269)
+    Pown = 0; for (auto& c0 : cl) if (c0.owned) Pown += c0.P;
+    LinvBall = dalloc<num>((size_t)Pown * N);
+    { int64_t o = 0; for (auto& c0 : cl) if (c0.owned) { c0.LinvB = LinvBall + o * N; o += c0.P; } }
     for (auto& c0 : cl) {
       if (!c0.owned) continue;
-      c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.LinvB = dalloc<num>((size_t)c0.P * N); c0.t = dalloc<num>(c0.P);
+      c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.t = dalloc<num>(c0.P);
       for (auto& b0 : c0.blocks) if (int rc = finalize_block(c0, b0)) return rc;
     }
     // scalars
@@ -796,10 +800,10 @@ template <int NL> struct Solver : SolverBase {
     if (N > 0) {
       par_clusters([&](Clu& c0) { if (c0.P) trsm_lower(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.B, N, N, c0.LinvB, N); });     // LinvB = L^-1 B  (:1258)
       CK(cudaEventRecord(ev[e0 + 2], st));
-      zero(Q, (int64_t)N * N);
-      for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
-        split_cols(tA, c0.LinvB, N, c0.P, N, use_tc(N, N, c0.P) ? 1 : 0);
-        gemm(tA, 0, tA, 0, N, N, Q, N, 2, Q, N); }                                                       // Q = sum LinvB^T LinvB  (:1268-1269)
+      if (Pown == 0) zero(Q, (int64_t)N * N);
+      else { split_cols(tA, LinvBall, N, Pown, N, use_tc(N, N, Pown) ? 1 : 0);
+        gemm(tA, 0, tA, 0, N, N, Q, N, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);                                  // Q = (vcat LinvB)^T (vcat LinvB), lower triangle  (:1268-1269)
+        nlaunch++, k_mirror<NL><<<grid_for((int64_t)N * N), 256, 0, st>>>(N, Q, N, 0); }
       allreduce(Q, (int64_t)N * N, 0);                                                                  // the only cross-cluster coupling
       CK(cudaEventRecord(ev[e0 + 3], st));
       chol(Q, N, N, QMinv, N, CLRS_ERR_CHOL_Q, false);
