@@ -431,8 +431,16 @@ template <int NL> struct Solver : SolverBase {
       nlaunch++, k_trsm32<NL><<<(ncols + 7) / 8, 256, 0, st>>>(nb, Lf + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, Xo + (int64_t)k0 * ldx, 1, ldx, ncols, rhs, 1, ldr);
     }
   }
+  // x <- L^-1 x (forward) or L^-T x (backward) by block substitution: diagonal block solve, then right-looking update
   void trsv(const num* Lf, int ldl, int n, const num* Minv, int ldm, num* xv, bool transposed) {
-    if (n > 0) nlaunch++, k_trsv<NL><<<1, 1024, 0, st>>>(n, Lf, ldl, Minv, ldm, xv, transposed ? 1 : 0);
+    const int nblk = (n + 31) / 32;
+    for (int bi = 0; bi < nblk; bi++) {
+      const int b = transposed ? nblk - 1 - bi : bi, k0 = b * 32, nb = std::min(32, n - k0);
+      nlaunch++, k_trsv_block<NL><<<1, 1024, 0, st>>>(nb, Lf + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, xv + k0, transposed ? 1 : 0);
+      if (!transposed) { const int rem = n - k0 - nb;                                           // rows below: L[k0+nb.., k0..k0+nb)
+        if (rem > 0) nlaunch++, k_trsv_update<NL><<<(rem + 7) / 8, 256, 0, st>>>(rem, nb, Lf + (int64_t)(k0 + nb) * ldl + k0, (int64_t)ldl, 1, xv + k0, xv + k0 + nb); }
+      else if (k0 > 0) nlaunch++, k_trsv_update<NL><<<(k0 + 7) / 8, 256, 0, st>>>(k0, nb, Lf + (int64_t)k0 * ldl, 1, (int64_t)ldl, xv + k0, xv);   // columns left: L[k0..k0+nb, 0..k0)^T
+    }
   }
 
   // ---- problem description -------------------------------------------------------------

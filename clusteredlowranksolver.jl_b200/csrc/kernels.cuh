@@ -217,28 +217,44 @@ template <int NL> __global__ void __launch_bounds__(256) k_trsm32(int nb, const 
   if (lane < nb) V[(int64_t)v * vs + (int64_t)lane * es] = r;
 }
 
-template <int NL> __global__ void __launch_bounds__(1024) k_trsv(int n, const mpn<NL>* L, int ldl, const mpn<NL>* Minv, int ldm, mpn<NL>* x, int transposed) {
+// One block step of the blocked vector solve, two kernels (host loop in Solver::trsv):
+//  k_trsv_block  - the 32 x 32 diagonal block: x_b <- L_bb^-1 x_b (or L_bb^-T).  With 8 or 16 limbs every row is owned by a
+//                  warp and the multiply-subtract of a step is warp-cooperative (mpw.cuh), one CTA barrier per column:
+//                  the chain is 32 x (w_mul + w_sub) instead of 32 single-thread multiplications.
+//  k_trsv_update - right-looking update of the rows still to be solved: r_i -= L[i, b] . x_b, one warp per row.
+template <int NL> __global__ void __launch_bounds__(1024) k_trsv_block(int nb, const mpn<NL>* Lkk, int ldl, const mpn<NL>* Mkk, int ldm, mpn<NL>* xb, int transposed) {
   __shared__ mpn<NL> Ls[528]; __shared__ mpn<NL> rinv[32]; __shared__ mpn<NL> rs[32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nblk = (n + 31) / 32;
-  for (int bi = 0; bi < nblk; bi++) {
-    const int b = transposed ? nblk - 1 - bi : bi, k0 = b * 32, nb = min(32, n - k0);
-    stage_tri32<NL>(Ls, rinv, nb, L + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, transposed);
-    if (w < nb) {
-      mpn<NL> acc; mp_zero(acc);
-      if (!transposed) { for (int c = lane; c < k0; c += 32) { mpn<NL> a = L[(int64_t)(k0 + w) * ldl + c], v = x[c]; mp_mul(a, a, v); mp_add(acc, acc, a); } }
-      else { for (int c = k0 + nb + lane; c < n; c += 32) { mpn<NL> a = L[(int64_t)c * ldl + k0 + w], v = x[c]; mp_mul(a, a, v); mp_add(acc, acc, a); } }
-      warp_reduce_add(acc);
-      if (lane == 0) { mpn<NL> r = x[k0 + w]; mp_sub(r, r, acc); rs[w] = r; }
-    }
+  stage_tri32<NL>(Ls, rinv, nb, Lkk, ldl, Mkk, ldm, transposed);
+  if (threadIdx.x < 32) { mpn<NL> v; if (threadIdx.x < nb) v = xb[threadIdx.x]; else mp_zero(v); rs[threadIdx.x] = v; }
+  __syncthreads();
+  if constexpr (NL == 8 || NL == 16) {
+    if (w < nb) { const wnum r = w_mul<NL>(w_load<NL>(&rs[w]), w_load<NL>(&rinv[w])); __syncwarp(); w_store<NL>(&rs[w], r); }
     __syncthreads();
-    if (w == 0) {
-      mpn<NL> r; if (lane < nb) r = rs[lane]; else mp_zero(r);
-      warp_trisolve32<NL>(nb, Ls, rinv, r, transposed);
-      if (lane < nb) x[k0 + lane] = r;
+    for (int s = 0; s < nb; s++) {
+      const int c = transposed ? nb - 1 - s : s;
+      const bool upd = transposed ? (w < c) : (w > c && w < nb);
+      if (upd) {
+        const wnum l = w_load<NL>(transposed ? &Ls[c * (c + 1) / 2 + w] : &Ls[w * (w + 1) / 2 + c]);
+        const wnum r = w_sub<NL>(w_load<NL>(&rs[w]), w_mul<NL>(l, w_load<NL>(&rs[c])));
+        __syncwarp(); w_store<NL>(&rs[w], r);
+      }
+      __syncthreads();
     }
+  } else {
+    if (w == 0) { mpn<NL> r = rs[lane]; warp_trisolve32<NL>(nb, Ls, rinv, r, transposed); rs[lane] = r; }
     __syncthreads();
   }
+  if (threadIdx.x < nb) xb[threadIdx.x] = rs[threadIdx.x];
+}
+// rows [0, nrows) of r: r[i] -= sum_{c < nb} Lp[i, c] * xb[c], element (i, c) at Lp[i * rs_ + c * cs_]
+template <int NL> __global__ void __launch_bounds__(256) k_trsv_update(int nrows, int nb, const mpn<NL>* Lp, int64_t rs_, int64_t cs_, const mpn<NL>* xb, mpn<NL>* r) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= nrows) return;
+  mpn<NL> acc; mp_zero(acc);
+  if (lane < nb) { mpn<NL> a = Lp[(int64_t)i * rs_ + (int64_t)lane * cs_], v = xb[lane]; mp_mul(acc, a, v); }
+  warp_reduce_add(acc);
+  if (lane == 0) { mpn<NL> v = r[i]; mp_sub(v, v, acc); r[i] = v; }
 }
 
 // ---------------------------------------------------------------------------
