@@ -306,16 +306,24 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
         }
       }
     } else if (warp >= 16) {
-      // ---- column c of the factor, then the trailing update with it
-      const int ut = tid - 512;                           // 0..223
-      if (ut == 0) { mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[ix(c, c)] = sq; }
-      for (int i = c + 1 + ut; i < nb; i += 224) { mpn<NL> a; mp_mul(a, As[ix(i, c)], rinv[c]); Ls[ix(i, c)] = a; }
-      asm volatile("bar.sync 1, 224;" ::: "memory");
-      const int w = nb - c - 1;
-      for (int idx = ut + 1; idx < w * (w + 1) / 2; idx += 224) {                // lower triangle only; idx 0 = (c+1,c+1) belongs to the pivot chain
-        int ii = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((ii + 1) * (ii + 2) / 2 <= idx) ii++; while (ii * (ii + 1) / 2 > idx) ii--;
-        const int i = c + 1 + ii, j = c + 1 + (idx - ii * (ii + 1) / 2);
-        mpn<NL> a = As[ix(i, j)], t; mp_mul(t, Ls[ix(i, c)], Ls[ix(j, c)]); mp_sub(a, a, t); As[ix(i, j)] = a;
+      // ---- column c of the factor, then the trailing update with it (warps 16-21); warp 22 forms the diagonal entry
+      // (square root with one correction step: nobody's input inside the kernel, so it stays off every critical path)
+      if (warp == 22) {
+        if constexpr (NL == 8 || NL == 16) {
+          const wnum d = w_load<NL>(&dpiv[c]), y = w_load<NL>(&rinv[c]);
+          wnum sq = w_mul<NL>(d, y); wnum t = w_mul<NL>(w_sub<NL>(d, w_mul<NL>(sq, sq)), y); t.exp -= (t.sign != 0); sq = w_add<NL>(sq, t);
+          w_store<NL>(&Ls[ix(c, c)], sq);
+        } else if (lane == 0) { mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[ix(c, c)] = sq; }
+      } else {
+        const int ut = tid - 512;                         // 0..191
+        for (int i = c + 1 + ut; i < nb; i += 192) { mpn<NL> a; mp_mul(a, As[ix(i, c)], rinv[c]); Ls[ix(i, c)] = a; }
+        asm volatile("bar.sync 1, 192;" ::: "memory");
+        const int w = nb - c - 1;
+        for (int idx = ut + 1; idx < w * (w + 1) / 2; idx += 192) {              // lower triangle only; idx 0 = (c+1,c+1) belongs to the pivot chain
+          int ii = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((ii + 1) * (ii + 2) / 2 <= idx) ii++; while (ii * (ii + 1) / 2 > idx) ii--;
+          const int i = c + 1 + ii, j = c + 1 + (idx - ii * (ii + 1) / 2);
+          mpn<NL> a = As[ix(i, j)], t; mp_mul(t, Ls[ix(i, c)], Ls[ix(j, c)]); mp_sub(a, a, t); As[ix(i, j)] = a;
+        }
       }
     } else {
       // ---- row c of the inverse: M[c][c] = r_c, M[c][j] = -r_c sum_{k=j}^{c-1} L[c][k] M[k][j]   (16 warps)

@@ -206,13 +206,49 @@ template <int NL> HD void mp_neg(mpn<NL>& r) { r.sign = -r.sign; }
 template <int NL> HD void mp_addmul(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>& b) { mpn<NL> t; mp_mul(t, a, b); mp_add(r, r, t); }
 template <int NL> HD void mp_submul(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>& b) { mpn<NL> t; mp_mul(t, a, b); mp_sub(r, r, t); }
 
-// ---- reciprocal, division, (inverse) square root: Newton from a double seed ----
-template <int NL> HD constexpr int mp_newton_steps() { return NL <= 3 ? 1 : (NL <= 6 ? 2 : (NL <= 13 ? 3 : (NL <= 26 ? 4 : 5))); }
+// ---- reciprocal, division, (inverse) square root: Newton from a double-double seed ----
+// The seed is one Newton step carried out in double-double arithmetic on the top 96 mantissa bits (~95 correct bits
+// for a dozen double operations), which saves one full-precision Newton step (two or three multi-limb products on the
+// sequential pivot chain of the Cholesky panels).  The double operations are written with explicit roundings
+// (__dmul_rn / __fma_rn on the device, no contraction on the host) so host and device produce the same seed.
+#ifdef __CUDA_ARCH__
+#define CLRS_DMUL(a, b) __dmul_rn((a), (b))
+#define CLRS_DADD(a, b) __dadd_rn((a), (b))
+#define CLRS_DFMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#define CLRS_DMUL(a, b) ((a) * (b))
+#define CLRS_DADD(a, b) ((a) + (b))
+#define CLRS_DFMA(a, b, c) fma((a), (b), (c))
+#endif
+template <int NL> HD constexpr int mp_newton_steps() { return 32 * NL <= 160 ? 1 : (32 * NL <= 352 ? 2 : (32 * NL <= 704 ? 3 : 4)); }
+// top 96 bits of a mantissa given by its three leading limbs, times 2^sc, as an exact sum hi + lo of two doubles
+HD void mp_mant_dd(uint32_t A, uint32_t B, uint32_t C, int sc, double& hi, double& lo) {
+  hi = ldexp((double)A, sc - 32) + ldexp((double)(B >> 11), sc - 53);      // 32 + 21 = 53 bits: exact
+  lo = ldexp((double)(B & 2047u), sc - 64) + ldexp((double)C, sc - 96);    // 11 + 32 = 43 bits: exact
+}
+// y0 + c = m^(-1/2) (1 + O(2^-95)) for m = mh + ml in [1/4, 1)
+HD void dd_rsqrt_seed(double mh, double ml, double& y0, double& c) {
+  y0 = 1.0 / sqrt(mh);
+  const double ph = CLRS_DMUL(y0, y0), pl = CLRS_DFMA(y0, y0, -ph);          // y0^2 = ph + pl
+  const double th = CLRS_DMUL(mh, ph), tl0 = CLRS_DFMA(mh, ph, -th);         // mh ph = th + tl0
+  const double tl = CLRS_DADD(tl0, CLRS_DADD(CLRS_DMUL(mh, pl), CLRS_DMUL(ml, ph)));
+  const double e = CLRS_DADD(CLRS_DADD(1.0, -th), -tl);                      // 1 - m y0^2 (1 - th is exact)
+  c = CLRS_DMUL(CLRS_DMUL(0.5, y0), e);
+}
+// x0 + c = 1/m (1 + O(2^-95)) for m = mh + ml in [1/2, 1)
+HD void dd_recip_seed(double mh, double ml, double& x0, double& c) {
+  x0 = 1.0 / mh;
+  const double th = CLRS_DMUL(mh, x0), tl0 = CLRS_DFMA(mh, x0, -th);
+  const double tl = CLRS_DADD(tl0, CLRS_DMUL(ml, x0));
+  const double e = CLRS_DADD(CLRS_DADD(1.0, -th), -tl);
+  c = CLRS_DMUL(x0, e);
+}
 
 template <int NL> HD void mp_recip(mpn<NL>& r, const mpn<NL>& a) {
   if (a.sign == 0) { mp_zero(r); return; }
   mpn<NL> m = a; m.exp = 0; m.sign = 1;                   // mantissa in [1/2,1)
-  mpn<NL> x, t, two; mp_from_double(x, 1.0 / mp_to_double(m)); mp_set_i32(two, 2);
+  double mh, ml, x0, c; mp_mant_dd(a.l[NL - 1], a.l[NL - 2], NL >= 3 ? a.l[NL >= 3 ? NL - 3 : 0] : 0u, 0, mh, ml); dd_recip_seed(mh, ml, x0, c);
+  mpn<NL> x, t, two; mp_from_double(x, x0); mp_from_double(t, c); mp_add(x, x, t); mp_set_i32(two, 2);
 #pragma unroll 1
   for (int it = 0; it < mp_newton_steps<NL>(); it++) { mp_mul(t, m, x); mp_sub(t, two, t); mp_mul(x, x, t); }
   x.exp -= a.exp; x.sign = a.sign; r = x;
@@ -224,7 +260,8 @@ template <int NL> HD void mp_div(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>& b)
 // r = a^(-1/2) for a > 0
 template <int NL> HD void mp_rsqrt(mpn<NL>& r, const mpn<NL>& a) {
   mpn<NL> m = a; const int odd = a.exp & 1; m.exp = -odd; m.sign = 1;   // m in [1/4,1), a = m 2^(exp+odd), exponent even
-  mpn<NL> y, t, three; mp_from_double(y, 1.0 / sqrt(mp_to_double(m))); mp_set_i32(three, 3);
+  double mh, ml, y0, c; mp_mant_dd(a.l[NL - 1], a.l[NL - 2], NL >= 3 ? a.l[NL >= 3 ? NL - 3 : 0] : 0u, -odd, mh, ml); dd_rsqrt_seed(mh, ml, y0, c);
+  mpn<NL> y, t, three; mp_from_double(y, y0); mp_from_double(t, c); mp_add(y, y, t); mp_set_i32(three, 3);
 #pragma unroll 1
   for (int it = 0; it < mp_newton_steps<NL>(); it++) { mp_mul(t, y, y); mp_mul(t, t, m); mp_sub(t, three, t); mp_mul(y, y, t); y.exp -= 1; }
   y.exp -= (a.exp + odd) / 2; r = y;

@@ -147,10 +147,10 @@ template <int NL> __device__ __forceinline__ wnum w_add(const wnum& a, const wnu
 // r = a^(-1/2), a > 0: Newton from a double seed, multiplications warp-cooperative
 template <int NL> __device__ __forceinline__ wnum w_rsqrt(const wnum& a) {
   wnum m = a; const int odd = a.exp & 1; m.exp = -odd; m.sign = 1;
-  const uint32_t h7 = __shfl_sync(0xffffffffu, a.limb, NL - 1), h6 = __shfl_sync(0xffffffffu, a.limb, NL - 2);
-  const double md = ldexp((double)(((uint64_t)h7 << 32) | h6), -64 - odd);
-  mpn<NL> y0, three; mp_from_double(y0, 1.0 / sqrt(md)); mp_set_i32(three, 3);
-  wnum y = w_from<NL>(y0); const wnum w3 = w_from<NL>(three);
+  const uint32_t A = __shfl_sync(0xffffffffu, a.limb, NL - 1), B = __shfl_sync(0xffffffffu, a.limb, NL - 2), C = __shfl_sync(0xffffffffu, a.limb, NL - 3);
+  double mh, ml, y0d, cd; mp_mant_dd(A, B, C, -odd, mh, ml); dd_rsqrt_seed(mh, ml, y0d, cd);     // same seed as mp_rsqrt
+  mpn<NL> y0, c0, three; mp_from_double(y0, y0d); mp_from_double(c0, cd); mp_set_i32(three, 3);
+  wnum y = w_add<NL>(w_from<NL>(y0), w_from<NL>(c0)); const wnum w3 = w_from<NL>(three);
 #pragma unroll 1
   for (int it = 0; it < mp_newton_steps<NL>(); it++) { wnum t = w_mul<NL>(y, y); t = w_mul<NL>(t, m); t = w_sub<NL>(w3, t); y = w_mul<NL>(y, t); y.exp -= 1; }
   y.exp -= (a.exp + odd) / 2;
