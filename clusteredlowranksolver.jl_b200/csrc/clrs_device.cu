@@ -398,7 +398,7 @@ template <int NL> struct Solver : SolverBase {
     if (ldm == n) zero(Minv, (int64_t)n * n); else for (int r = 0; r < n; r++) zero(Minv + (int64_t)r * ldm, n);
     for (int k0 = 0; k0 < n; k0 += 32) {
       const int nb = std::min(32, n - k0), rem = n - k0 - nb;
-      nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code);
+      nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code, full_inverse ? 1 : 0);
       if (rem > 0) {
         num* A21 = A + (int64_t)(k0 + nb) * lda + k0; num* A22 = A + (int64_t)(k0 + nb) * lda + k0 + nb;
         if (full_inverse) { split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);

@@ -267,7 +267,7 @@ template <int NL> __global__ void __launch_bounds__(256) k_trsv_update(int nrows
 // thread and is overlapped with the trailing update of the block (7 warps) and with the rows of the
 // inverse factor (16 warps); two CTA-wide barriers per column.
 #define POTRF_THREADS 768
-template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(int nb, mpn<NL>* A, int lda, mpn<NL>* Minv, int ldm, int* status, int code) {
+template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(int nb, mpn<NL>* A, int lda, mpn<NL>* Minv, int ldm, int* status, int code, int want_inv) {
   extern __shared__ unsigned char smraw[];
   // beyond 10 limbs four full 32 x 32 arrays do not fit in shared memory: keep the lower triangles only
   constexpr bool PACK = NL > 10; constexpr int SZ = PACK ? 528 : 1024;
@@ -305,21 +305,24 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
           dpiv[c + 1] = d; mpn<NL> r; mp_rsqrt(r, d); rinv[c + 1] = r;
         }
       }
-    } else if (warp >= 16) {
-      // ---- column c of the factor, then the trailing update with it (warps 16-21); warp 22 forms the diagonal entry
+    } else if (warp >= 16 || !want_inv) {
+      // ---- column c of the factor, then the trailing update with it (warps 16-21, plus warps 0-15 when the inverse of the
+      // factor is not wanted: Schur and Q blocks); warp 22 forms the diagonal entry
       // (square root with one correction step: nobody's input inside the kernel, so it stays off every critical path)
       if (warp == 22) {
         if constexpr (NL == 8 || NL == 16) {
           const wnum d = w_load<NL>(&dpiv[c]), y = w_load<NL>(&rinv[c]);
           wnum sq = w_mul<NL>(d, y); wnum t = w_mul<NL>(w_sub<NL>(d, w_mul<NL>(sq, sq)), y); t.exp -= (t.sign != 0); sq = w_add<NL>(sq, t);
           w_store<NL>(&Ls[ix(c, c)], sq);
-        } else if (lane == 0) { mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[ix(c, c)] = sq; }
+          if (!want_inv && lane == 0) Ms[ix(c, c)] = rinv[c];                   // only the reciprocal pivots are used by the substitution kernels
+        } else if (lane == 0) { if (!want_inv) Ms[ix(c, c)] = rinv[c]; mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[ix(c, c)] = sq; }
       } else {
-        const int ut = tid - 512;                         // 0..191
-        for (int i = c + 1 + ut; i < nb; i += 192) { mpn<NL> a; mp_mul(a, As[ix(i, c)], rinv[c]); Ls[ix(i, c)] = a; }
-        asm volatile("bar.sync 1, 192;" ::: "memory");
+        const int nupd = want_inv ? 192 : 704;            // threads of this role
+        const int ut = want_inv ? tid - 512 : tid;        // 0..nupd-1 (tid < 704: warps 0..21)
+        for (int i = c + 1 + ut; i < nb; i += nupd) { mpn<NL> a; mp_mul(a, As[ix(i, c)], rinv[c]); Ls[ix(i, c)] = a; }
+        asm volatile("bar.sync 1, %0;" ::"r"(nupd) : "memory");
         const int w = nb - c - 1;
-        for (int idx = ut + 1; idx < w * (w + 1) / 2; idx += 192) {              // lower triangle only; idx 0 = (c+1,c+1) belongs to the pivot chain
+        for (int idx = ut + 1; idx < w * (w + 1) / 2; idx += nupd) {              // lower triangle only; idx 0 = (c+1,c+1) belongs to the pivot chain
           int ii = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((ii + 1) * (ii + 2) / 2 <= idx) ii++; while (ii * (ii + 1) / 2 > idx) ii--;
           const int i = c + 1 + ii, j = c + 1 + (idx - ii * (ii + 1) / 2);
           mpn<NL> a = As[ix(i, j)], t; mp_mul(t, Ls[ix(i, c)], Ls[ix(j, c)]); mp_sub(a, a, t); As[ix(i, j)] = a;
