@@ -419,16 +419,19 @@ template <int NL> struct Solver : SolverBase {
       }
     }
   }
-  // X = L^-1 B by block forward substitution (approx_solve_tril!, src/solver.jl:1258): L_kk X_k = B_k - L[k,0:k0] X[0:k0]
-  num* trsm_R = nullptr; size_t trsm_cap = 0;
+  // X = L^-1 B by block forward substitution (approx_solve_tril!, src/solver.jl:1258), right-looking: the block row is
+  // solved against its diagonal block (k_trsm32), then it updates the rows below, B[k0+nb:, :] -= L[k0+nb:, k-block] X_k
+  // (a K = 32 product: every panel is split exactly once)
+  num* trsm_R = nullptr; size_t trsm_cap = 0;   // (per-context scratch slot, kept for the context swap)
   void trsm_lower(const num* Lf, int ldl, int n, const num* Minv, int ldm, const num* B, int ldb, int ncols, num* Xo, int ldx) {
     if (n == 0 || ncols == 0) return;
-    size_t need = (size_t)32 * ncols; if (need > trsm_cap) { trsm_R = dalloc<num>(need); trsm_cap = need; }
+    if (ldb == ncols && ldx == ncols) copy(Xo, B, (int64_t)n * ncols); else for (int r = 0; r < n; r++) copy(Xo + (int64_t)r * ldx, B + (int64_t)r * ldb, ncols);
     for (int k0 = 0; k0 < n; k0 += 32) {
-      const int nb = std::min(32, n - k0);
-      const num* rhs = B + (int64_t)k0 * ldb; int ldr = ldb;
-      if (k0 > 0) { mm(Lf + (int64_t)k0 * ldl, ldl, Xo, ldx, nb, ncols, k0, trsm_R, ncols, 1, B + (int64_t)k0 * ldb, ldb); rhs = trsm_R; ldr = ncols; }
-      nlaunch++, k_trsm32<NL><<<(ncols + 7) / 8, 256, 0, st>>>(nb, Lf + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, Xo + (int64_t)k0 * ldx, 1, ldx, ncols, rhs, 1, ldr);
+      const int nb = std::min(32, n - k0), rem = n - k0 - nb;
+      num* Xk = Xo + (int64_t)k0 * ldx;
+      nlaunch++, k_trsm32<NL><<<(ncols + 7) / 8, 256, 0, st>>>(nb, Lf + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, Xk, 1, ldx, ncols, Xk, 1, ldx);
+      if (rem > 0) { num* Xr = Xo + (int64_t)(k0 + nb) * ldx;
+        mm(Lf + (int64_t)(k0 + nb) * ldl + k0, ldl, Xk, ldx, rem, ncols, nb, Xr, ldx, 1, Xr, ldx); }
     }
   }
   // x <- L^-1 x (forward) or L^-T x (backward) by block substitution: diagonal block solve, then right-looking update
