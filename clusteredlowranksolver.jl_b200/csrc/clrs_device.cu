@@ -227,6 +227,11 @@ template <int NL> struct Solver : SolverBase {
     if (!is_view) ensure(s, v.nvec, v.K, lay);
     if (v.nvec == 0 || v.K == 0) return;
     if (lay == 0 && v.K <= 512) { nlaunch++, k_split_warp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl); return; }
+    if (v.K >= 8192 && (int64_t)v.nvec * 32 < 148 * 2048) {           // few long vectors: several CTAs per vector
+      const int ny = std::max(1, std::min((v.K + 2047) / 2048, (148 * 16 + v.nvec - 1) / v.nvec));
+      nlaunch++, k_fill_i32<<<(v.nvec + 255) / 256, 256, 0, st>>>(v.nvec, s.E, I8_EXP_NONE);
+      nlaunch++, k_vec_exp_long<NL><<<dim3(v.nvec, ny), 256, 0, st>>>(v, s.E);
+    } else
     nlaunch++, k_vec_exp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 255) / 256), 256, 0, st>>>(v, s.E);
     if (lay == 0) { int64_t tot_ = (int64_t)v.nvec * s.K4;
       nlaunch++, k_split<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0); }
@@ -598,6 +603,7 @@ template <int NL> struct Solver : SolverBase {
     own(b0.YS); own(b0.XiS); own(b0.MS); own(b0.MSY); b0.lay = use_tc(n, n, n) ? 1 : 0;
     if (b0.high_rank) {
       b0.np = (int)b0.dense_p.size();
+      if (use_tc(b0.np * n, n, n)) b0.lay = 1;          // the (np n) x n x n Schur products decide the panel layout of a dense block (n = 100: 7.1 ms on the CUDA cores -> 5.0 ms)
       std::vector<int32_t> pl(b0.dense_p.begin(), b0.dense_p.end()); b0.d_plist = upload(pl);
       std::vector<num> all((size_t)b0.np * n * n); for (int i = 0; i < b0.np; i++) std::copy(b0.dense_A[i].begin(), b0.dense_A[i].end(), all.begin() + (size_t)i * n * n);
       { // nonzero structure of the A_p (their zero entries contribute exact zeros to <A_p,Z> and sum_p x_p A_p):
@@ -770,14 +776,20 @@ template <int NL> struct Solver : SolverBase {
   }
   void pairings_dense(Block& b0) {                    // T = X^-1 A_p Y, S[p,q] += <A_q, T>   (src/solver.jl:1089-1104)
     const int n = b0.n, np = b0.np; if (np == 0) return; const int64_t nn = (int64_t)n * n;
-    static const int nchunk_env = getenv("CLRS_SCHUR_CHUNKS") ? atoi(getenv("CLRS_SCHUR_CHUNKS")) : 4;   // measured on n = P = 300: 16.6 / 16.4 / 16.2 / 16.0 ms for 1 / 2 / 3 / 4 chunks
-    const int nchunk = (b0.lay == 1 && b0.AallV.lay == 1 && (int64_t)np * n >= 32768) ? std::max(1, std::min(nchunk_env, NCTX)) : 1;
+    // chunk of constraints = a whole number of waves of the product's CTAs on the 148 SMs (n = 300: 3 column tiles x 148 row
+    // tiles = 63 constraints = exactly 3 waves), so chunking costs no extra partial wave
+    static const int chunks_off = getenv("CLRS_SCHUR_CHUNKS") ? atoi(getenv("CLRS_SCHUR_CHUNKS")) == 1 : 0;
+    int pc = np;
+    if (!chunks_off && b0.lay == 1 && b0.AallV.lay == 1 && (int64_t)np * n >= 32768) {
+      const int ntn = (n + 127) / 128; int k = 1; while ((148 * k) % ntn) k++;
+      pc = std::max(1, (148 * k / ntn) * 128 / n); }
+    const int nchunk = (np + pc - 1) / pc;
     if (nchunk > 1) {
       // the constraints are processed in chunks on different execution contexts: while one chunk's products occupy the
       // tensor pipe, the other's recombination / exponent / split kernels (HBM and load-store bound) run beside them
       ensure(b0.T1S, np * n, n, 1); ensure(b0.T2V, np, n * n, 1);
       par_for(nchunk, [&](int c) {
-        const int p0 = (int)((int64_t)np * c / nchunk), cnt = (int)((int64_t)np * (c + 1) / nchunk) - p0; if (cnt == 0) return;
+        const int p0 = c * pc, cnt = std::min(pc, np - p0); if (cnt <= 0) return;
         Sliced Ac = view(b0.AallB, p0 * n, cnt * n), T1c = view(b0.T1S, p0 * n, cnt * n), T2c = view(b0.T2V, p0, cnt);
         num* T1p = b0.T1 + (int64_t)p0 * nn; num* T2p = b0.T2 + (int64_t)p0 * nn;
         gemm(Ac, 0, b0.XiS, 0, cnt * n, n, T1p, n);

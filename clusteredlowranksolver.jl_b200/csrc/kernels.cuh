@@ -398,6 +398,21 @@ template <int NL> __global__ void k_vec_exp(VecView v, int32_t* E) {
   for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
   if (lane == 0) E[vec] = e;
 }
+// long vectors (the flattened n x n matrices of the dense Schur products, K = n^2): one warp per vector would leave the
+// GPU idle, so each vector is cut into gridDim.y ranges; E must be pre-filled with I8_EXP_NONE (k_fill_i32)
+template <int NL> __global__ void __launch_bounds__(256) k_vec_exp_long(VecView v, int32_t* E) {
+  __shared__ int32_t red[8];
+  const int vec = blockIdx.x;
+  const mpn<NL>* p = (const mpn<NL>*)v.base + vec_off(v, vec);
+  const int per = (v.K + gridDim.y - 1) / gridDim.y, k0 = blockIdx.y * per, k1 = min(v.K, k0 + per);
+  int32_t e = I8_EXP_NONE;
+  for (int k = k0 + threadIdx.x; k < k1; k += 256) { const mpn<NL>* q = p + (int64_t)k * v.sk; if (q->sign != 0) e = max(e, q->exp); }
+  for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int w = 1; w < 8; w++) e = max(e, red[w]); if (e != I8_EXP_NONE) atomicMax(E + vec, e); }
+}
+__global__ void k_fill_i32(int n, int32_t* p, int32_t val) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = val; }
 // one thread per (vec, k4): split 4 consecutive entries into NS digits and pack them per slice.
 // kfast != 0: consecutive threads take consecutive k4 (unit-stride vectors), else consecutive vectors.
 template <int NL> __global__ void k_split(VecView v, const int32_t* E, int K4, int32_t* sl, int kfast) {

@@ -428,3 +428,13 @@ def test_warm_start_continues_identically_on_the_device():
     xa, Xa, ya, Ya = a.get_state(); xb, Xb, yb, Yb = b.get_state()
     assert Xa.tobytes() == Xb.tobytes() and xa.tobytes() == xb.tobytes() and Ya.tobytes() == Yb.tobytes()
     a.close(); b.close()
+
+
+def test_maxcut_complete_graph_n100_dense_schur_on_tensor_cores():
+    """n = 100 < 128: the block products stay small, but the (P n) x n x n dense Schur products are tensor-core shaped and
+    decide the panel layout of the block."""
+    n = 100
+    dev = solvesdp(workloads.maxcut(workloads.laplacian_complete(n)), lib="device", duality_gap_threshold=1e-30)
+    assert dev.status == "Optimal"
+    assert abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -24
+    assert abs(dev.d_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -24
