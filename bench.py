@@ -250,7 +250,7 @@ def main():
     peak_src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense = 2x bf16 rate)" if peaks else "2 x 1.4 PFLOP/s fallback of B200_PROFILING.md"
     classes = {"dp4a": "k_gemm_dp4a (CUDA-core int8 path, small shapes)",
                "tc_small": "tc::k_gemm_tc + k_tc_recombine, products with < 1e6 outputs (block-level n x n products, split-K Schur dots)",
-               "tc_large": "tc::k_gemm_tc + k_tc_recombine, the two 90000 x 300 x 300 products of the dense Schur path"}
+               "tc_large": "tc::k_gemm_tc + k_tc_recombine, the two 90000 x 300 x 300 products of the dense Schur path (in chunks of 63 constraints = 3 waves of CTAs)"}
     def rl(c):
         ms, mpf, nl = prof[c]["ms"], prof[c]["mp_flops"], prof[c]["launches"]
         ach = (mpf * 528.0 / (ms / 1e3)) / 1e12 if ms > 0 else 0.0
@@ -259,8 +259,9 @@ def main():
     dom = max(classes, key=lambda c: prof[c]["ms"])
     r = rl(dom)
     roofline = {"bound": "tensor", "kernel": r["kernel"], "achieved": r["achieved"], "peak": 2 * bf16,
-                "unit": "TOP/s (int8, canonical 2*M*N*K*528 per 256-bit GEMM)", "frac": r["frac"], "traffic": 2.93e9 if dom == "tc_large" else None,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of the 90000x300x300 product, ncu --set full (profiles/r01_tc_kernel_ncu_full.txt); algorithmic 2.08e9",
+                "unit": "TOP/s (int8, canonical 2*M*N*K*528 per 256-bit GEMM)", "frac": r["frac"],
+                "traffic": (2.93e9 * (2.0 * min(K, 2)) / max(1, r["launches"])) if (dom == "tc_large" and args.workload == "maxcut" and args.n == 300) else None,
+                "traffic_note": "per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE 90000x300x300 launch (2.93e9; ncu --set full, profiles/r01_tc_kernel_ncu_full.txt; algorithmic 2.08e9) scaled by rows per launch - the two 90000-row products of an iteration run as wave-sized chunks of constraints, and traffic is proportional to rows (A slices in, byte planes out)",
                 "peak_source": peak_src, "launches": r["launches"], "avg_launch_ms": r["avg_launch_ms"], "gemm_share_of_step": r["share_of_step"],
                 "other_gemm_classes": {c: rl(c) for c in classes if c != dom}}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K,
