@@ -293,7 +293,7 @@ template <int NL> struct Solver : SolverBase {
     const int KMAX = ((1 << 17) / NS / 128) * 128; int tiles = 0;      // int32 headroom: NS * K * 2^14 < 2^31
     for (int by = 0; by < (M + tc::BM - 1) / tc::BM; by++) for (int bx = 0; bx < (N + BN - 1) / BN; bx++) if (!lower_only || bx * BN <= by * tc::BM + tc::BM - 1) tiles++;
     int nch = (A.Kp + KMAX - 1) / KMAX;
-    if (batch == 1 && tiles < 148 && A.Kp >= 256) { const int waves = (tiles * nch + 147) / 148; nch = std::max(nch, std::min(waves * 148 / tiles, A.Kp >= 2048 ? A.Kp / 512 : A.Kp / 128)); }
+    if (batch == 1 && tiles < 148 && A.Kp >= 256) { const int waves = (tiles * nch + 147) / 148; nch = std::max(nch, std::min(waves * 148 / tiles, A.Kp >= 2048 ? A.Kp / 512 : (A.Kp + 127) / 128)); }
     if (nch > 1 && batch != 1) throw CudaError("gemm_tc: split-K with a batch is not supported");
     int kch = ((A.Kp + nch - 1) / nch + 127) & ~127; nch = (A.Kp + kch - 1) / kch;
     const size_t outs2 = (size_t)std::max(batch, nch) * M * Npitch;
