@@ -61,16 +61,44 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
     def __init__(self):
-        self.rows = []
+        self.rows = []          # nvidia-smi rows (fallback)
         self.proc = None
+        self.samples = []       # (sm_mhz, reason bitmask) from NVML
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
+        self.max_mhz = None
 
-    def start(self):
+    def start(self, device=0):
+        # NVML in a polling thread (a sample every ~5 ms, so even a 100 ms timed region is covered); nvidia-smi -lms as fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and vis.split(",")[device].isdigit() else device
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
                  "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -80,6 +108,22 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self, device=0):
+        if self.nvml is not None:
+            self.stop_flag = True
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            n = self.nvml
+            names = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            mask = 0
+            for _, m in self.samples:
+                mask |= m
+            return {"sm_mhz": statistics.median(x for x, _ in self.samples), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, v in names.items() if mask & v), "samples": len(self.samples), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -92,7 +136,7 @@ class ClockSampler:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows), "source": "nvidia-smi"}
 
 
 def cpu_arm(n, steps, warmup, target_seconds=12.0, kind="maxcut"):
@@ -201,7 +245,7 @@ def main():
     # ---- device-resident throughput ----
     sampler = ClockSampler()
     if rank == 0:
-        sampler.start()
+        sampler.start(local_rank)
     S.profile(False)            # resets the launch counter
     sync()
     t0 = time.perf_counter()
