@@ -194,6 +194,33 @@ def maxcut(L, prec=256):
                             clusters=[cl], name=f"maxcut(n={n})")
 
 
+def lovasz_theta_cycle(n, prec=256):
+    """Lovasz theta of the n-cycle: maximize <J, X> s.t. tr X = 1, X_ij = 0 on the edges, X PSD (the problem behind
+    example_theta_problem, test/moi_tests.jl:7-8; theta(C_5) = sqrt 5).  General dense constraint matrices (identity and
+    off-diagonal pairs), one cluster, no free variables."""
+    with mpmath.workprec(prec + 64):
+        one = _w(1, prec)[()]
+        half = _w(mpf(1) / 2, prec)[()]
+        Cw = wire.wire_zeros((n, n), prec)
+        Cw[:, :] = one
+        blk = PSDBlock(m=1, delta=n, high_rank=True, C=Cw, name="X")
+        A0 = wire.wire_zeros((n, n), prec)
+        for i in range(n):
+            A0[i, i] = one
+        blk.dense[0] = A0
+        for e in range(n):
+            i, j = e, (e + 1) % n
+            A = wire.wire_zeros((n, n), prec)
+            A[i, j] = half
+            A[j, i] = half
+            blk.dense[1 + e] = A
+        c = wire.wire_zeros((n + 1,), prec)
+        c[0] = one
+        cl = Cluster(B=wire.wire_zeros((n + 1, 0), prec), c=c, blocks=[blk])
+        return ClusteredSDP(prec=prec, maximize=True, constant=_w(0, prec), b=wire.wire_zeros((0,), prec),
+                            clusters=[cl], name=f"theta(C_{n})")
+
+
 # ---------------------------------------------------------------------------
 # config 1: univariate polynomial minimisation (examples/PolyOpt.jl:7-30)
 # ---------------------------------------------------------------------------

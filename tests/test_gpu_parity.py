@@ -438,3 +438,23 @@ def test_maxcut_complete_graph_n100_dense_schur_on_tensor_cores():
     assert dev.status == "Optimal"
     assert abs(dev.p_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -24
     assert abs(dev.d_obj - mpmath.mpf(n * n) / 4) < mpmath.mpf(10) ** -24
+
+
+def test_delsarte_irrational_angles_known_answers_on_device():
+    """test/runtests_solver.jl:98-111 and :124-125: the Delsarte bound is 120 for (n=4, d=9, cos = 1/(sqrt5 - 1)) and 12 for
+    (n=3, d=2, cos = 1/sqrt5)."""
+    with mpmath.workprec(400):
+        for n, d, ct, ans in ((4, 9, 1 / (mpmath.sqrt(5) - 1), 120), (3, 2, 1 / mpmath.sqrt(5), 12)):
+            dev = solvesdp(workloads.delsarte(n, d, ct), lib="device", duality_gap_threshold=1e-30)
+            assert dev.status == "Optimal" and abs(dev.p_obj - ans) < mpmath.mpf(10) ** -26, (n, d, dev)
+
+
+def test_lovasz_theta_cycles_on_device():
+    """General dense constraint matrices (identity + off-diagonal pairs): theta(C_5) = sqrt 5 (test/moi_tests.jl:7-8), and a
+    40-cycle whose block runs the blocked Cholesky."""
+    with mpmath.workprec(400):
+        dev = solvesdp(workloads.lovasz_theta_cycle(5), lib="device", duality_gap_threshold=1e-30)
+        assert dev.status == "Optimal" and abs(dev.p_obj - mpmath.sqrt(5)) < mpmath.mpf(10) ** -26
+        n = 41
+        dev = solvesdp(workloads.lovasz_theta_cycle(n), lib="device", duality_gap_threshold=1e-30)
+        assert dev.status == "Optimal" and abs(dev.p_obj - n * mpmath.cos(mpmath.pi / n) / (1 + mpmath.cos(mpmath.pi / n))) < mpmath.mpf(10) ** -24

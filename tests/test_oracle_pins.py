@@ -46,6 +46,14 @@ def test_delsarte_e8_kissing_number_240():                 # test/runtests_solve
     assert abs(r.p_obj - 240) < mpmath.mpf(10) ** -26
 
 
+def test_delsarte_24_cell_and_icosahedron_irrational_angles():   # test/runtests_solver.jl:98-111 (n=4, d=9 -> 120), :124-125,158 (n=3, d=2 -> 12)
+    with mpmath.workprec(400):
+        r = solve(workloads.delsarte(4, 9, 1 / (mpmath.sqrt(5) - 1)))
+        assert abs(r.p_obj - 120) < mpmath.mpf(10) ** -26
+        r = solve(workloads.delsarte(3, 2, 1 / mpmath.sqrt(5)))
+        assert abs(r.p_obj - 12) < mpmath.mpf(10) ** -26
+
+
 def test_delsarte_3_10_half():                             # test/runtests_solver.jl:15
     r = solve(workloads.delsarte(3, 10, Fraction(1, 2)))
     assert abs(r.p_obj - mpmath.mpf("13.158314")) < mpmath.mpf(10) ** -5
@@ -70,3 +78,11 @@ def test_three_point_bound_n4_is_10():                       # test/runtests_sol
     assert sdp.num_constraints == 50 and len(sdp.clusters[0].blocks) == 19      # P=50, 19 blocks, K=79
     r = solve(sdp, omega_p=10 ** 3, omega_d=10 ** 3)
     assert abs(r.p_obj - 10) < mpmath.mpf(10) ** -25
+
+
+def test_lovasz_theta_of_the_five_cycle_is_sqrt5():          # test/moi_tests.jl:7-8 (example_theta_problem); odd cycles: n cos(pi/n) / (1 + cos(pi/n))
+    with mpmath.workprec(400):
+        r = solve(workloads.lovasz_theta_cycle(5))
+        assert abs(r.p_obj - mpmath.sqrt(5)) < mpmath.mpf(10) ** -26
+        r = solve(workloads.lovasz_theta_cycle(7))
+        assert abs(r.p_obj - 7 * mpmath.cos(mpmath.pi / 7) / (1 + mpmath.cos(mpmath.pi / 7))) < mpmath.mpf(10) ** -26
