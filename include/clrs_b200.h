@@ -88,7 +88,7 @@ enum {
  * src/solver.jl:138-139). */
 typedef struct clrs_options {
   int32_t prec;                      /* bits; 256 default (precision(BigFloat)); <= 512 in this build (8, 10 or 16 limbs) */
-  int32_t matmul_prec;               /* bits for pairings/S GEMMs; 0 = prec     */
+  int32_t matmul_prec;               /* bits for pairings/S GEMMs (solver.jl:125); 0 = prec.  This build computes the pairings at prec whatever the value (at least as accurate as asked) */
   double  beta_infeasible;           /* 3//10 */
   double  beta_feasible;             /* 1//10 */
   double  gamma;                     /* 9//10 */
