@@ -201,8 +201,25 @@ template <int NL> struct Solver : SolverBase {
 
   template <class T> T* dalloc(size_t n) { void* p = nullptr; if (n == 0) n = 1; CK(cudaMalloc(&p, n * sizeof(T))); CK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); allocs.push_back(p); return (T*)p; }
   template <class T> T* upload(const std::vector<T>& v) { T* p = dalloc<T>(v.size()); if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); return p; }
-  num* upload_wire(const void* w, size_t n) { std::vector<num> h(n); for (size_t i = 0; i < n; i++) wire_to_mpn(h[i], (const char*)w + i * wire_size()); return upload(h); }
-  void download_wire(void* w, const num* d, size_t n) { std::vector<num> h(n); CK(cudaMemcpyAsync(h.data(), d, n * sizeof(num), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); for (size_t i = 0; i < n; i++) mpn_to_wire((char*)w + i * wire_size(), h[i]); }
+  int W() const { return (prec + 63) / 64; }
+  void w2m(num& r, const void* src) const { wire_to_mpn<NL>(r, src, W()); }
+  void m2w(void* dst, const num& a) const { mpn_to_wire<NL>(dst, a, W()); }
+  // wire records cross PCIe as raw bytes through a device staging buffer; the conversion runs on the device
+  unsigned char* wstage = nullptr; size_t wstage_cap = 0;
+  unsigned char* stage(size_t bytes) { if (bytes > wstage_cap) { if (wstage) CK(cudaFree(wstage)); wstage_cap = bytes + bytes / 4 + 4096; CK(cudaMalloc((void**)&wstage, wstage_cap)); } return wstage; }
+  void wire_to_device(num* dst, const void* w, size_t n) {
+    if (!n) return; unsigned char* sbuf = stage(n * wire_size());
+    CK(cudaMemcpyAsync(sbuf, w, n * wire_size(), cudaMemcpyHostToDevice, st));
+    nlaunch++, k_wire_to_mpn<NL><<<grid_for((int64_t)n), 256, 0, st>>>((int64_t)n, sbuf, W(), dst);
+    CK(cudaStreamSynchronize(st));                        // the staging buffer is reused by the next piece
+  }
+  void device_to_wire(void* w, const num* src, size_t n) {
+    if (!n) return; unsigned char* sbuf = stage(n * wire_size());
+    nlaunch++, k_mpn_to_wire<NL><<<grid_for((int64_t)n), 256, 0, st>>>((int64_t)n, src, W(), sbuf);
+    CK(cudaMemcpyAsync(w, sbuf, n * wire_size(), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  }
+  num* upload_wire(const void* w, size_t n) { num* p = dalloc<num>(n); wire_to_device(p, w, n); return p; }
+  void download_wire(void* w, const num* d, size_t n) { device_to_wire(w, d, n); }
 
   // ---- sliced panels -------------------------------------------------------
   // lay 0: dp4a words sl[vec][K4][NSP];  lay 1: tc planes planes[t][vec][Kp] (gemm_tc.cuh)
@@ -516,38 +533,39 @@ template <int NL> struct Solver : SolverBase {
     for (Sliced* s : owned_sliced) { if (s->sl) cudaFree(s->sl); if (s->E) cudaFree(s->E); if (s->planes) cudaFree(s->planes); }
     if (tc_bytes) cudaFree(tc_bytes); if (tc_top) cudaFree(tc_top); if (pe0) cudaEventDestroy(pe0); if (pe1) cudaEventDestroy(pe1);
     for (void* p : allocs) cudaFree(p);
+    if (wstage) cudaFree(wstage);
     for (auto& e : ev) cudaEventDestroy(e);
     cudaStreamDestroy(st);
   }
-  int set_option_num(int which, const void* w) override { if (which < 0 || which > 9) return CLRS_ERR_ARG; wire_to_mpn(hopt[which], w); return 0; }
+  int set_option_num(int which, const void* w) override { if (which < 0 || which > 9) return CLRS_ERR_ARG; w2m(hopt[which], w); return 0; }
   int set_free(int N_, const void* b_, const void* constant, int maximize_) override {
-    N = N_; hb.resize(N); for (int i = 0; i < N; i++) wire_to_mpn(hb[i], (const char*)b_ + i * wire_size()); wire_to_mpn(hconst, constant); maximize = maximize_ != 0; return 0;
+    N = N_; hb.resize(N); for (int i = 0; i < N; i++) w2m(hb[i], (const char*)b_ + i * wire_size()); w2m(hconst, constant); maximize = maximize_ != 0; return 0;
   }
   int add_cluster(int j, int P, const void* B, const void* c_) override {
     if (j != (int)cl.size()) { err = "clusters must be added in order"; return CLRS_ERR_ARG; }
     cl.emplace_back(); Clu& c0 = cl.back(); c0.P = P; c0.hB.resize((size_t)P * N); c0.hc.resize(P);
-    for (size_t i = 0; i < c0.hB.size(); i++) wire_to_mpn(c0.hB[i], (const char*)B + i * wire_size());
-    for (int i = 0; i < P; i++) wire_to_mpn(c0.hc[i], (const char*)c_ + i * wire_size());
+    for (size_t i = 0; i < c0.hB.size(); i++) w2m(c0.hB[i], (const char*)B + i * wire_size());
+    for (int i = 0; i < P; i++) w2m(c0.hc[i], (const char*)c_ + i * wire_size());
     return 0;
   }
   int add_block(int j, int l, int m, int delta, int high_rank, const void* C) override {
     if (j >= (int)cl.size() || l != (int)cl[j].blocks.size()) { err = "blocks must be added in order"; return CLRS_ERR_ARG; }
     if (high_rank && m != 1) { err = "dense blocks have one subblock"; return CLRS_ERR_ARG; }
     cl[j].blocks.emplace_back(); Block& b0 = cl[j].blocks.back(); b0.j = j; b0.l = l; b0.m = m; b0.delta = delta; b0.n = m * delta; b0.high_rank = high_rank != 0;
-    b0.hC.resize((size_t)b0.n * b0.n); for (size_t i = 0; i < b0.hC.size(); i++) wire_to_mpn(b0.hC[i], (const char*)C + i * wire_size());
+    b0.hC.resize((size_t)b0.n * b0.n); for (size_t i = 0; i < b0.hC.size(); i++) w2m(b0.hC[i], (const char*)C + i * wire_size());
     return 0;
   }
   int add_dense_term(int j, int l, int p_, const void* A) override {
     Block& b0 = cl[j].blocks[l]; if (!b0.high_rank) { err = "dense term on a low-rank block"; return CLRS_ERR_ARG; }
     b0.dense_p.push_back(p_); b0.dense_A.emplace_back((size_t)b0.n * b0.n); auto& v = b0.dense_A.back();
-    for (size_t i = 0; i < v.size(); i++) wire_to_mpn(v[i], (const char*)A + i * wire_size());
+    for (size_t i = 0; i < v.size(); i++) w2m(v[i], (const char*)A + i * wire_size());
     return 0;
   }
   int add_lowrank_term(int j, int l, int r, int s, int p_, int rank, const void* lam, const void* vs, const void* ws) override {
     Block& b0 = cl[j].blocks[l]; if (b0.high_rank) { err = "low-rank term on a dense block"; return CLRS_ERR_ARG; }
     for (int k = 0; k < rank; k++) { b0.lr.emplace_back(); HTerm& t = b0.lr.back(); t.r = r; t.s = s; t.p = p_; t.k = k;
-      wire_to_mpn(t.lam, (const char*)lam + k * wire_size()); t.v.resize(b0.delta); t.w.resize(b0.delta);
-      for (int a = 0; a < b0.delta; a++) { wire_to_mpn(t.v[a], (const char*)vs + ((size_t)k * b0.delta + a) * wire_size()); wire_to_mpn(t.w[a], (const char*)ws + ((size_t)k * b0.delta + a) * wire_size()); } }
+      w2m(t.lam, (const char*)lam + k * wire_size()); t.v.resize(b0.delta); t.w.resize(b0.delta);
+      for (int a = 0; a < b0.delta; a++) { w2m(t.v[a], (const char*)vs + ((size_t)k * b0.delta + a) * wire_size()); w2m(t.w[a], (const char*)ws + ((size_t)k * b0.delta + a) * wire_size()); } }
     return 0;
   }
   static bool same_vec(const std::vector<num>& a, const std::vector<num>& b) {
@@ -962,13 +980,13 @@ template <int NL> struct Solver : SolverBase {
   }
   int get_objectives(void* d_, void* p_, void* g_) override {
     objectives(); num h[SC_COUNT]; CK(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-    mpn_to_wire(d_, h[SC_DOBJ]); mpn_to_wire(p_, h[SC_POBJ]); mpn_to_wire(g_, h[SC_GAP]); return 0;
+    m2w(d_, h[SC_DOBJ]); m2w(p_, h[SC_POBJ]); m2w(g_, h[SC_GAP]); return 0;
   }
   int64_t matrix_count() const override { return gtot; }
   // x: all constraints; X, Y: all blocks of the SDP in (j,l) order (global layout).  A sharded handle reads/writes the
   // parts it owns; get_state leaves the others untouched (the host merges the ranks' outputs).
   int set_state(const void* x_, const void* X_, const void* y_, const void* Y_) override {
-    auto up = [&](num* dst, const void* w, size_t n) { if (!w || !n) return; std::vector<num> h(n); for (size_t i = 0; i < n; i++) wire_to_mpn(h[i], (const char*)w + i * wire_size()); CK(cudaMemcpyAsync(dst, h.data(), n * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); };
+    auto up = [&](num* dst, const void* w, size_t n) { if (!w || !n) return; wire_to_device(dst, w, n); };
     if (x_) for (auto& c0 : cl) if (c0.owned) up(x + c0.off, (const char*)x_ + (size_t)c0.off * wire_size(), c0.P);
     up(y, y_, N);
     for (Block* b0 : blk) { size_t nn = (size_t)b0->n * b0->n; if (X_) up(X + b0->off, (const char*)X_ + (size_t)b0->goff * wire_size(), nn); if (Y_) up(Y + b0->off, (const char*)Y_ + (size_t)b0->goff * wire_size(), nn); }

@@ -18,6 +18,8 @@ int hc_unop(int op, const void* a, void* r) {
   switch (op) { case 0: mp_recip(z, x); break; case 1: mp_sqrt_rsqrt(z, w, x); break; case 2: mp_rsqrt(z, x); break; default: return 1; }
   mpn_to_wire(r, z); return 0;
 }
+// wire record with W 64-bit limbs -> 8-limb device number -> wire record with W2 limbs (top-aligned mantissas)
+int hc_wire_convert(int W, const void* in, int W2, void* out) { N8 x; wire_to_mpn<8>(x, in, W); mpn_to_wire<8>(out, x, W2); return x.sign; }
 double hc_to_double(const void* a) { N8 x; wire_to_mpn(x, a); return mp_to_double(x); }
 void hc_from_double(double d, void* r) { N8 x; mp_from_double(x, d); mpn_to_wire(r, x); }
 int hc_cmp(const void* a, const void* b) { N8 x, y; wire_to_mpn(x, a); wire_to_mpn(y, b); return mp_cmp(x, y); }

@@ -413,6 +413,35 @@ template <int NL> __global__ void __launch_bounds__(256) k_vec_exp_long(VecView 
   if (threadIdx.x == 0) { for (int w = 1; w < 8; w++) e = max(e, red[w]); if (e != I8_EXP_NONE) atomicMax(E + vec, e); }
 }
 __global__ void k_fill_i32(int n, int32_t* p, int32_t val) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = val; }
+// wire records (include/clrs_b200.h: int64 exp, int32 sign, int32 0, uint64 limb[W]) <-> device numbers, on the device, so
+// that clrs_set_state / clrs_get_state move raw bytes over PCIe and no host loop touches the numbers
+template <int NL> __global__ void k_wire_to_mpn(int64_t n, const unsigned char* w, int W, mpn<NL>* out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const unsigned char* s = w + i * (16 + 8 * (int64_t)W);
+  const int64_t ex0 = *(const int64_t*)s; const int32_t sg = *(const int32_t*)(s + 8); const uint32_t* wl = (const uint32_t*)(s + 16);
+  mpn<NL> r; mp_zero(r);
+  if (sg != 0) {
+    const int nw = 2 * W;
+#pragma unroll
+    for (int k = 0; k < NL; k++) { const int q = k - (NL - nw); r.l[k] = (q >= 0 && q < nw) ? wl[q] : 0u; }
+    int64_t ex = ex0; if (ex > (1 << 28)) ex = (1 << 28); if (ex < -(1 << 28)) ex = -(1 << 28);
+    r.exp = (int32_t)ex; r.sign = sg < 0 ? -1 : 1;
+  }
+  out[i] = r;
+  }
+}
+template <int NL> __global__ void k_mpn_to_wire(int64_t n, const mpn<NL>* in, int W, unsigned char* w) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  unsigned char* s = w + i * (16 + 8 * (int64_t)W);
+  const mpn<NL> a = in[i]; const int nw = 2 * W; uint32_t* wl = (uint32_t*)(s + 16);
+  *(int64_t*)s = a.sign ? (int64_t)a.exp : 0; *(int32_t*)(s + 8) = a.sign; *(int32_t*)(s + 12) = 0;
+  for (int q = 0; q < nw; q++) wl[q] = 0u;
+  if (a.sign != 0) {
+#pragma unroll
+    for (int k = 0; k < NL; k++) { const int q = k - (NL - nw); if (q >= 0 && q < nw) wl[q] = a.l[k]; }
+  }
+  }
+}
 // one thread per (vec, k4): split 4 consecutive entries into NS digits and pack them per slice.
 // kfast != 0: consecutive threads take consecutive k4 (unit-stride vectors), else consecutive vectors.
 template <int NL> __global__ void k_split(VecView v, const int32_t* E, int K4, int32_t* sl, int kfast) {

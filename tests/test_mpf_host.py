@@ -106,3 +106,21 @@ def test_wire_round_trip():
             with mpmath.workprec(PREC):
                 assert b == +mpmath.mpf(v)
     assert wire.wire_dtype(256).itemsize == 16 + 8 * 4 and wire.wire_dtype(300).itemsize == 16 + 8 * 5
+
+
+def test_wire_records_are_top_aligned_for_any_limb_count():
+    """A wire record carries ceil(prec/64) 64-bit limbs; the device number has 8, 10 or 16 32-bit limbs.  Shorter records
+    fill the upper limbs, longer ones are truncated, and the value survives (exactly when nothing is cut)."""
+    import ctypes as C
+    import mpmath
+    from clrs_b200 import wire
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "clusteredlowranksolver.jl_b200", "csrc", "libclrs_hostcheck.so"))
+    with mpmath.workprec(600):
+        v = -mpmath.mpf(2) ** 77 / 3
+        for prec_in, prec_out in ((128, 128), (128, 256), (256, 128), (256, 256), (384, 256), (256, 512)):
+            a = wire.to_wire([v], prec_in)
+            out = wire.wire_zeros((1,), prec_out)
+            assert lib.hc_wire_convert(C.c_int((prec_in + 63) // 64), a.ctypes.data_as(C.c_void_p), C.c_int((prec_out + 63) // 64), out.ctypes.data_as(C.c_void_p)) == -1
+            back = wire.from_wire(out, prec_out)[0]
+            kept = min(prec_in, prec_out, 256)
+            assert abs(back - v) <= abs(v) * mpmath.mpf(2) ** (-(kept - 2)), (prec_in, prec_out)
