@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--size", dest="n", type=int, default=300, help="graph size (300 = the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-time-to-gap", action="store_true", help="skip the full solve to gap 1e-30 (for runs under ncu)")
     ap.add_argument("--gemm-path", type=int, default=0)
     ap.add_argument("--workload", default="maxcut", choices=["maxcut", "sphere", "threepoint"],
                     help="maxcut = BASELINE configs[1] (default, the metric's config); sphere = configs[4], sharded by cluster when N > 1")
@@ -315,7 +316,7 @@ def main():
                    "path": "clrs_set_state + clrs_iterate + clrs_get_state with host wire buffers"},
            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
     # ---- time to duality gap 1e-30 (the second half of BASELINE.json's metric): a full solve from the default start ----
-    if rank == 0 and world == 1 and args.workload == "maxcut":
+    if rank == 0 and world == 1 and args.workload == "maxcut" and not args.no_time_to_gap:
         try:
             from clrs_b200 import solvesdp
             torch.cuda.synchronize()
