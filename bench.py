@@ -143,6 +143,7 @@ def cpu_arm(n, steps, warmup, target_seconds=12.0, kind="maxcut"):
     """The oracle on the host cores, bounded sample.  Returns (it/s, description, seconds per step list)."""
     import ctypes as C
     from clrs_b200 import Solver
+    import oracle.binding  # noqa: F401  (the one place bench.py touches oracle/: the CPU baseline / reference arm)
     sdp = workload(n, kind)
     S = Solver(sdp, lib="oracle", oracle_skip_zeros=True)
     lib = S.lib

@@ -9,8 +9,9 @@ iteration exactly like the Julia shim in INTEGRATION.md, so verbose printing,
 saving callbacks and maxiterations stay on the host.
 
 `Solver(lib="device")` binds libclrs_b200.so (CUDA, no CPU fallback: creating
-it without an sm_100 GPU raises).  `Solver(lib="oracle")` binds the MPFR oracle
-under oracle/ and exists for tests and baselines only.
+it without an sm_100 GPU raises).  The package itself binds ONLY that library.  Test infrastructure can register
+a second library with the same entry points under another name (`register_backend`); `oracle/binding.py` does that
+for the MPFR oracle, and only tests/, `__graft_entry__.smoke()` and the CPU legs of bench.py import it.
 """
 from __future__ import annotations
 
@@ -29,7 +30,6 @@ from .sdp import ClusteredSDP
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 DEVICE_LIB = os.path.join(_HERE, "csrc", "libclrs_b200.so")
-ORACLE_LIB = os.path.join(_ROOT, "oracle", "libclrs_oracle.so")
 
 PHASES = ["decomp", "predictor", "corrector", "alpha", "Xinv", "R", "residuals", "schur", "cholS",
           "LinvB", "Q", "cholQ", "Z", "rhs_x", "solve", "dX", "dY"]
@@ -71,16 +71,26 @@ class SolverFailure(RuntimeError):
 
 
 _libs = {}
+_BACKENDS = {"device": (DEVICE_LIB, "clrs_", C.RTLD_GLOBAL)}      # name -> (shared library, symbol prefix, dlopen mode)
+
+
+def register_backend(name: str, path: str, prefix: str) -> None:
+    """Make `Solver(lib=name)` bind another shared library exporting the ABI of include/clrs_b200.h under `prefix`.
+    Used by oracle/binding.py (test infrastructure); the product never calls it."""
+    _BACKENDS[name] = (path, prefix, C.RTLD_LOCAL)
 
 
 def load_library(kind: str) -> C.CDLL:
-    """Load the device library or the oracle; fail loudly if it is missing."""
+    """Load a registered library; fail loudly if it is unknown or missing (there is no fallback between libraries)."""
     if kind in _libs:
         return _libs[kind]
-    path = DEVICE_LIB if kind == "device" else ORACLE_LIB
+    if kind not in _BACKENDS:
+        raise RuntimeError(f"unknown library {kind!r}: this package binds only the CUDA library ('device'); the CPU oracle is "
+                           f"test infrastructure and has to be registered explicitly (import oracle.binding)")
+    path, _, mode = _BACKENDS[kind]
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL if kind == "device" else C.RTLD_LOCAL)
+    lib = C.CDLL(path, mode=mode)
     _libs[kind] = lib
     return lib
 
@@ -101,7 +111,7 @@ class Solver:
         (one per GPU / process); every rank uploads the same SDP and calls iterate() in lock step."""
         self.kind = lib
         self.lib = load_library(lib)
-        self.pre = "clrs_" if lib == "device" else "clrs_oracle_"
+        self.pre = _BACKENDS[lib][1]
         self.sdp = sdp
         self.prec = sdp.prec
         self.W = wire.limbs_for(self.prec)
@@ -138,7 +148,7 @@ class Solver:
         if comm and lib == "device" and comm[1] > 1:
             uid = (C.c_char * 128).from_buffer_copy(bytes(comm[2]))
             self._call("comm_init", self.h, C.c_int32(comm[0]), C.c_int32(comm[1]), uid)
-        if lib == "oracle" and oracle_skip_zeros:
+        if lib != "device" and oracle_skip_zeros:
             fn = self._fn("set_dense_skip_zeros")
             fn.restype = None
             fn(self.h, C.c_int32(1))

@@ -16,4 +16,5 @@ def pytest_configure(config):
 def _built():
     import __graft_entry__ as g
     g.build()
+    import oracle.binding  # noqa: F401  (registers the CPU oracle as lib="oracle": the checker of these tests)
     yield

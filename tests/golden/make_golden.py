@@ -14,6 +14,7 @@ from fractions import Fraction
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import mpmath
 import clrs_b200
+import oracle.binding  # noqa: F401  (registers lib="oracle")
 from clrs_b200 import workloads, solvesdp
 
 HERE = os.path.dirname(os.path.abspath(__file__))

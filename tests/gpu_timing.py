@@ -3,6 +3,7 @@ import sys, time
 from fractions import Fraction
 sys.path.insert(0, ".")
 import clrs_b200
+import oracle.binding  # noqa: F401  (registers lib="oracle")
 from clrs_b200 import workloads, solvesdp, PHASES
 import numpy as np
 

@@ -47,3 +47,15 @@ def test_create_fails_loudly_without_a_gpu():
     with pytest.raises(RuntimeError) as e:
         clrs_b200.Solver(workloads.maxcut(workloads.laplacian_cycle(3)), lib="device")
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_package_cannot_reach_the_oracle_without_registration():
+    """The host mirror binds only the CUDA library; lib="oracle" exists only after test infrastructure registers it."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, '.'); import clrs_b200; from clrs_b200 import workloads, Solver\n"
+            "try:\n    Solver(workloads.maxcut(workloads.laplacian_cycle(3)), lib='oracle'); print('reachable')\n"
+            "except RuntimeError as e:\n    print('refused')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert out.stdout.strip() == "refused", (out.stdout, out.stderr[-500:])
