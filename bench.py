@@ -1,23 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — IPM iterations/sec of the B200 hot path on the BASELINE workload.
+"""bench.py — IPM iterations/sec of the B200 hot path (BASELINE.json metric).
 
-Workload (config.workload): BASELINE.json configs[1] — Goemans-Williamson MAX-CUT
-relaxation, Laplacian of G(300, 0.5) (numpy default_rng(0)), every constraint matrix
-E_pp stored dense (the reference's dense Schur path), prec = 256 bit.  One "step" is
-one predictor-corrector IPM iteration (src/solver.jl:362-592) on the resident SDP.
+One "step" is one predictor-corrector IPM iteration (src/solver.jl:362-592) on the resident SDP.
 
-  value   iterations/s from the device time of K consecutive clrs_iterate calls
-          (CUDA events on the library's stream, problem and iterate resident in HBM)
-  e2e     the same K iterations driven through the C ABI with HOST buffers every step:
-          clrs_set_state (H2D of x,X,y,Y) + clrs_iterate + clrs_get_state (D2H)
-  roofline  the tcgen05 slice-pair GEMM launches, canonical int8 op count
-          2*M*N*K*528 / CUDA-event time, against 2x the measured bf16 peak
-  cpu_baseline  the MPFR oracle (a port of the reference, not the reference) on the host cores,
-          bounded sample: a few rows of the dense Schur path at full cost, the rest of the
-          iteration measured in full, scaled to one iteration
+Workloads
+  N = 1   BASELINE.json configs[1]: Goemans-Williamson MAX-CUT relaxation, Laplacian of G(300, 0.5)
+          (numpy default_rng(0)), every constraint matrix E_pp stored dense (the reference's dense
+          Schur path), prec = 256 bit.  One cluster with one block: it does not shard.
+  N > 1   BASELINE.json configs[4]: sphere packing n = 8, d = 31, four radii (SURVEY.md §8(d) size
+          (4,31): J = 16 clusters, P = 1294, N = 641 free variables), prec = 512 bit (the example's default; at 256 bit
+          the reference's own algorithm fails on this shape: "Q was not decomposed correctly"), clusters sharded
+          over the ranks, strong scaling.  The line also carries the 1-GPU rate of the
+          SAME workload measured in the same run on rank 0 (`strong_scaling`), because the N = 1 line of
+          this script is the MAX-CUT headline.
 
---impl reference runs only that CPU arm.  N > 1 (torchrun): the workload is one cluster with
-one block, it does not shard: every rank solves an independent replica.
+Keys
+  value     iterations/s from the device time of K consecutive clrs_iterate calls (CUDA events on the
+            library's stream, SDP and iterate resident in HBM); every call is asserted to be a real
+            iteration (info.stop == 0).  The solver runs with duality_gap_threshold = 1e-30 and the iterate
+            is put back to a snapshot (iteration 3 of the solve) every 24 iterations, between timed calls,
+            so no timed, e2e or profiled call can fall on a converged (no-op) iteration.
+  e2e       the same K iterations driven through the C ABI with HOST buffers every step: clrs_set_state
+            (H2D of x, X, y, Y from pinned host memory) + clrs_iterate + clrs_get_state (D2H), wall clock
+  roofline  the dominant GEMM class: canonical int8 ops 2*M*N*K*528 / CUDA-event time of
+            every launch, against 2 x the measured bf16 peak (burst: the launches are timed one by one)
+  cpu_baseline  the MPFR oracle (a port of the reference, not the reference) on the host cores, bounded sample
+  configs   (N = 1) iterations/s, ms/step and the 17 phase timers of the other BASELINE configs
+
+--impl reference runs only the CPU arm on the same workload as the B200 arm at that N.
 """
 import argparse
 import json
@@ -33,24 +43,45 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ipm_iterations_per_sec"
 UNIT = "iterations/s"
+RESTORE_EVERY = 24          # iterations after which the iterate is put back to the snapshot (config 2 converges in 55)
+SNAP_ITER = 3               # the snapshot is the iterate after this many iterations from the default start
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from `ncu --set full` captures of this
+# build (profiles/): keyed by (workload, class).  None = not captured for this build.
+NCU_TRAFFIC = {}
 
 
 def workload(n, kind="maxcut"):
-    import clrs_b200
+    import clrs_b200  # noqa: F401
     from clrs_b200 import workloads
     from fractions import Fraction as F
     if kind == "sphere":        # BASELINE.json configs[4]: many clusters coupled through the free variables; shards by cluster
-        return workloads.sphere_packing(8, n if n != 300 else 31, [F(1, 2), F(1, 2), F(3, 4), F(1)], prec=512)   # SURVEY.md §8(d) size (4,31): J=16, N=641, P=1294
+        # SURVEY.md §8(d) size (4,31): J=16, N=641, P=1294.  prec = 512 (the default of examples/SpherePacking.jl:13): at 256 bit the
+        # reference's own algorithm fails on this shape in the first iteration ("Q was not decomposed correctly", oracle and device alike)
+        return workloads.sphere_packing(8, n if n != 300 else 31, [F(1, 2), F(1, 2), F(3, 4), F(1)], prec=512)
+    if kind == "sphere2":       # (2,31): J=7, N=193, P=389
+        return workloads.sphere_packing(8, n if n != 300 else 31, [F(1, 2), F(1, 2)], prec=512)
+    if kind == "sphere8":       # (8,40): J=46, N=2953, P=5948 — the largest shape of SURVEY.md §8(d) (device only: one oracle iteration is ~1e11 512-bit MACs)
+        return workloads.sphere_packing(8, n if n != 300 else 40, [F(1, 2), F(5, 8), F(3, 4), F(7, 8), F(1), F(9, 8), F(5, 4), F(11, 8)], prec=512)
+    if kind == "threepoint14":  # configs[3] at d2 = d3 = 14: P=894, 61 blocks up to n=225
+        return workloads.three_point_bound(4, F(1, 6), 14, 14, prec=256)
     if kind == "threepoint":    # configs[3] at the size of examples/ThreePointBound.jl (one cluster: the dense F_k blocks are shared)
         return workloads.three_point_bound(4, F(1, 6), n if n != 300 else 10, n if n != 300 else 10, prec=256)
+    if kind == "delsarte":      # configs[2]
+        return workloads.delsarte(8, n if n != 300 else 16, F(1, 2), prec=256)
+    if kind == "polyopt":       # configs[0]
+        return workloads.polyopt_random(n if n != 300 else 20, 0, prec=256)
     return workloads.maxcut(workloads.laplacian_random(n, 0.5, 0), prec=256)
+
+
+CONFIG_INDEX = {"polyopt": 0, "maxcut": 1, "delsarte": 2, "threepoint": 3, "threepoint14": 3, "sphere": 4, "sphere2": 4, "sphere8": 4}
 
 
 def config(n, n_gpus, kind="maxcut", sdp=None):
     if kind != "maxcut":
-        return {"workload": f"{sdp.describe() if sdp is not None else kind} (BASELINE.json configs[{4 if kind == 'sphere' else 3}])",
+        return {"workload": f"{sdp.describe() if sdp is not None else kind} (BASELINE.json configs[{CONFIG_INDEX[kind]}])",
                 "step": "one predictor-corrector IPM iteration", "l2": "L2 flushed by the iteration's own temporaries only; latency-bound small blocks",
-                "parallelism": ("clusters sharded over ranks (LPT), NCCL all-gather of Q, u, p and scalars" if kind == "sphere" else "replicas only") if n_gpus > 1 else "single GPU"}
+                "parallelism": ("clusters sharded over ranks (LPT on P^3 + sum n^3), NCCL on the free-variable coupling (Q, u, p) and scalars" if kind.startswith("sphere") else "replicas only") if n_gpus > 1 else "single GPU"}
     return {"workload": f"GW MAX-CUT relaxation, G({n},0.5) numpy default_rng(0), dense constraint path "
                         f"(BASELINE.json configs[1]), prec=256, J=1 P={n} one dense block {n}x{n}, N=0",
             "step": "one predictor-corrector IPM iteration", "l2": "working set (~7 GB of slices/temporaries) exceeds the 126 MB L2",
@@ -139,25 +170,42 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows), "source": "nvidia-smi"}
 
 
-def cpu_arm(n, steps, warmup, target_seconds=12.0, kind="maxcut"):
-    """The oracle on the host cores, bounded sample.  Returns (it/s, description, seconds per step list)."""
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed to run on (torchrun's OMP_NUM_THREADS=1 is ignored on purpose)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_arm(n, steps, warmup, target_seconds=12.0, kind="maxcut", budget_seconds=100.0):
+    """The oracle on the host cores, bounded sample.  Returns (it/s, OpenMP threads actually used, description)."""
     import ctypes as C
     from clrs_b200 import Solver
     import oracle.binding  # noqa: F401  (the one place bench.py touches oracle/: the CPU baseline / reference arm)
     sdp = workload(n, kind)
-    S = Solver(sdp, lib="oracle", oracle_skip_zeros=True)
+    S = Solver(sdp, lib="oracle", oracle_skip_zeros=True, duality_gap_threshold=1e-30)
     lib = S.lib
     lib.clrs_oracle_set_sample_limit.restype = None
     lib.clrs_oracle_get_sample_times.restype = None
-    cores = os.cpu_count() or 1
+    lib.clrs_oracle_set_threads.restype = None
+    lib.clrs_oracle_get_threads.restype = C.c_int32
+    lib.clrs_oracle_set_threads(C.c_int32(host_threads()))      # explicit: the environment may carry OMP_NUM_THREADS=1 (torchrun)
+    threads = int(lib.clrs_oracle_get_threads())
     limit = 1
     times = []
     desc = ""
+    t_begin = time.perf_counter()
     for it in range(warmup + steps):
+        if times and time.perf_counter() - t_begin > budget_seconds:      # bounded: the arm must end within minutes whatever K is
+            desc += f"; stopped after {len(times)} timed steps ({budget_seconds:.0f} s budget)"
+            break
         lib.clrs_oracle_set_sample_limit(S.h, C.c_int32(limit))
         t0 = time.perf_counter()
-        S.iterate()
+        info = S.iterate()
         wall = time.perf_counter() - t0
+        if info.stop != 0:
+            raise RuntimeError(f"CPU arm: iteration {it} did not run (stop = {info.stop})")
         out = (C.c_double * 3)()
         lib.clrs_oracle_get_sample_times(S.h, out)
         t_plain, t_skip, np_ = out[0], out[1], int(out[2])
@@ -175,7 +223,81 @@ def cpu_arm(n, steps, warmup, target_seconds=12.0, kind="maxcut"):
         limit = max(1, min(np_, int(target_seconds / max(per_row, 1e-3))))
     S.close()
     its = len(times) / sum(times)
-    return its, cores, desc
+    return its, threads, desc
+
+
+class Runner:
+    """A Solver plus the snapshot discipline: every call of step() is a real iteration (asserted), and the iterate goes
+    back to the snapshot every RESTORE_EVERY iterations, outside the device-timed part of a step."""
+
+    def __init__(self, S, alloc=None):
+        self.S = S
+        for _ in range(SNAP_ITER):
+            self._iterate()
+        self.snap = tuple(None if a is None else a.copy() for a in S.get_state(out=S.state_buffers()))
+        self.since = 0
+        self.alloc = alloc
+
+    def _iterate(self):
+        info = self.S.iterate()
+        if info.stop != 0:
+            raise RuntimeError(f"bench: clrs_iterate returned stop = {info.stop} (a timed call must be a real iteration)")
+        return info
+
+    def restore(self):
+        self.S.set_state(*self.snap)
+        self.since = 0
+
+    def step(self):
+        if self.since >= RESTORE_EVERY:
+            self.restore()
+        info = self._iterate()
+        self.since += 1
+        return info
+
+
+def measure(S, K, W, sync, alloc, e2e=True):
+    """(device ms total, wall s, launches, e2e seconds, bytes per e2e step, last info) of K steps after W warm-ups."""
+    R = Runner(S, alloc)
+    for _ in range(W):
+        R.step()
+    R.restore()
+    S.profile(False)            # resets the launch counter
+    sync()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    info = None
+    for _ in range(K):
+        info = R.step()
+        dev_ms += S.last_iteration_ms()
+    sync()
+    wall = time.perf_counter() - t0
+    launches = S.profile_get()["kernel_launches"]
+    if not e2e:
+        return R, dev_ms, wall, launches, None, 0, info
+    # ---- end to end through the C ABI with host buffers (pinned) every step ----
+    bufs = S.state_buffers(alloc=alloc)
+
+    def load_snapshot():
+        for dst, src in zip(bufs, R.snap):
+            dst[:len(src)] = src          # (y has max(N, 1) records in the buffer, N in the snapshot)
+    load_snapshot()
+    x, X, y, Y = bufs
+    nbytes = S.owned_state_bytes()
+    sync()
+    t0 = time.perf_counter()
+    for k in range(K):
+        if k and k % RESTORE_EVERY == 0:
+            load_snapshot()
+        S.set_state(x, X, y, Y)
+        info2 = S.iterate()
+        if info2.stop != 0:
+            raise RuntimeError(f"bench e2e: clrs_iterate returned stop = {info2.stop}")
+        S.get_state(out=bufs)
+    sync()
+    e2e_s = time.perf_counter() - t0
+    R.restore()
+    return R, dev_ms, wall, launches, e2e_s, nbytes, info
 
 
 def main():
@@ -188,30 +310,33 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--size", dest="n", type=int, default=300, help="graph size (300 = the BASELINE config)")
+    ap.add_argument("--size", dest="n", type=int, default=300, help="workload size parameter (300 = the BASELINE size of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-time-to-gap", action="store_true", help="skip the full solve to gap 1e-30 (for runs under ncu)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (configs 1, 3, 4, 5 at one GPU)")
     ap.add_argument("--gemm-path", type=int, default=0)
-    ap.add_argument("--workload", default="maxcut", choices=["maxcut", "sphere", "threepoint"],
-                    help="maxcut = BASELINE configs[1] (default, the metric's config); sphere = configs[4], sharded by cluster when N > 1")
+    ap.add_argument("--workload", default=None, choices=["maxcut", "sphere", "sphere2", "sphere8", "threepoint", "threepoint14", "delsarte", "polyopt"],
+                    help="default: maxcut (BASELINE configs[1], the metric's config) at one GPU; sphere (configs[4], sharded by cluster) at N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    kind = args.workload or ("maxcut" if n_gpus == 1 else "sphere")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        its, cores, desc = cpu_arm(args.n, max(1, args.steps), max(0, min(args.warmup, 1)), kind=args.workload)
+        its, threads, desc = cpu_arm(args.n, max(1, args.steps), max(0, min(args.warmup, 1)), kind=kind)
+        sdp = workload(args.n, kind) if kind != "maxcut" else None
         print(file=real_stdout, flush=True, *[json.dumps({"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "mpfr (cpu)", "data": "synthetic", "config": config(args.n, args.gpus, args.workload, workload(args.n, args.workload) if args.workload != "maxcut" else None),
-                          "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+                          "warmup": args.warmup, "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "strong" if (kind.startswith("sphere") and n_gpus > 1) else "weak", "vs_baseline": None,
+                          "dtype": "mpfr (cpu)", "data": "synthetic", "config": config(args.n, args.gpus, kind, sdp),
+                          "cpu_baseline": {"value": its, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc, "host_cpus": os.cpu_count()},
                           "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
         return
 
     import torch
-    import numpy as np
     import __graft_entry__ as g
     if rank == 0:
         g.build()
@@ -223,9 +348,9 @@ def main():
     if dist is not None:
         dist.barrier()
     import clrs_b200
-    from clrs_b200 import Solver, wire
-    sdp = workload(args.n, args.workload)
-    sharded = world > 1 and args.workload == "sphere"
+    from clrs_b200 import Solver
+    sdp = workload(args.n, kind)
+    sharded = world > 1 and kind in ("sphere", "sphere2", "sphere8")
     comm = None
     if sharded:                 # one communicator over the ranks; the id travels through torch.distributed
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -233,7 +358,8 @@ def main():
             uid = torch.tensor(list(clrs_b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         comm = (rank, world, bytes(uid.cpu().tolist()))
-    S = Solver(sdp, lib="device", device=local_rank, gemm_path=args.gemm_path, comm=comm)
+    GAP = 1e-30
+    S = Solver(sdp, lib="device", device=local_rank, gemm_path=args.gemm_path, comm=comm, duality_gap_threshold=GAP)
     reps = 1 if sharded else world
     W, K = max(args.warmup, 3), args.steps
 
@@ -242,99 +368,122 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    for _ in range(W):
-        S.iterate()
-    # ---- device-resident throughput ----
+    def pinned(nbytes):
+        return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, pin_memory=True).numpy()
+
+    def allmax(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler()
     if rank == 0:
         sampler.start(local_rank)
-    S.profile(False)            # resets the launch counter
-    sync()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(K):
-        S.iterate()
-        dev_ms += S.last_iteration_ms()
-    sync()
-    wall = time.perf_counter() - t0
-    launches = S.profile_get()["kernel_launches"]
+    R, dev_ms, wall, launches, e2e_s, nbytes, last_info = measure(S, K, W, sync, pinned)
     clocks = sampler.stop(local_rank) if rank == 0 else None
-    t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
+    dev_ms_max = allmax(dev_ms)
     value = reps * K / (dev_ms_max / 1e3)
-
-    # ---- end to end through the C ABI with host buffers every step ----
-    x, X, y, Y = S.get_state()
-    h2d = sum(a.nbytes for a in (x, X, y, Y) if a is not None)
-    sync()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        S.set_state(x, X, y, Y)
-        S.iterate()
-        x, X, y, Y = S.get_state()
-    sync()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    e2e_value = reps * K / allmax(e2e_s)
+    nbytes_all = nbytes
     if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = reps * K / float(te.item())
+        t = torch.tensor([float(nbytes)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        nbytes_all = int(t.item())
 
     # ---- roofline of the dominant kernel: per-launch CUDA-event timing of every GEMM ----
+    NP = min(K, 2)
     S.profile(True)
-    for _ in range(min(K, 2)):
-        S.iterate()
+    for _ in range(NP):
+        R.step()
     prof = S.profile_get()
     S.profile(False)
+    R.restore()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense = 2x bf16 rate)" if peaks else "2 x 1.4 PFLOP/s fallback of B200_PROFILING.md"
+    bf16_burst = peaks.get("bf16_tflops") or 1400.0
+    bf16_sus = peaks.get("bf16_tflops_sustained") or bf16_burst
+    peak_src = ("2 x bf16_tflops (burst) of MEASURED_PEAKS.json: int8 dense = 2x the bf16 rate; burst because every launch is timed alone between CUDA events"
+                if peaks else "2 x 1.4 PFLOP/s fallback of B200_PROFILING.md")
     classes = {"dp4a": "k_gemm_dp4a (CUDA-core int8 path, small shapes)",
-               "tc_small": "tc::k_gemm_tc + k_tc_recombine, products with < 1e6 outputs (block-level n x n products, split-K Schur dots)",
-               "tc_large": "tc::k_gemm_tc + k_tc_recombine, the two 90000 x 300 x 300 products of the dense Schur path (in chunks of 63 constraints = 3 waves of CTAs)"}
+               "tc_small": "tc::k_gemm_tc + recombination, products with < 1e6 outputs (block-level n x n products, split-K Schur dots)",
+               "tc_large": "tc::k_gemm_tc + k_tc_recombine, products with >= 1e6 outputs (the two 90000 x 300 x 300 products of the dense Schur path, in wave-sized chunks of constraints)"}
+
     def rl(c):
         ms, mpf, nl = prof[c]["ms"], prof[c]["mp_flops"], prof[c]["launches"]
         ach = (mpf * 528.0 / (ms / 1e3)) / 1e12 if ms > 0 else 0.0
-        return {"kernel": classes[c], "achieved": ach, "frac": ach / (2 * bf16), "launches": nl, "avg_launch_ms": ms / max(1, nl),
-                "share_of_step": ms / max(1e-9, min(K, 2) * dev_ms_max / K)}
+        return {"kernel": classes[c], "achieved": ach, "frac": ach / (2 * bf16_burst), "frac_of_sustained_peak": ach / (2 * bf16_sus), "launches": nl,
+                "avg_launch_ms": ms / max(1, nl), "share_of_step": ms / max(1e-9, NP * dev_ms_max / K)}
     dom = max(classes, key=lambda c: prof[c]["ms"])
     r = rl(dom)
-    roofline = {"bound": "tensor", "kernel": r["kernel"], "achieved": r["achieved"], "peak": 2 * bf16,
-                "unit": "TOP/s (int8, canonical 2*M*N*K*528 per 256-bit GEMM)", "frac": r["frac"],
-                "traffic": (2.93e9 * (2.0 * min(K, 2)) / max(1, r["launches"])) if (dom == "tc_large" and args.workload == "maxcut" and args.n == 300) else None,
-                "traffic_note": "per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE 90000x300x300 launch (2.93e9; ncu --set full, profiles/r01_tc_kernel_ncu_full.txt; algorithmic 2.08e9) scaled by rows per launch - the two 90000-row products of an iteration run as wave-sized chunks of constraints, and traffic is proportional to rows (A slices in, byte planes out)",
-                "peak_source": peak_src, "launches": r["launches"], "avg_launch_ms": r["avg_launch_ms"], "gemm_share_of_step": r["share_of_step"],
+    if r["launches"] <= 0:
+        raise RuntimeError("bench: the profiled iterations launched no GEMM (roofline would be empty)")
+    traffic = NCU_TRAFFIC.get((kind, dom))
+    roofline = {"bound": "tensor", "kernel": r["kernel"], "achieved": r["achieved"], "peak": 2 * bf16_burst,
+                "unit": "TOP/s (int8, canonical 2*M*N*K*528 per 256-bit GEMM)", "frac": r["frac"], "frac_of_sustained_peak": r["frac_of_sustained_peak"],
+                "traffic": traffic, "peak_source": peak_src, "launches": r["launches"], "avg_launch_ms": r["avg_launch_ms"], "gemm_share_of_step": r["share_of_step"],
                 "other_gemm_classes": {c: rl(c) for c in classes if c != dom}}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K,
            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": f"int8 slices of {sdp.prec}-bit mantissas (exact int32 accumulation)",
-           "data": "synthetic", "config": config(args.n, world, args.workload, sdp), "wall_ms_per_step": 1e3 * wall / K,
-           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
-                   "path": "clrs_set_state + clrs_iterate + clrs_get_state with host wire buffers"},
-           "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
-    # ---- time to duality gap 1e-30 (the second half of BASELINE.json's metric): a full solve from the default start ----
-    if rank == 0 and world == 1 and args.workload == "maxcut" and not args.no_time_to_gap:
-        try:
-            from clrs_b200 import solvesdp
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            full = solvesdp(sdp, lib="device", device=local_rank, gemm_path=args.gemm_path, duality_gap_threshold=1e-30)
-            torch.cuda.synchronize()
-            out["time_to_gap_1e-30"] = {"seconds": time.perf_counter() - t0, "iterations": full.iterations, "status": full.status,
-                                        "note": "wall clock of solvesdp(...) through the C ABI incl. upload of the SDP and the per-iteration host round trip"}
-        except Exception as e:
-            out["time_to_gap_1e-30"] = {"seconds": None, "note": f"failed: {e}"}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            its, cores, desc = cpu_arm(args.n, 1, 1, kind=args.workload)
-            out["cpu_baseline"] = {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
-        except Exception as e:      # the baseline must never take the GPU number down
-            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+           "data": "synthetic", "config": config(args.n, world, kind, sdp), "wall_ms_per_step": 1e3 * wall / K,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes_all, "d2h_bytes_per_step": nbytes_all,
+                   "path": "clrs_set_state + clrs_iterate + clrs_get_state with pinned host wire buffers"},
+           "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+           "phase_ms": dict(zip(clrs_b200.PHASES, [round(v, 4) for v in last_info.phase_ms])),
+           "solver": {"duality_gap_threshold": GAP, "snapshot_iteration": SNAP_ITER, "restore_every": RESTORE_EVERY,
+                      "cuda_graph": os.environ.get("CLRS_GRAPH", "1") != "0"}}
     S.close()
+
+    # ---- strong-scaling base: the same workload on ONE GPU, measured on rank 0 in the same run ----
+    if sharded:
+        if rank == 0:
+            S1 = Solver(sdp, lib="device", device=local_rank, gemm_path=args.gemm_path, duality_gap_threshold=GAP)
+            _, dms1, _, _, _, _, _ = measure(S1, K, W, torch.cuda.synchronize, None, e2e=False)
+            S1.close()
+            v1 = K / (dms1 / 1e3)
+            out["strong_scaling"] = {"value_1gpu": v1, "ms_per_step_1gpu": dms1 / K, "speedup": value / v1, "n_gpus": world,
+                                     "note": "same SDP, same build, unsharded handle on rank 0's GPU while the other ranks wait"}
+        dist.barrier()
+
+    if rank == 0 and world == 1:
+        # ---- the other BASELINE configs at one GPU: it/s, ms/step, phase timers ----
+        if not args.no_configs:
+            from clrs_b200.api import PHASES
+            table = {}
+            for name in ("polyopt", "delsarte", "threepoint", "sphere2", "sphere"):
+                if name == kind:
+                    continue
+                try:
+                    s2 = workload(300, name)
+                    S2 = Solver(s2, lib="device", device=local_rank, duality_gap_threshold=GAP)
+                    _, dms, _, nl, _, _, info = measure(S2, 4, 3, torch.cuda.synchronize, None, e2e=False)
+                    table[name] = {"workload": s2.describe(), "config_index": CONFIG_INDEX[name], "value": 4 / (dms / 1e3), "ms_per_step": dms / 4,
+                                   "gpu_launches_per_step": nl / 4, "phase_ms": dict(zip(PHASES, [round(v, 4) for v in info.phase_ms]))}
+                    S2.close()
+                except Exception as e:      # a side table must never take the headline down
+                    table[name] = {"error": str(e)}
+            out["configs"] = table
+        # ---- time to duality gap 1e-30 (the second half of BASELINE.json's metric): a full solve from the default start ----
+        if kind == "maxcut" and not args.no_time_to_gap:
+            try:
+                from clrs_b200 import solvesdp
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                full = solvesdp(sdp, lib="device", device=local_rank, gemm_path=args.gemm_path, duality_gap_threshold=1e-30)
+                torch.cuda.synchronize()
+                out["time_to_gap_1e-30"] = {"seconds": time.perf_counter() - t0, "iterations": full.iterations, "status": full.status,
+                                            "note": "wall clock of solvesdp(...) through the C ABI incl. upload of the SDP and the per-iteration host round trip"}
+            except Exception as e:
+                out["time_to_gap_1e-30"] = {"seconds": None, "note": f"failed: {e}"}
+        if not args.no_cpu_baseline:
+            try:
+                its, threads, desc = cpu_arm(args.n, 1, 1, kind=kind)
+                out["cpu_baseline"] = {"value": its, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc, "host_cpus": os.cpu_count()}
+            except Exception as e:      # the baseline must never take the GPU number down
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(out), file=real_stdout, flush=True)
     if dist is not None:

@@ -231,13 +231,24 @@ class Solver:
         fn.restype = C.c_int64
         return int(fn(self.h))
 
-    def get_state(self, matrices: bool = True):
+    def state_buffers(self, matrices: bool = True, alloc=None):
+        """Caller-owned wire buffers for (x, X, y, Y).  `alloc(nbytes) -> uint8 ndarray` lets the caller supply the memory
+        (bench.py passes pinned host memory so that clrs_set_state / clrs_get_state copy by DMA)."""
         sdp = self.sdp
-        x = wire.wire_zeros((sdp.num_constraints,), self.prec)
-        y = wire.wire_zeros((max(sdp.N, 1),), self.prec)
         cnt = self.matrix_count()
-        X = wire.wire_zeros((cnt,), self.prec) if matrices else None
-        Y = wire.wire_zeros((cnt,), self.prec) if matrices else None
+
+        def mk(n):
+            if alloc is None:
+                return wire.wire_zeros((n,), self.prec)
+            raw = alloc(n * self.dtype.itemsize)
+            raw[:] = 0
+            return raw.view(self.dtype)
+        return mk(sdp.num_constraints), (mk(cnt) if matrices else None), mk(max(sdp.N, 1)), (mk(cnt) if matrices else None)
+
+    def get_state(self, matrices: bool = True, out=None):
+        """Download (x, X, y, Y).  out = buffers from state_buffers() to write into (y has max(N, 1) records)."""
+        sdp = self.sdp
+        x, X, y, Y = out if out is not None else self.state_buffers(matrices)
         vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         self._call("get_state", self.h, vp(x), vp(X), vp(y), vp(Y))
         return x, X, y[:sdp.N], Y
@@ -259,6 +270,15 @@ class Solver:
             raise KeyError(what)
         return buf[:n]
 
+    def owned_state_bytes(self) -> int:
+        """Bytes of (x, X, y, Y) this handle reads in set_state / writes in get_state: the clusters it owns plus y."""
+        n = self.sdp.N
+        for j, cl in enumerate(self.sdp.clusters):
+            if self.kind == "device" and self.nranks > 1 and self.cluster_owner(j) != self.rank:
+                continue
+            n += cl.P + 2 * sum(b.n * b.n for b in cl.blocks)
+        return n * self.dtype.itemsize
+
     def cluster_owner(self, j: int) -> int:
         fn = self._fn("cluster_owner"); fn.restype = C.c_int
         return int(fn(self.h, C.c_int32(j)))
@@ -275,6 +295,10 @@ class Solver:
         for i, nm in enumerate(names):
             d[nm] = {"ms": out[3 * i], "mp_flops": out[3 * i + 1], "launches": int(out[3 * i + 2])}
         return d
+
+    def use_graph(self, enable: bool):
+        """CUDA-graph replay of the iteration on/off (device library; on by default)."""
+        fn = self._fn("use_graph"); fn.restype = None; fn(self.h, C.c_int32(int(enable)))
 
     def last_iteration_ms(self) -> float:
         fn = self._fn("last_iteration_ms"); fn.restype = C.c_double

@@ -19,6 +19,7 @@
 #include "../../include/clrs_b200.h"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
+#include "lanes.cuh"
 #include "wire_host.h"
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
@@ -31,14 +32,14 @@ struct NcclUid { char b[128]; };
 struct NcclApi {
   void* lib = nullptr;
   int (*GetUniqueId)(void*) = nullptr; int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
-  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr; int (*CommDestroy)(void*) = nullptr; const char* (*GetErrorString)(int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr; int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr; int (*CommDestroy)(void*) = nullptr; const char* (*GetErrorString)(int) = nullptr;
   bool load(std::string& err) {
     if (lib) return true;
     for (const char* n : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
     if (!lib) { err = "libnccl.so.2 not found"; return false; }
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId"); CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
-    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather"); CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy"); GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather"); AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce"); CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy"); GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllGather || !AllReduce || !CommDestroy) { err = "NCCL symbols missing"; return false; }
     return true;
   }
 };
@@ -109,7 +110,7 @@ template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, doub
     num mn = mp_cmp(ad, ap) < 0 ? ad : ap;
     if (mp_cmp(mn, sc[SC_STEPTHR]) < 0) { fl[FL_STOP] = CLRS_STOP_STEP_TOO_SHORT; mp_zero(sc[SC_ALPHAD]); mp_zero(sc[SC_ALPHAP]); }
     else if (fl[FL_PDFEAS] && cfg.safe_step) { sc[SC_ALPHAD] = mn; sc[SC_ALPHAP] = mn; }
-    if (fl[FL_STOP] == CLRS_STOP_MAX_COMPLEMENTARY_GAP) { mp_zero(sc[SC_ALPHAD]); mp_zero(sc[SC_ALPHAP]); }
+    if (fl[FL_STOP] == CLRS_STOP_MAX_COMPLEMENTARY_GAP || fl[FL_STATUS] != 0) { mp_zero(sc[SC_ALPHAD]); mp_zero(sc[SC_ALPHAP]); }   // the reference throws before the step (:394,1248,1276,1645): the last good iterate is kept
   } else if (phase == 4) {     // objectives and gap (src/solver.jl:792-847)
     num d = sc[SC_CX]; if (!cfg.maximize) d.sign = -d.sign; mp_add(d, d, sc[SC_CONSTANT]);
     num p; mp_add(p, sc[SC_CY], sc[SC_BY]); mp_add(p, p, sc[SC_CONSTANT]);
@@ -150,6 +151,25 @@ template <int NL> __global__ void k_combine_gathered(int64_t n, int R, const mpn
     out[i] = acc;
   }
 }
+// ---- cross-rank sums of multi-limb values with NCCL's own reductions: lanes.cuh holds the arithmetic ----
+template <int NL> __global__ void k_lane_exp(int64_t n, const mpn<NL>* v, int32_t* E) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) E[i] = mp_lane_exp(v[i]);
+}
+template <int NL> __global__ void k_to_lanes(int64_t n, const mpn<NL>* v, const int32_t* E, long long* lanes) {     // lanes[k][i]: plane-major, coalesced
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    long long t[NL + 1]; mp_to_lanes<NL>(v[i], E[i], t);
+#pragma unroll
+    for (int k = 0; k <= NL; k++) lanes[(int64_t)k * n + i] = t[k];
+  }
+}
+template <int NL> __global__ void k_from_lanes(int64_t n, const long long* lanes, const int32_t* E, mpn<NL>* v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    long long t[NL + 1];
+#pragma unroll
+    for (int k = 0; k <= NL; k++) t[k] = lanes[(int64_t)k * n + i];
+    mpn<NL> r; mp_from_lanes<NL>(r, t, E[i]); v[i] = r;
+  }
+}
 __global__ void k_combine_flags(int n, int R, const int* gathered, int* out) {
   int i = threadIdx.x; if (i >= n) return; int m = gathered[i]; for (int r = 1; r < R; r++) m = max(m, gathered[r * n + i]); out[i] = m;
 }
@@ -186,6 +206,7 @@ struct SolverBase {
   virtual void profile(int enable) = 0;
   virtual void profile_get(double* out) = 0;
   virtual double last_iteration_ms() = 0;
+  virtual void use_graph(int enable) = 0;
   virtual int bench_gemm(int M, int N, int K, int reps, int path, double* out) = 0;
   virtual int comm_init(int rank, int nranks, const void* uid) = 0;
   virtual int selftest() = 0;
@@ -230,11 +251,11 @@ template <int NL> struct Solver : SolverBase {
   static Sliced view(const Sliced& f, int v0, int cnt) { Sliced s = f; s.planes = f.planes + (size_t)v0 * f.Kp; s.E = f.E + v0; s.nvec = cnt; s.vpitch = f.pitch(); s.cap_w = s.cap_v = s.cap_b = 0; return s; }
   void ensure(Sliced& s, int nvec, int K, int lay) {
     int K4 = (K + 3) / 4; int Kp = (K + 31) & ~31;
-    if ((size_t)nvec > s.cap_v) { if (s.E) CK(cudaFreeAsync(s.E, st)); s.cap_v = nvec; CK(cudaMallocAsync((void**)&s.E, std::max<size_t>(s.cap_v, 1) * sizeof(int32_t), st)); }
+    if ((size_t)nvec > s.cap_v) { alloc_gen++; if (s.E) CK(cudaFreeAsync(s.E, st)); s.cap_v = nvec; CK(cudaMallocAsync((void**)&s.E, std::max<size_t>(s.cap_v, 1) * sizeof(int32_t), st)); }
     if (lay == 0) { size_t need = (size_t)nvec * K4 * NSP;
-      if (need > s.cap_w) { if (s.sl) CK(cudaFreeAsync(s.sl, st)); s.cap_w = need; CK(cudaMallocAsync((void**)&s.sl, std::max<size_t>(s.cap_w, 4) * sizeof(int32_t), st)); } }
+      if (need > s.cap_w) { alloc_gen++; if (s.sl) CK(cudaFreeAsync(s.sl, st)); s.cap_w = need; CK(cudaMallocAsync((void**)&s.sl, std::max<size_t>(s.cap_w, 4) * sizeof(int32_t), st)); } }
     else { size_t need = (size_t)NS * nvec * Kp;
-      if (need > s.cap_b) { if (s.planes) CK(cudaFreeAsync(s.planes, st)); s.cap_b = need; CK(cudaMallocAsync((void**)&s.planes, std::max<size_t>(s.cap_b, 16), st)); } }
+      if (need > s.cap_b) { alloc_gen++; if (s.planes) CK(cudaFreeAsync(s.planes, st)); s.cap_b = need; CK(cudaMallocAsync((void**)&s.planes, std::max<size_t>(s.cap_b, 16), st)); } }
     s.nvec = nvec; s.K = K; s.K4 = K4; s.Kp = Kp; s.lay = lay; s.vpitch = 0;
   }
   std::vector<Sliced*> owned_sliced;
@@ -284,7 +305,8 @@ template <int NL> struct Solver : SolverBase {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeFn encode_fn = nullptr;
-  uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0;
+  uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0; int32_t* tc_raw = nullptr; size_t tc_raw_cap = 0;
+  long alloc_gen = 0;     // bumped whenever a scratch buffer used by the iteration is reallocated (a captured graph is stale then)
   CUtensorMap make_map(const Sliced& P, int box_rows) {
     if (!encode_fn) { void* fn = nullptr; cudaDriverEntryPointQueryResult q; CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q)); if (!fn) throw CudaError("cuTensorMapEncodeTiled not available"); encode_fn = (EncodeFn)fn; }
     CUtensorMap m; cuuint64_t dims[3] = {(cuuint64_t)P.Kp, (cuuint64_t)P.nvec, (cuuint64_t)NS};
@@ -295,14 +317,23 @@ template <int NL> struct Solver : SolverBase {
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return m;
   }
+  // column tiling of a product with N columns: 128-wide tiles with a narrower last one and four diagonals per group, or
+  // tiles of up to 160 columns with three (both fill the 512 TMEM columns).  The slice-pair count is the same either way,
+  // so the choice minimises the summed MMA time of the tiles of one row block: an M=128, K=32 int8 MMA costs
+  // max(operand bytes / 128 B per clock of shared memory, tensor work) cycles (+ issue overhead).
+  static double mma_cycles(int bn) { return std::max((4096.0 + 32.0 * bn) / 128.0, 0.53 * bn) + 6.0; }
+  static void pick_tiles(int N, int& BN, int& group) {
+    const int N16 = (N + 15) & ~15;
+    auto cost = [&](int bn) { double c = 0; for (int n0 = 0; n0 < N; n0 += bn) c += mma_cycles(std::min(bn, (N - n0 + 15) & ~15)); return c; };
+    const int bnA = std::min(128, N16);
+    const int ntB = (N16 + tc::BNMAX - 1) / tc::BNMAX; int bnB = (((N16 + ntB - 1) / ntB) + 15) & ~15; if (bnB > tc::BNMAX) bnB = tc::BNMAX;
+    static const int force = getenv("CLRS_TC_GROUP") ? atoi(getenv("CLRS_TC_GROUP")) : 0;
+    if (force == 4 || bnB <= 128 || (force != 3 && cost(bnA) <= cost(bnB) * 1.02)) { BN = bnA; group = 4; } else { BN = bnB; group = 3; }
+  }
   void gemm_tc(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode, const num* D, int ldd,
                int batch, int64_t a_bvec, int64_t b_bvec, int64_t c_bs, int64_t d_bs, int lower_only, int trans = 0) {
     if (a0 != 0 || b0 != 0) throw CudaError("gemm_tc: panel offsets are not supported");
-    // default: both operands in shared memory (k_gemm_tc); CLRS_TC_TS=1 selects the variant with the left
-    // operand chunk in TMEM (k_gemm_ts, tiles of at most 112 columns) — measured slower once four warps issue MMAs
-    static const bool ts = getenv("CLRS_TC_TS") != nullptr;
-    // column tiles: full 128-column tiles with a narrower last one (k_gemm_tc issues N = 16..128 per tile); the TS variant keeps balanced tiles <= 112
-    const int bnmax = ts ? 112 : 128; const int ntn = (N + bnmax - 1) / bnmax; int BN = ts ? (((N + ntn - 1) / ntn + 15) & ~15) : std::min(128, (N + 15) & ~15); if (BN > bnmax) BN = bnmax;
+    int BN, group; pick_tiles(N, BN, group);
     const int Npitch = (N + 15) & ~15;
     CUtensorMap mA = make_map(A, tc::BM), mB = make_map(B, BN);
     // K longer than the int32 headroom (35 slices * K * 2^14 < 2^31), or few tiles with a long K: split K over
@@ -313,14 +344,30 @@ template <int NL> struct Solver : SolverBase {
     if (batch == 1 && tiles < 148 && A.Kp >= 256) { const int waves = (tiles * nch + 147) / 148; nch = std::max(nch, std::min(waves * 148 / tiles, A.Kp >= 2048 ? A.Kp / 512 : (A.Kp + 127) / 128)); }
     if (nch > 1 && batch != 1) throw CudaError("gemm_tc: split-K with a batch is not supported");
     int kch = ((A.Kp + nch - 1) / nch + 127) & ~127; nch = (A.Kp + kch - 1) / kch;
+    tc::Args a; a.M = M; a.N = N; a.Kp = A.Kp; a.k0 = 0; a.BN = BN; a.group = group; a.dsplit = 0; a.oraw = nullptr; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch;
+    a.lower_only = lower_only; a.Kp_total = A.Kp; a.dbg = nullptr;
+    // under-parallelised products (a few tiles on 148 SMs): one CTA per (tile, K range, diagonal group), raw int32 sums
+    // accumulated with red.add, carries resolved in k_tc_recombine_raw
+    static const int dsplit_off = getenv("CLRS_TC_DSPLIT") ? atoi(getenv("CLRS_TC_DSPLIT")) == 0 : 0;
+    const int ngroups = (NS + group - 1) / group;
+    if (!dsplit_off && batch == 1 && tiles * nch < 74 && (int64_t)M * Npitch <= (1 << 19) && A.Kp <= KMAX) {
+      const int nkc = (A.Kp + 127) / 128; int nzk = std::max(1, std::min(nkc, (296 + tiles * ngroups - 1) / (tiles * ngroups)));
+      kch = ((nkc + nzk - 1) / nzk) * 128; nzk = (A.Kp + kch - 1) / kch;
+      const size_t need = (size_t)NS * M * Npitch;
+      if (need > tc_raw_cap) { if (tc_raw) CK(cudaFreeAsync(tc_raw, st)); tc_raw_cap = need; alloc_gen++; CK(cudaMallocAsync((void**)&tc_raw, tc_raw_cap * sizeof(int32_t), st)); }
+      CK(cudaMemsetAsync(tc_raw, 0, need * sizeof(int32_t), st));
+      a.dsplit = 1; a.oraw = tc_raw; a.batch = 1; a.obytes = nullptr; a.otop = nullptr; a.kz_stride = kch;
+      dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, nzk * ngroups);
+      nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
+      nlaunch++, k_tc_recombine_raw<NL><<<(unsigned)(((int64_t)M * N + 127) / 128), 128, 0, st>>>(M, N, Npitch, tc_raw, A.E, B.E, C, ldc, D, ldd, mode, lower_only, trans);
+      return;
+    }
     const size_t outs2 = (size_t)std::max(batch, nch) * M * Npitch;
-    if (outs2 > tc_cap) { if (tc_bytes) CK(cudaFreeAsync(tc_bytes, st)); if (tc_top) CK(cudaFreeAsync(tc_top, st)); tc_cap = outs2;
+    if (outs2 > tc_cap) { if (tc_bytes) CK(cudaFreeAsync(tc_bytes, st)); if (tc_top) CK(cudaFreeAsync(tc_top, st)); tc_cap = outs2; alloc_gen++;
       CK(cudaMallocAsync((void**)&tc_bytes, tc_cap * NS, st)); CK(cudaMallocAsync((void**)&tc_top, tc_cap * sizeof(int32_t), st)); }
-    tc::Args a; a.M = M; a.N = N; a.Kp = A.Kp; a.k0 = 0; a.BN = BN; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch;
-    a.batch = nch > 1 ? nch : batch; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = lower_only; a.kz_stride = nch > 1 ? kch : 0; a.Kp_total = A.Kp; a.dbg = nullptr;
+    a.batch = nch > 1 ? nch : batch; a.obytes = tc_bytes; a.otop = tc_top; a.kz_stride = nch > 1 ? kch : 0;
     dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, a.batch);
-    if (ts) { tc::ArgsTS p; p.g = a; p.planesA = A.planes; p.nvecA = A.nvec; p.KpA = A.Kp; nlaunch++, tc::k_gemm_ts<<<grid, tc::TS_THREADS, tc::TS_SMEM_BYTES, st>>>(mB, p); }
-    else nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
+    nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
     const int64_t tot_ = (int64_t)batch * M * N;
     nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1, trans);
   }
@@ -333,13 +380,13 @@ template <int NL> struct Solver : SolverBase {
   // second execution context (stream + scratch) for work that is independent of the main chain: the Cholesky of Y
   // for the step length only needs the iterate, so it runs beside the Schur assembly.  swap_ctx() exchanges the
   // members the helpers use; kernels capture their pointers at enqueue time, so swapping while enqueuing is safe.
-  struct Ctx { cudaStream_t st = nullptr; Sliced tA, tB; num* chol_W = nullptr; size_t chol_W_cap = 0; uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0;
+  struct Ctx { cudaStream_t st = nullptr; Sliced tA, tB; num* chol_W = nullptr; size_t chol_W_cap = 0; uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0; int32_t* tc_raw = nullptr; size_t tc_raw_cap = 0;
                num* trsm_R = nullptr; size_t trsm_cap = 0; cudaEvent_t ev = nullptr; };
   Ctx side, side2;                                   // side: Cholesky of Y; side2: R = mu I - XY beside chol(X), and Y's step-length eigenvalue beside X's
   cudaEvent_t evR0 = nullptr, evR1 = nullptr, evE0 = nullptr, evE1 = nullptr; num *U2 = nullptr, *T1b = nullptr; double* Td2 = nullptr; double* eigV2 = nullptr; EigTask* eigT2 = nullptr;
   cudaEvent_t evY0 = nullptr, evY1 = nullptr; num *LY = nullptr, *MinvY = nullptr;
   void swap_with(Ctx& c) { std::swap(st, c.st); std::swap(tA, c.tA); std::swap(tB, c.tB); std::swap(chol_W, c.chol_W); std::swap(chol_W_cap, c.chol_W_cap);
-    std::swap(tc_bytes, c.tc_bytes); std::swap(tc_top, c.tc_top); std::swap(tc_cap, c.tc_cap); std::swap(trsm_R, c.trsm_R); std::swap(trsm_cap, c.trsm_cap); }
+    std::swap(tc_bytes, c.tc_bytes); std::swap(tc_top, c.tc_top); std::swap(tc_cap, c.tc_cap); std::swap(tc_raw, c.tc_raw); std::swap(tc_raw_cap, c.tc_raw_cap); std::swap(trsm_R, c.trsm_R); std::swap(trsm_cap, c.trsm_cap); }
   void swap_ctx() { swap_with(side); }
   // Independent items (PSD blocks, clusters) are enqueued round-robin on NCTX execution contexts, so that the many small
   // kernels of a many-block problem (one diagonal-block Cholesky CTA, 16-CTA GEMMs) overlap instead of queueing on one
@@ -385,9 +432,24 @@ template <int NL> struct Solver : SolverBase {
     rank = rank_; nranks = nranks_; gflags = dalloc<int>((size_t)nranks * FL_COUNT); return CLRS_OK;
   }
   int owner_of(int j) override { return (j >= 0 && j < (int)cl.size()) ? cl[j].owner : -1; }
+  long long* lane_buf = nullptr; int32_t* lane_E = nullptr; size_t lane_cap = 0;
   void allreduce(num* v, int64_t n, int op) {      // op 0 sum, 1 max-abs, 2 min
     if (nranks == 1 || n == 0) return;
-    if ((size_t)n * nranks > gcap) { gcap = (size_t)n * nranks; gbuf = dalloc<num>(gcap); }
+    // vectors and matrices (Q, sum_j u_j, p): exponent max + int64-lane sum with NCCL's own all-reduce; the handful of scalar
+    // reductions (max-abs, min, dot products) keep the all-gather + ordered combine below
+    static const int lanes_min = getenv("CLRS_LANES_MIN") ? atoi(getenv("CLRS_LANES_MIN")) : 16;
+    if (op == 0 && n >= lanes_min) {
+      constexpr int LN = NL + 1;
+      if ((size_t)n > lane_cap) { if (lane_buf) CK(cudaFreeAsync(lane_buf, st)); if (lane_E) CK(cudaFreeAsync(lane_E, st)); lane_cap = (size_t)n; alloc_gen++;
+        CK(cudaMallocAsync((void**)&lane_buf, lane_cap * LN * sizeof(long long), st)); CK(cudaMallocAsync((void**)&lane_E, lane_cap * sizeof(int32_t), st)); }
+      nlaunch++, k_lane_exp<NL><<<grid_for(n), 256, 0, st>>>(n, v, lane_E);
+      if (g_nccl.AllReduce(lane_E, lane_E, (size_t)n, /*ncclInt32*/ 2, /*ncclMax*/ 2, comm, st) != 0) throw CudaError("ncclAllReduce (max) failed");
+      nlaunch++, k_to_lanes<NL><<<grid_for(n), 256, 0, st>>>(n, v, lane_E, lane_buf);
+      if (g_nccl.AllReduce(lane_buf, lane_buf, (size_t)n * LN, /*ncclInt64*/ 4, /*ncclSum*/ 0, comm, st) != 0) throw CudaError("ncclAllReduce (sum) failed");
+      nlaunch++, k_from_lanes<NL><<<grid_for(n), 256, 0, st>>>(n, lane_buf, lane_E, v);
+      return;
+    }
+    if ((size_t)n * nranks > gcap) { if (gbuf) CK(cudaFreeAsync(gbuf, st)); gcap = (size_t)n * nranks; alloc_gen++; CK(cudaMallocAsync((void**)&gbuf, gcap * sizeof(num), st)); }
     int rc = g_nccl.AllGather(v, gbuf, (size_t)n * sizeof(num), /*ncclChar*/ 0, comm, st);
     if (rc != 0) throw CudaError("ncclAllGather failed");
     nlaunch++, k_combine_gathered<NL><<<grid_for(n), 256, 0, st>>>(n, nranks, gbuf, v, op);
@@ -415,25 +477,39 @@ template <int NL> struct Solver : SolverBase {
   num* chol_W = nullptr; size_t chol_W_cap = 0;
   // full_inverse: also assemble L^-1 below the diagonal blocks (X and Y blocks: products with L^-1 and X^-1 follow);
   // otherwise only the inverses of the 32 x 32 diagonal blocks are formed and solves go by block substitution.
+  // Two-level blocking: 128-column outer panels, 32-column steps inside a panel.  A step factors its 32 x 32 diagonal block
+  // (k_potrf_diag), solves the rows below it and updates only the REST OF THE PANEL (K = 32, CUDA cores); the trailing
+  // matrix is updated once per panel with K = 128, which is a tensor-core shape (src/tools.jl:69-107 is the unblocked loop).
+  static constexpr int PNL = 128;
   void chol(num* A, int lda, int n, num* Minv, int ldm, int code, bool full_inverse = true) {
     if (n == 0) return;
     if (ldm == n) zero(Minv, (int64_t)n * n); else for (int r = 0; r < n; r++) zero(Minv + (int64_t)r * ldm, n);
-    for (int k0 = 0; k0 < n; k0 += 32) {
-      const int nb = std::min(32, n - k0), rem = n - k0 - nb;
-      nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code, full_inverse ? 1 : 0);
-      if (rem > 0) {
-        num* A21 = A + (int64_t)(k0 + nb) * lda + k0; num* A22 = A + (int64_t)(k0 + nb) * lda + k0 + nb;
+    static const int pnl_env = getenv("CLRS_CHOL_PANEL") ? std::max(32, atoi(getenv("CLRS_CHOL_PANEL")) / 32 * 32) : 0;
+    const int pnl = pnl_env ? pnl_env : (n >= 448 ? PNL : 32);        // measured: n = 640 gains (L^-1 B 7.8 -> 4.4 ms at 16 limbs), n <= 400 does not
+    for (int K0 = 0; K0 < n; K0 += pnl) {
+      const int KE = std::min(n, K0 + pnl);
+      for (int k0 = K0; k0 < KE; k0 += 32) {
+        const int nb = std::min(32, KE - k0), rem = n - k0 - nb;
+        nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code, full_inverse ? 1 : 0);
+        if (rem <= 0) continue;
+        num* A21 = A + (int64_t)(k0 + nb) * lda + k0;
         if (full_inverse) { split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);
           gemm(tA, 0, tB, 0, rem, nb, A21, lda); }                    // L21 = A21 * inv(L11)^T
         else nlaunch++, k_trsm32<NL><<<(rem + 7) / 8, 256, 0, st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, A21, lda, 1, rem, A21, lda, 1);   // rows of L21 by substitution
-        split_rows(tA, A21, lda, rem, nb);
-        gemm(tA, 0, tA, 0, rem, rem, A22, lda, 1, A22, lda, 1, 0, 0, 0, 0, 1);   // A22 -= L21 L21^T (lower)
+        const int pc = KE - k0 - nb;                                  // columns of this panel still to be factored
+        if (pc > 0) { num* Ap = A + (int64_t)(k0 + nb) * lda + k0 + nb;
+          split_rows(tA, A21, lda, rem, nb);
+          gemm(tA, 0, tA, 0, rem, pc, Ap, lda, 1, Ap, lda); }           // A[k0+nb:, k0+nb:KE] -= L21 L21[0:pc]^T  (the strict upper part of A is never read)
       }
+      const int remO = n - KE;
+      if (remO > 0) { const int kw = KE - K0; num* Lp = A + (int64_t)KE * lda + K0; num* A22 = A + (int64_t)KE * lda + KE;
+        split_rows(tA, Lp, lda, remO, kw, use_tc(remO, remO, kw) ? 1 : 0);
+        gemm(tA, 0, tA, 0, remO, remO, A22, lda, 1, A22, lda, 1, 0, 0, 0, 0, 1); }   // A22 -= L21 L21^T (lower), K = panel width
     }
     nlaunch++, k_zero_upper<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, A, lda);
     // rows of the inverse below the diagonal blocks: M[i,0:k0] = -inv(L_ii) * (L[i,0:k0] * M[0:k0,0:k0])
     if (full_inverse && n > 32) {
-      size_t need = (size_t)32 * n; if (need > chol_W_cap) { chol_W = dalloc<num>(need); chol_W_cap = need; }
+      size_t need = (size_t)32 * n; if (need > chol_W_cap) { chol_W = dalloc<num>(need); chol_W_cap = need; alloc_gen++; }
       for (int k0 = 32; k0 < n; k0 += 32) {
         const int nb = std::min(32, n - k0);
         mm(A + (int64_t)k0 * lda, lda, Minv, ldm, nb, k0, k0, chol_W, k0);
@@ -441,24 +517,39 @@ template <int NL> struct Solver : SolverBase {
       }
     }
   }
-  // X = L^-1 B by block forward substitution (approx_solve_tril!, src/solver.jl:1258), right-looking: the block row is
-  // solved against its diagonal block (k_trsm32), then it updates the rows below, B[k0+nb:, :] -= L[k0+nb:, k-block] X_k
-  // (a K = 32 product: every panel is split exactly once)
+  // X = L^-1 B by block forward substitution (approx_solve_tril!, src/solver.jl:1258), right-looking with the same two-level
+  // blocking: a 32-row block is solved against its diagonal block (k_trsm32) and updates the rest of its 128-row panel
+  // (K = 32); the rows below the panel are updated once per panel, B[KE:, :] -= L[KE:, K0:KE] X[K0:KE, :] (K = 128, tensor cores)
   num* trsm_R = nullptr; size_t trsm_cap = 0;   // (per-context scratch slot, kept for the context swap)
   void trsm_lower(const num* Lf, int ldl, int n, const num* Minv, int ldm, const num* B, int ldb, int ncols, num* Xo, int ldx) {
     if (n == 0 || ncols == 0) return;
     if (ldb == ncols && ldx == ncols) copy(Xo, B, (int64_t)n * ncols); else for (int r = 0; r < n; r++) copy(Xo + (int64_t)r * ldx, B + (int64_t)r * ldb, ncols);
-    for (int k0 = 0; k0 < n; k0 += 32) {
-      const int nb = std::min(32, n - k0), rem = n - k0 - nb;
-      num* Xk = Xo + (int64_t)k0 * ldx;
-      nlaunch++, k_trsm32<NL><<<(ncols + 7) / 8, 256, 0, st>>>(nb, Lf + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, Xk, 1, ldx, ncols, Xk, 1, ldx);
-      if (rem > 0) { num* Xr = Xo + (int64_t)(k0 + nb) * ldx;
-        mm(Lf + (int64_t)(k0 + nb) * ldl + k0, ldl, Xk, ldx, rem, ncols, nb, Xr, ldx, 1, Xr, ldx); }
+    static const int pnl_env = getenv("CLRS_CHOL_PANEL") ? std::max(32, atoi(getenv("CLRS_CHOL_PANEL")) / 32 * 32) : 0;
+    const int pnl = pnl_env ? pnl_env : (n >= 448 ? PNL : 32);
+    for (int K0 = 0; K0 < n; K0 += pnl) {
+      const int KE = std::min(n, K0 + pnl);
+      for (int k0 = K0; k0 < KE; k0 += 32) {
+        const int nb = std::min(32, KE - k0), pr = KE - k0 - nb;
+        num* Xk = Xo + (int64_t)k0 * ldx;
+        nlaunch++, k_trsm32<NL><<<(ncols + 7) / 8, 256, 0, st>>>(nb, Lf + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, Xk, 1, ldx, ncols, Xk, 1, ldx);
+        if (pr > 0) { num* Xr = Xo + (int64_t)(k0 + nb) * ldx;
+          mm(Lf + (int64_t)(k0 + nb) * ldl + k0, ldl, Xk, ldx, pr, ncols, nb, Xr, ldx, 1, Xr, ldx); }
+      }
+      const int remO = n - KE;
+      if (remO > 0) { num* Xr = Xo + (int64_t)KE * ldx;
+        mm(Lf + (int64_t)KE * ldl + K0, ldl, Xo + (int64_t)K0 * ldx, ldx, remO, ncols, KE - K0, Xr, ldx, 1, Xr, ldx); }
     }
   }
-  // x <- L^-1 x (forward) or L^-T x (backward) by block substitution: diagonal block solve, then right-looking update
-  void trsv(const num* Lf, int ldl, int n, const num* Minv, int ldm, num* xv, bool transposed) {
-    const int nblk = (n + 31) / 32;
+  // x <- L^-1 x (forward) or L^-T x (backward) by block substitution in one launch (k_trsv_fused: one CTA per 32-row block,
+  // blocks chained through `ready` flags); CLRS_TRSV_FUSED=0 selects the two-launches-per-block form (same bits)
+  void trsv(const num* Lf, int ldl, int n, const num* Minv, int ldm, num* xv, bool transposed, unsigned* ready) {
+    const int nblk = (n + 31) / 32; if (nblk == 0) return;
+    static const int fused = getenv("CLRS_TRSV_FUSED") ? atoi(getenv("CLRS_TRSV_FUSED")) : 1;
+    if (fused && nblk > 1 && nblk <= 148) {
+      CK(cudaMemsetAsync(ready, 0, nblk * sizeof(unsigned), st));
+      nlaunch++, k_trsv_fused<NL><<<nblk, 1024, 0, st>>>(n, Lf, ldl, Minv, ldm, xv, transposed ? 1 : 0, ready);
+      return;
+    }
     for (int bi = 0; bi < nblk; bi++) {
       const int b = transposed ? nblk - 1 - bi : bi, k0 = b * 32, nb = std::min(32, n - k0);
       nlaunch++, k_trsv_block<NL><<<1, 1024, 0, st>>>(nb, Lf + (int64_t)k0 * ldl + k0, ldl, Minv + (int64_t)k0 * ldm + k0, ldm, xv + k0, transposed ? 1 : 0);
@@ -488,14 +579,14 @@ template <int NL> struct Solver : SolverBase {
     // per-iteration cached panels (layout `lay`: 1 = tensor-core panels for large blocks)
     Sliced YS, XiS, MS, MSY; int lay = 0;
   };
-  struct Clu { int owner = 0; bool owned = true; int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; int off = 0; };
+  struct Clu { int owner = 0; bool owned = true; int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; unsigned* ready = nullptr; int off = 0; };
   std::vector<Clu> cl; std::vector<Block*> blk;   // blk: all blocks in (j,l) order
   int N = 0, Ptot = 0, Ksum = 0, maximize = 1; std::vector<num> hb; num hconst;
   int64_t tot = 0;   // numbers in the flat block storage of the blocks this rank owns
   int64_t gtot = 0;  // numbers in all blocks of the SDP
   // device state
   num *X = nullptr, *Y = nullptr, *Cm = nullptr, *L = nullptr, *Minv = nullptr, *Xi = nullptr, *R = nullptr, *P = nullptr, *dX = nullptr, *dY = nullptr, *T1 = nullptr, *TXY = nullptr, *U = nullptr;
-  num* tmpU = nullptr; num* LinvBall = nullptr; int Pown = 0;
+  num* tmpU = nullptr; num* LinvBall = nullptr; int Pown = 0; unsigned* q_ready = nullptr;
   num *x = nullptr, *y = nullptr, *c = nullptr, *b = nullptr, *d = nullptr, *p = nullptr, *dx = nullptr, *dy = nullptr, *tr = nullptr, *Q = nullptr, *QMinv = nullptr, *tmpN = nullptr;
   num* sc = nullptr; int* flags = nullptr; double* dinfo = nullptr; double* Td = nullptr; double* lamX = nullptr; double* lamY = nullptr; double* eigV = nullptr; EigTask* eigT = nullptr;
   int64_t* d_boff = nullptr; int32_t* d_bn = nullptr; BlockTab bt;
@@ -511,10 +602,9 @@ template <int NL> struct Solver : SolverBase {
     if (pr.major < 10) throw CudaError("an sm_100 device is required");
     CK(cudaStreamCreate(&st)); CK(cudaStreamCreate(&side.st)); CK(cudaStreamCreate(&side2.st)); for (cudaEvent_t* e : {&evR0, &evR1, &evE0, &evE1}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY1, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming)); for (int k = 1; k < NCTX; k++) { CK(cudaStreamCreate(&pctx[k].st)); CK(cudaEventCreateWithFlags(&pctx[k].ev, cudaEventDisableTiming)); }
-    for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (auto& e : ev) CK(cudaEventCreate(&e)); for (auto& r : evD) for (auto& e : r) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
     CK(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tc::k_gemm_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TS_SMEM_BYTES));
     CK(cudaEventCreate(&pe0)); CK(cudaEventCreate(&pe1));
     mp_zero(hconst);
     double dv[10] = {o.beta_infeasible, o.beta_feasible, o.gamma, o.omega_p, o.omega_d, o.duality_gap_threshold, o.dual_error_threshold, o.primal_error_threshold, o.max_complementary_gap, o.step_length_threshold};
@@ -525,16 +615,16 @@ template <int NL> struct Solver : SolverBase {
     cudaSetDevice(opt.device); cudaDeviceSynchronize();
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     owned_sliced.push_back(&tA); owned_sliced.push_back(&tB); owned_sliced.push_back(&side.tA); owned_sliced.push_back(&side.tB); owned_sliced.push_back(&side2.tA); owned_sliced.push_back(&side2.tB);
-    if (side2.tc_bytes) cudaFree(side2.tc_bytes); if (side2.tc_top) cudaFree(side2.tc_top); cudaStreamDestroy(side2.st); for (cudaEvent_t e : {evR0, evR1, evE0, evE1}) if (e) cudaEventDestroy(e);
-    if (side.tc_bytes) cudaFree(side.tc_bytes); if (side.tc_top) cudaFree(side.tc_top); cudaEventDestroy(evY0); cudaEventDestroy(evY1); cudaStreamDestroy(side.st);
-    for (int k = 1; k < NCTX; k++) { Ctx& c = pctx[k]; owned_sliced.push_back(&c.tA); owned_sliced.push_back(&c.tB); if (c.tc_bytes) cudaFree(c.tc_bytes); if (c.tc_top) cudaFree(c.tc_top);
+    if (side2.tc_bytes) cudaFree(side2.tc_bytes); if (side2.tc_top) cudaFree(side2.tc_top); if (side2.tc_raw) cudaFree(side2.tc_raw); cudaStreamDestroy(side2.st); for (cudaEvent_t e : {evR0, evR1, evE0, evE1}) if (e) cudaEventDestroy(e);
+    if (side.tc_bytes) cudaFree(side.tc_bytes); if (side.tc_top) cudaFree(side.tc_top); if (side.tc_raw) cudaFree(side.tc_raw); cudaEventDestroy(evY0); cudaEventDestroy(evY1); cudaStreamDestroy(side.st);
+    for (int k = 1; k < NCTX; k++) { Ctx& c = pctx[k]; owned_sliced.push_back(&c.tA); owned_sliced.push_back(&c.tB); if (c.tc_bytes) cudaFree(c.tc_bytes); if (c.tc_top) cudaFree(c.tc_top); if (c.tc_raw) cudaFree(c.tc_raw);
       if (c.ev) cudaEventDestroy(c.ev); if (c.st) cudaStreamDestroy(c.st); }
     if (evFork) cudaEventDestroy(evFork);
     for (Sliced* s : owned_sliced) { if (s->sl) cudaFree(s->sl); if (s->E) cudaFree(s->E); if (s->planes) cudaFree(s->planes); }
-    if (tc_bytes) cudaFree(tc_bytes); if (tc_top) cudaFree(tc_top); if (pe0) cudaEventDestroy(pe0); if (pe1) cudaEventDestroy(pe1);
+    if (tc_bytes) cudaFree(tc_bytes); if (tc_top) cudaFree(tc_top); if (tc_raw) cudaFree(tc_raw); if (pe0) cudaEventDestroy(pe0); if (pe1) cudaEventDestroy(pe1);
     for (void* p : allocs) cudaFree(p);
-    if (wstage) cudaFree(wstage);
-    for (auto& e : ev) cudaEventDestroy(e);
+    if (wstage) cudaFree(wstage); if (gbuf) cudaFree(gbuf); if (lane_buf) cudaFree(lane_buf); if (lane_E) cudaFree(lane_E);
+    drop_graph(); for (auto& e : ev) cudaEventDestroy(e); for (auto& r : evD) for (auto& e : r) cudaEventDestroy(e);
     cudaStreamDestroy(st);
   }
   int set_option_num(int which, const void* w) override { if (which < 0 || which > 9) return CLRS_ERR_ARG; w2m(hopt[which], w); return 0; }
@@ -549,20 +639,25 @@ template <int NL> struct Solver : SolverBase {
     return 0;
   }
   int add_block(int j, int l, int m, int delta, int high_rank, const void* C) override {
-    if (j >= (int)cl.size() || l != (int)cl[j].blocks.size()) { err = "blocks must be added in order"; return CLRS_ERR_ARG; }
+    if (j < 0 || j >= (int)cl.size() || l != (int)cl[j].blocks.size()) { err = "blocks must be added in order"; return CLRS_ERR_ARG; }
+    if (m < 1 || delta < 1) { err = "clrs_add_block: m and delta must be positive"; return CLRS_ERR_ARG; }
     if (high_rank && m != 1) { err = "dense blocks have one subblock"; return CLRS_ERR_ARG; }
     cl[j].blocks.emplace_back(); Block& b0 = cl[j].blocks.back(); b0.j = j; b0.l = l; b0.m = m; b0.delta = delta; b0.n = m * delta; b0.high_rank = high_rank != 0;
     b0.hC.resize((size_t)b0.n * b0.n); for (size_t i = 0; i < b0.hC.size(); i++) w2m(b0.hC[i], (const char*)C + i * wire_size());
     return 0;
   }
   int add_dense_term(int j, int l, int p_, const void* A) override {
+    if (j < 0 || j >= (int)cl.size() || l < 0 || l >= (int)cl[j].blocks.size()) { err = "clrs_add_dense_term: no such block"; return CLRS_ERR_ARG; }
+    if (p_ < 0 || p_ >= cl[j].P) { err = "clrs_add_dense_term: constraint row out of range"; return CLRS_ERR_ARG; }
     Block& b0 = cl[j].blocks[l]; if (!b0.high_rank) { err = "dense term on a low-rank block"; return CLRS_ERR_ARG; }
     b0.dense_p.push_back(p_); b0.dense_A.emplace_back((size_t)b0.n * b0.n); auto& v = b0.dense_A.back();
     for (size_t i = 0; i < v.size(); i++) w2m(v[i], (const char*)A + i * wire_size());
     return 0;
   }
   int add_lowrank_term(int j, int l, int r, int s, int p_, int rank, const void* lam, const void* vs, const void* ws) override {
+    if (j < 0 || j >= (int)cl.size() || l < 0 || l >= (int)cl[j].blocks.size()) { err = "clrs_add_lowrank_term: no such block"; return CLRS_ERR_ARG; }
     Block& b0 = cl[j].blocks[l]; if (b0.high_rank) { err = "low-rank term on a dense block"; return CLRS_ERR_ARG; }
+    if (p_ < 0 || p_ >= cl[j].P || r < 0 || r >= b0.m || s < 0 || s >= b0.m || rank < 0) { err = "clrs_add_lowrank_term: index out of range"; return CLRS_ERR_ARG; }
     for (int k = 0; k < rank; k++) { b0.lr.emplace_back(); HTerm& t = b0.lr.back(); t.r = r; t.s = s; t.p = p_; t.k = k;
       w2m(t.lam, (const char*)lam + k * wire_size()); t.v.resize(b0.delta); t.w.resize(b0.delta);
       for (int a = 0; a < b0.delta; a++) { w2m(t.v[a], (const char*)vs + ((size_t)k * b0.delta + a) * wire_size()); w2m(t.w[a], (const char*)ws + ((size_t)k * b0.delta + a) * wire_size()); } }
@@ -589,7 +684,7 @@ template <int NL> struct Solver : SolverBase {
     x = dalloc<num>(Ptot); d = dalloc<num>(Ptot); dx = dalloc<num>(Ptot); tr = dalloc<num>(Ptot);
     y = dalloc<num>(N); p = dalloc<num>(N); dy = dalloc<num>(N); tmpN = dalloc<num>(N); Q = dalloc<num>((size_t)N * N); QMinv = dalloc<num>((size_t)N * N);
     { std::vector<num> hc; num z; mp_zero(z); for (auto& c0 : cl) { if (c0.owned) hc.insert(hc.end(), c0.hc.begin(), c0.hc.end()); else hc.insert(hc.end(), c0.P, z); } c = upload(hc); b = upload(hb); }   // c of clusters owned elsewhere reads as 0
-    tmpU = dalloc<num>(N);
+    tmpU = dalloc<num>(N); q_ready = dalloc<unsigned>((size_t)(N + 31) / 32 + 1);
     Td = dalloc<double>(tot); lamX = dalloc<double>(blk.size()); lamY = dalloc<double>(blk.size());
     { std::vector<EigTask> et; size_t vtot = 0; for (Block* b0 : blk) vtot += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); eigV = dalloc<double>(vtot); size_t o = 0;
       for (Block* b0 : blk) { EigTask t; t.T = Td + b0->off; t.n = b0->n; t.V = eigV + o; o += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); et.push_back(t); } eigT = upload(et);
@@ -601,7 +696,7 @@ template <int NL> struct Solver : SolverBase {
     { int64_t o = 0; for (auto& c0 : cl) if (c0.owned) { c0.LinvB = LinvBall + o * N; o += c0.P; } }
     for (auto& c0 : cl) {
       if (!c0.owned) continue;
-      c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.t = dalloc<num>(c0.P);
+      c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.t = dalloc<num>(c0.P); c0.ready = dalloc<unsigned>((size_t)(c0.P + 31) / 32 + 1);
       for (auto& b0 : c0.blocks) if (int rc = finalize_block(c0, b0)) return rc;
     }
     // scalars
@@ -794,13 +889,13 @@ template <int NL> struct Solver : SolverBase {
   }
   void pairings_dense(Block& b0) {                    // T = X^-1 A_p Y, S[p,q] += <A_q, T>   (src/solver.jl:1089-1104)
     const int n = b0.n, np = b0.np; if (np == 0) return; const int64_t nn = (int64_t)n * n;
-    // chunk of constraints = a whole number of waves of the product's CTAs on the 148 SMs (n = 300: 3 column tiles x 148 row
-    // tiles = 63 constraints = exactly 3 waves), so chunking costs no extra partial wave
+    // chunk of constraints = a whole number of waves of the product's CTAs on the 148 SMs (n = 300: 2 column tiles x 148 row
+    // tiles = 63 constraints = exactly 2 waves), so chunking costs no extra partial wave
     static const int chunks_off = getenv("CLRS_SCHUR_CHUNKS") ? atoi(getenv("CLRS_SCHUR_CHUNKS")) == 1 : 0;
     int pc = np;
     if (!chunks_off && b0.lay == 1 && b0.AallV.lay == 1 && (int64_t)np * n >= 32768) {
-      const int ntn = (n + 127) / 128; int k = 1; while ((148 * k) % ntn) k++;
-      pc = std::max(1, (148 * k / ntn) * 128 / n); }
+      int BNt, grp; pick_tiles(n, BNt, grp); const int ntn = (n + BNt - 1) / BNt;       // column tiles of the product
+      pc = std::max(1, ((2 * 148 / ntn) * 128) / n); }                                    // two waves of CTAs per chunk
     const int nchunk = (np + pc - 1) / pc;
     if (nchunk > 1) {
       // the constraints are processed in chunks on different execution contexts: while one chunk's products occupy the
@@ -835,45 +930,51 @@ template <int NL> struct Solver : SolverBase {
     par_clusters([&](Clu& c0) { zero(c0.S, (int64_t)c0.P * c0.P);
       for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_add_dense(c0, b0); else schur_add_lowrank(c0, b0); }
       if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); });
-    CK(cudaEventRecord(ev[e0], st));
+    rec(ev[e0]);
     par_clusters([&](Clu& c0) { chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S, false); });
-    CK(cudaEventRecord(ev[e0 + 1], st));
+    rec(ev[e0 + 1]);
     if (N > 0) {
       par_clusters([&](Clu& c0) { if (c0.P) trsm_lower(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.B, N, N, c0.LinvB, N); });     // LinvB = L^-1 B  (:1258)
-      CK(cudaEventRecord(ev[e0 + 2], st));
+      rec(ev[e0 + 2]);
       if (Pown == 0) zero(Q, (int64_t)N * N);
       else { split_cols(tA, LinvBall, N, Pown, N, use_tc(N, N, Pown) ? 1 : 0);
         gemm(tA, 0, tA, 0, N, N, Q, N, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);                                  // Q = (vcat LinvB)^T (vcat LinvB), lower triangle  (:1268-1269)
         nlaunch++, k_mirror<NL><<<grid_for((int64_t)N * N), 256, 0, st>>>(N, Q, N, 0); }
       allreduce(Q, (int64_t)N * N, 0);                                                                  // the only cross-cluster coupling
-      CK(cudaEventRecord(ev[e0 + 3], st));
+      rec(ev[e0 + 3]);
       chol(Q, N, N, QMinv, N, CLRS_ERR_CHOL_Q, false);
-    } else { CK(cudaEventRecord(ev[e0 + 2], st)); CK(cudaEventRecord(ev[e0 + 3], st)); }
-    CK(cudaEventRecord(ev[e0 + 4], st));
+    } else { rec(ev[e0 + 2]); rec(ev[e0 + 3]); }
+    rec(ev[e0 + 4]);
   }
   // search direction  (compute_search_direction!, src/solver.jl:1474-1616)
-  void direction() {
+  void direction(int which) {                                          // which: 0 predictor, 1 corrector (phase timers 13-17)
+    rec(evD[which][0]);
     par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, P + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); });     // P Y
     addsub(T1, T1, 1, R, -1, tot);
     par_blocks([&](Block* b0) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n, b0->lay); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); });    // Z = X^-1 (P Y - R)
     nlaunch++, k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
+    rec(evD[which][1]);
     trace_vectors(tr, dY);
     if (Ptot) nlaunch++, k_vec_rhs<NL><<<(Ptot + 127) / 128, 128, 0, st>>>(Ptot, dx, d, tr);                                                          // rhs_x = -d - <A_*, Z>
+    rec(evD[which][2]);
     // block elimination  (:1527-1582)
     if (N > 0) zero(tmpU, N);
-    par_clusters([&](Clu& c0) { if (c0.P) { copy(c0.t, dx + c0.off, c0.P); trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, false); } });                 // t_j = L_j^-1 rhs_j
+    par_clusters([&](Clu& c0) { if (c0.P) { copy(c0.t, dx + c0.off, c0.P); trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, false, c0.ready); } });                 // t_j = L_j^-1 rhs_j
     if (N > 0) for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
       nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                                        // u += LinvB_j^T t_j
     if (N > 0) { allreduce(tmpU, N, 0); addsub(dy, p, 1, tmpU, -1, N);                                                                       // dy = p - sum_j u_j
-      trsv(Q, N, N, QMinv, N, dy, false); trsv(Q, N, N, QMinv, N, dy, true); }                                                              // dy = Q^-1 dy
+      trsv(Q, N, N, QMinv, N, dy, false, q_ready); trsv(Q, N, N, QMinv, N, dy, true, q_ready); }                                                              // dy = Q^-1 dy
     par_clusters([&](Clu& c0) { if (c0.P == 0) return;
       if (N > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
-      trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, true); copy(dx + c0.off, c0.t, c0.P); });                                                 // dx_j = L_j^-T t_j
+      trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, true, c0.ready); copy(dx + c0.off, c0.t, c0.P); });                                                 // dx_j = L_j^-T t_j
+    rec(evD[which][3]);
     weighted_A(dX, dx); addsub(dX, dX, 1, P, 1, tot);                                                                                       // dX = P + sum dx_p A_p
+    rec(evD[which][4]);
     par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, T1 + b0->off, n); });     // dX Y
     addsub(T1, R, 1, T1, -1, tot);
     par_blocks([&](Block* b0) { const int n = b0->n; split_cols(tB, T1 + b0->off, n, n, n, b0->lay); gemm(b0->XiS, 0, tB, 0, n, n, dY + b0->off, n); });    // dY = X^-1 (R - dX Y)
     nlaunch++, k_symmetrize<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, dY);
+    rec(evD[which][5]);
   }
   // lambda_min( L^-1 dM L^-T ) per block in Float64  (compute_step_length, src/solver.jl:1620-1693); Mi holds L^-1
   void step_eigs(const num* Mi, const num* dM, double* lam, bool forY) {
@@ -885,7 +986,7 @@ template <int NL> struct Solver : SolverBase {
       split_rows(tA, Ub + b0->off, n, n, n, b0->lay); gemm(tA, 0, ms, 0, n, n, Tb + b0->off, n); });       // T = U L^-T
     nlaunch++, k_to_double_sym<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, Tb, Tdb);
     if (!blk.empty()) { int maxn = 1; for (Block* b0 : blk) maxn = std::max(maxn, b0->n);
-      nlaunch++, k_min_eig<<<(unsigned)blk.size(), maxn <= 32 ? 128 : (maxn <= 128 ? 256 : EIG_THREADS), 0, st>>>(et, lam); }
+      nlaunch++, k_min_eig<<<(unsigned)blk.size(), maxn <= 32 ? 128 : (maxn <= 128 ? 256 : EIG_THREADS), 0, st>>>(et, lam, flags + FL_STATUS, CLRS_ERR_EIG); }
   }
 
   int check_status() { return hflags[FL_STATUS]; }
@@ -898,12 +999,14 @@ template <int NL> struct Solver : SolverBase {
   }
 
   // ---- one iteration  (loop body src/solver.jl:362-592) -----------------------------------
-  int iterate(clrs_iter_info* info) override {
-    if (!finalized) { err = "clrs_finalize has not been called"; return CLRS_ERR_ARG; }
-    memset(info, 0, sizeof(*info)); info->iter = iter; info->d_obj = h_dobj; info->p_obj = h_pobj; info->gap = h_gap; info->pd_feasible = h_pdfeas;
-    int reason = 0; if (host_terminate(reason)) { info->stop = reason; return 0; }
+  // timing events: recorded as external event nodes while the iteration is being captured into a CUDA graph
+  bool capturing = false; cudaEvent_t evD[2][6];
+  void rec(cudaEvent_t e) { if (capturing) CK(cudaEventRecordWithFlags(e, st, cudaEventRecordExternal)); else CK(cudaEventRecord(e, st)); }
+  // everything the iteration enqueues, from the flag reset to the last reduction: pure stream work with no host
+  // decision in between (scalars live on the device), so it can be replayed as a graph
+  void enqueue_iteration() {
     CK(cudaMemsetAsync(flags + FL_STOP, 0, 2 * sizeof(int), st));
-    CK(cudaEventRecord(ev[0], st));
+    rec(ev[0]);
     // side stream: Cholesky of Y and L_Y^-1 for the step length (Y does not change until the step at the end)
     CK(cudaEventRecord(evY0, st)); swap_ctx(); CK(cudaStreamWaitEvent(st, evY0, 0));
     copy(LY, Y, tot);
@@ -914,29 +1017,29 @@ template <int NL> struct Solver : SolverBase {
     par_blocks([&](Block* b0) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n, b0->lay); });      // Y panels: used by R, the Schur products and the directions
     CK(cudaEventRecord(evR0, st)); swap_with(side2); CK(cudaStreamWaitEvent(st, evR0, 0));                      // R is first needed by the predictor: beside chol(X) and the Schur assembly
     par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, X + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); });
-    k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, (const num*)nullptr, sc + SC_MUP);
+    nlaunch++, k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, (const num*)nullptr, sc + SC_MUP);
     CK(cudaEventRecord(evR1, st)); swap_with(side2);
-    CK(cudaEventRecord(ev[1], st));
+    rec(ev[1]);
     // Cholesky of X, L^-1, X^-1  (src/solver.jl:388-399, 1117)
     copy(L, X, tot);
     par_blocks([&](Block* b0) { const int n = b0->n; chol(L + b0->off, n, n, Minv + b0->off, n, CLRS_ERR_CHOL_X);
       split_cols(tA, Minv + b0->off, n, n, n, b0->lay); gemm(tA, 0, tA, 0, n, n, Xi + b0->off, n);               // X^-1 = L^-T L^-1
       split_rows(b0->XiS, Xi + b0->off, n, n, n, b0->lay); });
-    CK(cudaEventRecord(ev[2], st));
+    rec(ev[2]);
     decomposition(3);                                                 // events 3..7
     trace_pairings(tr); residuals();
     CK(cudaStreamWaitEvent(st, evR1, 0));
-    CK(cudaEventRecord(ev[8], st));
-    direction();                                                      // predictor
-    CK(cudaEventRecord(ev[9], st));
+    rec(ev[8]);
+    direction(0);                                                     // predictor
+    rec(ev[9]);
     reduce(X, dY, tot, sc + SC_D1, 0); reduce(dX, Y, tot, sc + SC_D2, 0); reduce(dX, dY, tot, sc + SC_D3, 0); allreduce(sc + SC_D1, 3, 0);   // D1..D3 adjacent
     errors(); scalar(1);
-    CK(cudaEventRecord(ev[10], st));
+    rec(ev[10]);
     par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, dX + b0->off, n, n, n, b0->lay); split_cols(tB, dY + b0->off, n, n, n, b0->lay); gemm(tA, 0, tB, 0, n, n, T1 + b0->off, n); });
-    k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, T1, sc + SC_MUC);                     // R = mu_c I - XY - dXdY
-    CK(cudaEventRecord(ev[11], st));
-    direction();                                                      // corrector
-    CK(cudaEventRecord(ev[12], st));
+    nlaunch++, k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, T1, sc + SC_MUC);                     // R = mu_c I - XY - dXdY
+    rec(ev[11]);
+    direction(1);                                                     // corrector
+    rec(ev[12]);
     // step lengths: X reuses its factor of this iteration (X is unchanged); Y is factored here
     CK(cudaEventRecord(evE0, st)); swap_with(side2); CK(cudaStreamWaitEvent(st, evE0, 0)); CK(cudaStreamWaitEvent(st, evY1, 0));
     step_eigs(MinvY, dY, lamY, true);                                                                           // Y's eigenvalue beside X's
@@ -944,34 +1047,71 @@ template <int NL> struct Solver : SolverBase {
     step_eigs(Minv, dX, lamX, false); scalar(2, X, dX, lamX); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAD);
     CK(cudaStreamWaitEvent(st, evY1, 0)); CK(cudaStreamWaitEvent(st, evE1, 0));
     scalar(2, Y, dY, lamY); allreduce(sc + SC_TMP, 1, 2); scalar(6, nullptr, nullptr, nullptr, SC_ALPHAP);
+    allreduce_flags();                                                 // a failed factorisation on any rank stops every rank: no step is taken then
     scalar(3);
-    CK(cudaEventRecord(ev[13], st));
-    // the step  (src/solver.jl:485-495)
+    rec(ev[13]);
+    // the step  (src/solver.jl:485-495); alpha = 0 after a failure or a stop, so the iterate stays the last good one (:594-628)
     if (Ptot) nlaunch++, k_axpy<NL><<<grid_for(Ptot), 256, 0, st>>>(Ptot, x, dx, sc + SC_ALPHAD);
     if (N) nlaunch++, k_axpy<NL><<<grid_for(N), 256, 0, st>>>(N, y, dy, sc + SC_ALPHAP);
     nlaunch++, k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, X, dX, sc + SC_ALPHAD);
     nlaunch++, k_axpy<NL><<<grid_for(tot), 256, 0, st>>>(tot, Y, dY, sc + SC_ALPHAP);
     objectives();
     reduce(X, Y, tot, sc + SC_D0, 0); allreduce(sc + SC_D0, 1, 0);     // <X,Y> of the new iterate for the next mu
-    allreduce_flags();                                                 // a failed Cholesky on any rank stops every rank
-    CK(cudaEventRecord(ev[14], st));
+    rec(ev[14]);
+  }
+  // CUDA graph of the iteration: captured on the second iteration of a handle (the first one runs eagerly and sizes every
+  // scratch buffer), replayed afterwards; re-captured if a scratch buffer was reallocated in between (alloc_gen)
+  cudaGraphExec_t gexec = nullptr; long graph_gen = -1; long graph_nodes_launches = 0; int eager_iters = 0; bool graph_off = false;
+  void drop_graph() { if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; } }
+  void run_iteration() {
+    static const int env_graph = getenv("CLRS_GRAPH") ? atoi(getenv("CLRS_GRAPH")) : 1;
+    if (!env_graph || graph_off || prof_on || eager_iters < 1) { enqueue_iteration(); eager_iters++; return; }
+    if (gexec && graph_gen != alloc_gen) drop_graph();
+    if (!gexec) {
+      const long gen0 = alloc_gen, nl0 = nlaunch; cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      capturing = true;
+      try { enqueue_iteration(); }
+      catch (...) { capturing = false; cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); graph_off = true; throw; }
+      capturing = false;
+      cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (e != cudaSuccess || !g || alloc_gen != gen0) {           // a buffer grew during the capture: run this iteration eagerly, capture the next one
+        if (g) cudaGraphDestroy(g); cudaGetLastError(); nlaunch = nl0;
+        if (e != cudaSuccess) graph_off = true;
+        enqueue_iteration(); return; }
+      graph_nodes_launches = nlaunch - nl0; nlaunch = nl0;
+      e = cudaGraphInstantiate(&gexec, g, 0); cudaGraphDestroy(g);
+      if (e != cudaSuccess) { gexec = nullptr; cudaGetLastError(); graph_off = true; enqueue_iteration(); return; }
+      graph_gen = alloc_gen;
+    }
+    CK(cudaGraphLaunch(gexec, st)); nlaunch += graph_nodes_launches;
+  }
+  int iterate(clrs_iter_info* info) override {
+    if (!finalized) { err = "clrs_finalize has not been called"; return CLRS_ERR_ARG; }
+    memset(info, 0, sizeof(*info)); info->iter = iter; info->d_obj = h_dobj; info->p_obj = h_pobj; info->gap = h_gap; info->pd_feasible = h_pdfeas;
+    int reason = 0; if (host_terminate(reason)) { info->stop = reason; last_ms = 0; return 0; }
+    run_iteration();
     pull_info();
     if (int s = check_status()) {
       const char* msg = s == CLRS_ERR_CHOL_X ? "The cholesky decomposition of X was not computed correctly. Try again with higher precision"
                       : s == CLRS_ERR_CHOL_S ? "S was not decomposed succesfully, try again with higher precision."
                       : s == CLRS_ERR_CHOL_Q ? "Q was not decomposed correctly. Try restarting with a higher precision."
+                      : s == CLRS_ERR_EIG ? "The eigenvalues could not be computed during the computation of the step length."
                       : "The cholesky decomposition could not be computed during the computation of the step length.";
-      err = msg; return s;
+      CK(cudaMemsetAsync(flags + FL_STATUS, 0, sizeof(int), st));
+      err = msg; last_ms = 0; return s;
     }
     info->stop = hflags[FL_STOP]; info->pd_feasible = hflags[FL_PDFEAS];
     info->mu = hinfo[INFO_MU]; info->err_P = hinfo[INFO_ERRP]; info->err_p = hinfo[INFO_ERRp]; info->err_d = hinfo[INFO_ERRd];
     info->alpha_d = hinfo[INFO_ALPHAD]; info->alpha_p = hinfo[INFO_ALPHAP]; info->beta_c = hinfo[INFO_BETAC];
     info->d_obj_new = hinfo[INFO_DOBJ + 10]; info->p_obj_new = hinfo[INFO_POBJ + 10]; info->gap_new = hinfo[INFO_GAP + 10];
-    auto ms = [&](int a, int b_) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b_]); return (double)t; };
+    auto ms = [&](int a, int b_) { float t = 0; if (cudaEventElapsedTime(&t, ev[a], ev[b_]) != cudaSuccess) { cudaGetLastError(); t = 0; } return (double)t; };
+    auto msd = [&](int k) { float t0 = 0, t1 = 0; if (cudaEventElapsedTime(&t0, evD[0][k], evD[0][k + 1]) != cudaSuccess || cudaEventElapsedTime(&t1, evD[1][k], evD[1][k + 1]) != cudaSuccess) { cudaGetLastError(); return 0.0; } return (double)t0 + (double)t1; };
     last_ms = ms(0, 14);
     info->phase_ms[0] = ms(2, 7); info->phase_ms[1] = ms(8, 9); info->phase_ms[2] = ms(11, 12); info->phase_ms[3] = ms(12, 13); info->phase_ms[4] = ms(1, 2);
     info->phase_ms[5] = ms(0, 1) + ms(10, 11); info->phase_ms[6] = ms(7, 8);
     info->phase_ms[7] = ms(2, 3); info->phase_ms[8] = ms(3, 4); info->phase_ms[9] = ms(4, 5); info->phase_ms[10] = ms(5, 6); info->phase_ms[11] = ms(6, 7);
+    for (int k = 0; k < 5; k++) info->phase_ms[12 + k] = msd(k);        // Z, rhs_x, solve, dX, dY of predictor + corrector (src/solver.jl:540)
     h_pdfeas = hflags[FL_PDFEAS];
     h_derr = std::max(info->err_P, info->err_p); h_perr = info->err_d;
     if (info->stop == 0) { h_dobj = info->d_obj_new; h_pobj = info->p_obj_new; h_gap = info->gap_new; iter++; }
@@ -985,22 +1125,43 @@ template <int NL> struct Solver : SolverBase {
   int64_t matrix_count() const override { return gtot; }
   // x: all constraints; X, Y: all blocks of the SDP in (j,l) order (global layout).  A sharded handle reads/writes the
   // parts it owns; get_state leaves the others untouched (the host merges the ranks' outputs).
+  // The four arrays cross PCIe as raw wire bytes through ONE device staging buffer: every contiguous run of owned
+  // numbers is one copy + one conversion kernel, and the call synchronises once (pinned caller buffers make the copies true DMA).
+  struct Run { num* dev; size_t first; size_t n; int arr; };            // device destination, first record in caller array `arr`, count
+  void state_runs(std::vector<Run>& runs, bool hx, bool hX, bool hy, bool hY) {
+    auto push = [&](num* dev, size_t first, size_t n, int arr) { if (!n) return;
+      if (!runs.empty() && runs.back().arr == arr && runs.back().first + runs.back().n == first && runs.back().dev + runs.back().n == dev) runs.back().n += n; else runs.push_back({dev, first, n, arr}); };
+    if (hx) for (auto& c0 : cl) if (c0.owned) push(x + c0.off, (size_t)c0.off, (size_t)c0.P, 0);
+    if (hy) push(y, 0, (size_t)N, 2);
+    if (hX) for (Block* b0 : blk) push(X + b0->off, (size_t)b0->goff, (size_t)b0->n * b0->n, 1);
+    if (hY) for (Block* b0 : blk) push(Y + b0->off, (size_t)b0->goff, (size_t)b0->n * b0->n, 3);
+  }
   int set_state(const void* x_, const void* X_, const void* y_, const void* Y_) override {
-    auto up = [&](num* dst, const void* w, size_t n) { if (!w || !n) return; wire_to_device(dst, w, n); };
-    if (x_) for (auto& c0 : cl) if (c0.owned) up(x + c0.off, (const char*)x_ + (size_t)c0.off * wire_size(), c0.P);
-    up(y, y_, N);
-    for (Block* b0 : blk) { size_t nn = (size_t)b0->n * b0->n; if (X_) up(X + b0->off, (const char*)X_ + (size_t)b0->goff * wire_size(), nn); if (Y_) up(Y + b0->off, (const char*)Y_ + (size_t)b0->goff * wire_size(), nn); }
-    initial_quantities(); return 0;
+    std::vector<Run> runs; state_runs(runs, x_ != nullptr, X_ != nullptr, y_ != nullptr, Y_ != nullptr);
+    size_t total = 0; for (auto& r : runs) total += r.n;
+    const void* src[4] = {x_, X_, y_, Y_}; const size_t ws = wire_size();
+    if (total) { unsigned char* sbuf = stage(total * ws); size_t o = 0;
+      for (auto& r : runs) { CK(cudaMemcpyAsync(sbuf + o * ws, (const char*)src[r.arr] + r.first * ws, r.n * ws, cudaMemcpyHostToDevice, st));
+        nlaunch++, k_wire_to_mpn<NL><<<grid_for((int64_t)r.n), 256, 0, st>>>((int64_t)r.n, sbuf + o * ws, W(), r.dev); o += r.n; } }
+    initial_quantities(); return 0;                     // (synchronises once, reading the report)
   }
   int get_state(void* x_, void* X_, void* y_, void* Y_) override {
-    if (x_) for (auto& c0 : cl) if (c0.owned && c0.P) download_wire((char*)x_ + (size_t)c0.off * wire_size(), x + c0.off, c0.P);
-    if (y_ && N) download_wire(y_, y, N);
-    for (Block* b0 : blk) { size_t nn = (size_t)b0->n * b0->n; if (X_) download_wire((char*)X_ + (size_t)b0->goff * wire_size(), X + b0->off, nn); if (Y_) download_wire((char*)Y_ + (size_t)b0->goff * wire_size(), Y + b0->off, nn); }
-    return 0;
+    std::vector<Run> runs; state_runs(runs, x_ != nullptr, X_ != nullptr, y_ != nullptr && N > 0, Y_ != nullptr);
+    size_t total = 0; for (auto& r : runs) total += r.n;
+    void* dst[4] = {x_, X_, y_, Y_}; const size_t ws = wire_size();
+    if (!total) return 0;
+    unsigned char* sbuf = stage(total * ws); size_t o = 0;
+    for (auto& r : runs) { nlaunch++, k_mpn_to_wire<NL><<<grid_for((int64_t)r.n), 256, 0, st>>>((int64_t)r.n, r.dev, W(), sbuf + o * ws);
+      CK(cudaMemcpyAsync((char*)dst[r.arr] + r.first * ws, sbuf + o * ws, r.n * ws, cudaMemcpyDeviceToHost, st)); o += r.n; }
+    CK(cudaStreamSynchronize(st)); return 0;
   }
   // ---- standalone kernels -----------------------------------------------------------------
+  // scratch of one call: freed when the call returns (the handle's `allocs` list only holds the SDP's own buffers)
+  struct Scratch { std::vector<void*> p; ~Scratch() { for (void* q : p) cudaFree(q); } };
+  template <class T> T* talloc(Scratch& sc_, size_t n) { void* p = nullptr; CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T))); sc_.p.push_back(p); CK(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), st)); return (T*)p; }
   int mp_gemm(int M, int N_, int K, const void* A, const void* B, void* C, int path, double* ms) override {
-    num* dA = upload_wire(A, (size_t)M * K); num* dB = upload_wire(B, (size_t)K * N_); num* dC = dalloc<num>((size_t)M * N_);
+    Scratch tmp; num* dA = talloc<num>(tmp, (size_t)M * K); num* dB = talloc<num>(tmp, (size_t)K * N_); num* dC = talloc<num>(tmp, (size_t)M * N_);
+    wire_to_device(dA, A, (size_t)M * K); wire_to_device(dB, B, (size_t)K * N_);
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int saved = opt.gemm_path; if (path) opt.gemm_path = path;
     CK(cudaEventRecord(e0, st)); mm(dA, K, dB, N_, M, N_, K, dC, N_); CK(cudaEventRecord(e1, st)); opt.gemm_path = saved; CK(cudaStreamSynchronize(st));
@@ -1009,7 +1170,8 @@ template <int NL> struct Solver : SolverBase {
     download_wire(C, dC, (size_t)M * N_); return 0;
   }
   int mp_cholesky(int n, const void* A, void* Lw) override {
-    num* dA = upload_wire(A, (size_t)n * n); num* dM = dalloc<num>((size_t)n * n);
+    Scratch tmp; num* dA = talloc<num>(tmp, (size_t)n * n); num* dM = talloc<num>(tmp, (size_t)n * n);
+    wire_to_device(dA, A, (size_t)n * n);
     CK(cudaMemsetAsync(flags, 0, FL_COUNT * sizeof(int), st));
     chol(dA, n, n, dM, n, CLRS_ERR_CHOL_X);
     int f[FL_COUNT]; CK(cudaMemcpyAsync(f, flags, sizeof(f), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
@@ -1021,6 +1183,7 @@ template <int NL> struct Solver : SolverBase {
   void profile(int enable) override { prof_on = enable != 0; for (int i = 0; i < 3; i++) { prof_ms[i] = 0; prof_flops[i] = 0; prof_n[i] = 0; } nlaunch = 0; }
   void profile_get(double* o) override { for (int i = 0; i < 3; i++) { o[3 * i] = prof_ms[i]; o[3 * i + 1] = prof_flops[i]; o[3 * i + 2] = (double)prof_n[i]; } o[9] = (double)nlaunch; }
   double last_iteration_ms() override { return last_ms; }
+  void use_graph(int enable) override { graph_off = !enable; if (!enable) drop_graph(); }
   // device self-test: warp-cooperative arithmetic (mpw.cuh) against the single-thread routines on random operands; returns mismatches
   int selftest() override {
     if constexpr (NL != 8 && NL != 16) return 0;                       // 10 limbs: the pivot chain stays on one thread
@@ -1032,7 +1195,7 @@ template <int NL> struct Solver : SolverBase {
   }
   // kernel-only timing of C = A*B on device-generated operands: out = {split ms, gemm ms per rep (kernel + recombine), kernel-only ms per rep}
   int bench_gemm(int M, int N_, int K, int reps, int path, double* out) override {
-    num* dA = dalloc<num>((size_t)M * K); num* dB = dalloc<num>((size_t)K * N_); num* dC = dalloc<num>((size_t)M * N_);
+    Scratch tmp; num* dA = talloc<num>(tmp, (size_t)M * K); num* dB = talloc<num>(tmp, (size_t)K * N_); num* dC = talloc<num>(tmp, (size_t)M * N_);
     nlaunch++, k_fill_random<NL><<<grid_for((int64_t)M * K), 256, 0, st>>>((int64_t)M * K, dA, 1234, 4);
     nlaunch++, k_fill_random<NL><<<grid_for((int64_t)K * N_), 256, 0, st>>>((int64_t)K * N_, dB, 99, 4);
     const int lay = path == 2 ? 1 : (path == 1 ? 0 : (use_tc(M, N_, K) ? 1 : 0));
@@ -1044,20 +1207,21 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaEventRecord(e2, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
     float t01 = 0, t12 = 0; cudaEventElapsedTime(&t01, e0, e1); cudaEventElapsedTime(&t12, e1, e2);
     out[0] = t01; out[1] = t12 / reps; out[2] = 0;
-    if (lay == 1) {      // kernel alone
-      CUtensorMap mA = make_map(sa, tc::BM); const int ntn = (N_ + 127) / 128; int BN = ((N_ + ntn - 1) / ntn + 15) & ~15; if (BN > 128) BN = 128; CUtensorMap mB = make_map(sb, BN);
-      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(((1 << 17) / NS / 128) * 128, sa.Kp); a.k0 = 0; a.BN = BN; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp; a.dbg = nullptr;
+    if (lay == 1) {      // the product kernel alone, one K range (no recombination)
+      int BN, group; pick_tiles(N_, BN, group);
+      CUtensorMap mA = make_map(sa, tc::BM), mB = make_map(sb, BN);
+      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(((1 << 17) / NS / 128) * 128, sa.Kp); a.k0 = 0; a.BN = BN; a.group = group; a.dsplit = 0; a.oraw = nullptr; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp; a.dbg = nullptr;
+      if ((size_t)M * a.Npitch > tc_cap) throw CudaError("bench_gemm: byte planes smaller than one product");
       dim3 grid((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1);
       CK(cudaEventRecord(e1, st));
-      const bool ts = getenv("CLRS_TC_TS") != nullptr; if (ts) { const int ntn2 = (N_ + 111) / 112; BN = ((N_ + ntn2 - 1) / ntn2 + 15) & ~15; if (BN > 112) BN = 112; mB = make_map(sb, BN); a.BN = BN; grid = dim3((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1); }
-      tc::ArgsTS pts; pts.g = a; pts.planesA = sa.planes; pts.nvecA = sa.nvec; pts.KpA = sa.Kp;
-      for (int r = 0; r < reps; r++) { if (ts) nlaunch++, tc::k_gemm_ts<<<grid, tc::TS_THREADS, tc::TS_SMEM_BYTES, st>>>(mB, pts); else nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a); }
+      for (int r = 0; r < reps; r++) nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
       CK(cudaEventRecord(e2, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
       cudaEventElapsedTime(&t12, e1, e2); out[2] = t12 / reps;
-      if (getenv("CLRS_TC_TIMELINE") && !ts) { long long* dd = dalloc<long long>(128); a.dbg = dd; tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a); long long hh[128]; CK(cudaMemcpyAsync(hh, dd, sizeof(hh), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-        fprintf(stderr, "group: wait_epi  mma_issue  | epilogue: wait_mma  work   (cycles, CTA 0)\n"); for (int gg = 0; gg < (NS + 3) / 4; gg++) { long long* q = hh + gg * 8; fprintf(stderr, "%2d: %8lld %8lld | %8lld %8lld   t0=%lld\n", gg, q[1] - q[0], q[2] - q[1], q[4] - q[3], q[5] - q[4], q[0] - hh[0]); } }
+      if (getenv("CLRS_TC_TIMELINE")) { long long* dd = talloc<long long>(tmp, 256); a.dbg = dd; tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a); long long hh[256]; CK(cudaMemcpyAsync(hh, dd, sizeof(hh), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        fprintf(stderr, "group: wait_epi  mma_issue  | epilogue: wait_mma  work   (cycles, CTA 0)\n"); for (int gg = 0; gg < (NS + group - 1) / group; gg++) { long long* q = hh + gg * 8; fprintf(stderr, "%2d: %8lld %8lld | %8lld %8lld   t0=%lld\n", gg, q[1] - q[0], q[2] - q[1], q[4] - q[3], q[5] - q[4], q[0] - hh[0]); } }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    CK(cudaStreamSynchronize(st));
     if (sa.sl) cudaFree(sa.sl); if (sa.E) cudaFree(sa.E); if (sa.planes) cudaFree(sa.planes); if (sb.sl) cudaFree(sb.sl); if (sb.E) cudaFree(sb.E); if (sb.planes) cudaFree(sb.planes);
     return 0;
   }
@@ -1120,6 +1284,7 @@ int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L) { GUARD(
 void clrs_profile(clrs_handle* h, int32_t enable) { h->s->profile(enable); }
 void clrs_profile_get(clrs_handle* h, double* out10) { h->s->profile_get(out10); }
 double clrs_last_iteration_ms(clrs_handle* h) { return h->s->last_iteration_ms(); }
+void clrs_use_graph(clrs_handle* h, int32_t enable) { h->s->use_graph(enable); }
 int clrs_bench_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, int32_t reps, int32_t path, double* out3) { GUARD(h, return h->s->bench_gemm(M, N, K, reps, path, out3);) }
 int64_t clrs_debug_get(clrs_handle* h, const char* what, int32_t j, int32_t l, void* out, int64_t cap) { try { return h->s->debug_get(what, j, l, out, cap); } catch (const std::exception& e) { h->err = e.what(); return -1; } }
 }

@@ -5,10 +5,12 @@
 // Operands are "tc panels": for every slice t an int8 matrix [nvec][Kp] (K-major,
 // Kp = K rounded up to 32), i.e. one 3-D tensor {Kp, nvec, NS} described to TMA.
 // An output tile is 128 (rows of the left panel) x BN (rows of the right panel).
-// The slice-pair sums D_s = sum_{t+u=s} A_t B_u^T are produced four diagonals at
-// a time, least significant first:
+// The slice-pair sums D_s = sum_{t+u=s} A_t B_u^T are produced `group` diagonals at
+// a time, least significant first (group = 4 with BN <= 128, or 3 with BN <= 160: both
+// fill the 512 TMEM columns; the wider tile makes the MMA tensor-bound instead of
+// shared-memory-bound and cuts N = 300 into 160 + 144 instead of 128 + 128 + 48):
 //
-//   group g = diagonals d0..d1 (d0 = 4g): four int32 accumulators of BN columns in
+//   group g = diagonals d0..d1 (d0 = group*g): `group` int32 accumulators of BN columns in
 //   TMEM.  For every 128-byte K chunk the slices stream through two shared-memory
 //   rings:  A_0..A_d1  and  B_d1..B_0 ; A_i meets the window B_{d0-i..d1-i}, so each
 //   operand chunk is loaded once per group and used by up to four MMAs.
@@ -21,6 +23,12 @@
 // sum_s D_s 256^(NS-1-s) in two's complement radix 256.  k_tc_recombine turns it
 // into multi-limb numbers (same i8_recombine as the CUDA-core path: the two paths
 // produce identical bits).
+//
+// Products with few output tiles (the n x n block products of the iteration: 6-9 tiles on
+// 148 SMs) run in "dsplit" mode: blockIdx.z enumerates (K chunk, diagonal group), every CTA
+// produces the raw int32 sums of ONE group over ONE K range and adds them into int32
+// planes with red.global.add (exact, order-independent); k_tc_recombine_raw resolves
+// the carries.  27 CTAs x 150 us become ~220 CTAs x 20 us.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -31,13 +39,13 @@ namespace tc {
 
 constexpr int BM = 128;            // rows per tile = TMEM lanes
 constexpr int KC = 128;            // bytes of K per ring slot (one 128B swizzle atom row)
-constexpr int SLOT_BYTES = BM * KC;   // 16 KiB
+constexpr int BNMAX = 160;         // widest column tile (3 accumulators x 160 columns = 480 of the 512 TMEM columns)
+constexpr int SLOT_BYTES = BM * KC;      // 16 KiB: one left-operand chunk
+constexpr int SLOTB_BYTES = BNMAX * KC;  // 20 KiB: one right-operand chunk
 constexpr int NA = 4, NB = 8;      // ring slots for left / right operand chunks (powers of two)
-constexpr int NSLOT = NA + NB;
-constexpr int GROUP = 4;           // diagonals resident in TMEM
 constexpr int NMMA = 4;            // MMA-issuing warps: warp 1+k owns window offset k (one accumulator per step)
 constexpr int NTHREADS = 288;      // warp 0: TMA, warps 1-4: MMA, warps 5-8: epilogue
-constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int SMEM_BYTES = NA * SLOT_BYTES + NB * SLOTB_BYTES + 1024 /*align*/ + 512 /*barriers*/;   // 230912 <= 232448
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
@@ -79,7 +87,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 struct Args {
   int M, N, Kp;            // Kp: padded K (multiple of 32) of this launch's K range
   int k0;                  // first K byte of the range (multiple of 128)
-  int BN;                  // tile width, multiple of 16, <= 128
+  int BN;                  // tile width, multiple of 16, <= 128 (group 4) or <= 160 (group 3)
+  int group;               // diagonals per group: 4 or 3
+  int dsplit;              // != 0: blockIdx.z = kz * ngroups + group index; raw int32 sums are added into oraw
+  int32_t* oraw;           // dsplit: [NS][M][Npitch] int32, zeroed by the caller
   int a_bvec, b_bvec;      // panel rows per batch step (0: shared)
   int NS;                  // slices
   int Npitch, batch;
@@ -97,7 +108,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   unsigned char* ring = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* ringA = ring;
   unsigned char* ringB = ring + NA * SLOT_BYTES;
-  uint64_t* full_a = (uint64_t*)(ring + NSLOT * SLOT_BYTES);
+  uint64_t* full_a = (uint64_t*)(ring + NA * SLOT_BYTES + NB * SLOTB_BYTES);
   uint64_t* full_b = full_a + NA;
   uint64_t* empty_a = full_b + NB;
   uint64_t* empty_b = empty_a + NA;
@@ -106,11 +117,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * a.BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
+  const int n0 = blockIdx.x * a.BN, m0 = blockIdx.y * BM;
   if (a.lower_only && n0 > m0 + BM - 1) return;
-  const int NS = a.NS, BN = a.BN;
+  const int NS = a.NS, BN = a.BN, GROUP = a.group;
   const int bn = min(BN, ((a.N - n0) + 15) & ~15);            // the last column tile may be narrower: MMAs and epilogue cover bn columns (TMA still fills BN rows, zeros beyond N)
   const int ngroups = (NS + GROUP - 1) / GROUP;
+  // dsplit: this CTA owns ONE diagonal group (the heaviest groups, i.e. the largest g, get the lowest blockIdx.z so they start first)
+  const int bz = a.dsplit ? (int)blockIdx.z / ngroups : (int)blockIdx.z;
+  const int g_hi = a.dsplit ? ngroups - 1 - (int)blockIdx.z % ngroups : ngroups - 1, g_lo = a.dsplit ? g_hi : 0;
   const int kbase = a.kz_stride > 0 ? a.k0 + bz * a.kz_stride : a.k0;
   const int Kp = a.kz_stride > 0 ? min(a.kz_stride, a.Kp_total - bz * a.kz_stride) : a.Kp;
   const int nkc = (Kp + KC - 1) / KC;
@@ -139,7 +153,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t ca = 0, cb = 0;                                  // running load counters of the two rings
       const int arow = brow_z * a.a_bvec + m0, brow = brow_z * a.b_bvec + n0;
       const uint32_t abytes = BM * KC, bbytes = (uint32_t)BN * KC;
-      for (int g = ngroups - 1; g >= 0; g--) {
+      for (int g = g_hi; g >= g_lo; g--) {
         const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
         for (int kc = 0; kc < nkc; kc++) {
           const int kcoord = kbase + kc * KC;
@@ -147,7 +161,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t slot = cb & (NB - 1);
             mbar_wait(&empty_b[slot], ((cb >> 3) & 1) ^ 1);
             mbar_expect_tx(&full_b[slot], bbytes);
-            tma_load_3d(ringB + slot * SLOT_BYTES, &tmB, &full_b[slot], kcoord, brow, slice);
+            tma_load_3d(ringB + slot * SLOTB_BYTES, &tmB, &full_b[slot], kcoord, brow, slice);
             cb++;
           };
           auto loadA = [&](int slice) {
@@ -176,9 +190,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const bool leader = (lane == 0);
     const bool dbgon = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 1;
     uint32_t ca = 0, cbase = 0; uint32_t epi_parity = 0;
-    for (int g = ngroups - 1; g >= 0; g--) {
+    for (int g = g_hi; g >= g_lo; g--) {
       const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
-      const bool carry_in = (g != ngroups - 1);
+      const bool carry_in = (g != g_hi);
       if (dbgon && leader) a.dbg[(ngroups - 1 - g) * 8 + 0] = clock64();
       if (carry_in) { mbar_wait(tmem_empty, epi_parity); epi_parity ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
       if (dbgon && leader) a.dbg[(ngroups - 1 - g) * 8 + 1] = clock64();
@@ -197,7 +211,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (active) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t dA = descA0 + (uint64_t)(slotA * (SLOT_BYTES >> 4));
-            const uint64_t dB = descB0 + (uint64_t)(((cbase + (uint32_t)sp) & (NB - 1)) * (SLOT_BYTES >> 4));
+            const uint64_t dB = descB0 + (uint64_t)(((cbase + (uint32_t)sp) & (NB - 1)) * (SLOTB_BYTES >> 4));
             const uint32_t acc0 = (kc == 0 && i == 0) ? ((carry_in && koff == 0) ? 1u : 0u) : 1u;   // koff == 0 is the least significant diagonal
             if (leader) {
               if (ninstr == 4) {
@@ -227,13 +241,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const size_t plane = (size_t)a.batch * a.M * a.Npitch;
     const size_t rowoff = ((size_t)bz * a.M + m) * a.Npitch;
     uint32_t full_parity = 0;
-    for (int g = ngroups - 1; g >= 0; g--) {
+    for (int g = g_hi; g >= g_lo; g--) {
       const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
       const bool dbge = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 160;
       if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 3] = clock64();
       mbar_wait(tmem_full, full_parity); full_parity ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 4] = clock64();
+      if (a.dsplit) {
+        // raw sums of this group and K range: added into the int32 planes (exact, so the order of the CTAs does not matter)
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+          const bool store_ok = (m < a.M) && (n0 + c0 < a.Npitch);
+          for (int acc = w; acc >= 0; acc--) {
+            uint32_t v[16];
+            tmem_ld16(tlane + (uint32_t)(acc * BN + c0), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (store_ok) {
+              int32_t* dst = a.oraw + ((size_t)(d0 + acc) * a.M + m) * a.Npitch + n0 + c0;
+#pragma unroll
+              for (int q = 0; q < 16; q++) if ((int32_t)v[q] != 0) atomicAdd(dst + q, (int32_t)v[q]);
+            }
+          }
+        }
+        continue;
+      }
       for (int c0 = 0; c0 < bn; c0 += 16) {
         int32_t carry[16];
 #pragma unroll
@@ -276,224 +307,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-
-// ---------------------------------------------------------------------------
-// TS variant: the left operand chunk lives in TMEM, the right one in shared memory.
-// With both operands in shared memory an M=128, N<=128 int8 MMA needs more operand
-// bytes per cycle than the 128 B/clk a SM's shared memory delivers (profiles/: the MMA
-// phases of k_gemm_tc run at ~40 % of the tensor pipe).  Here four "feeder" warps
-// copy the 128-byte row chunk of A_i from global memory into a TMEM buffer
-// (tcgen05.st, one TMEM lane = one row), so shared memory only serves the right
-// operand.  TMEM: 4 accumulators x BN (BN <= 112) columns + 2 A buffers x 32 columns.
-// ---------------------------------------------------------------------------
-constexpr int TS_NB = 8;                                   // B ring slots
-constexpr int TS_THREADS = 416;                            // warp 0 TMA(B), 1-4 MMA, 5-8 A feeders, 9-12 epilogue
-constexpr int TS_SMEM_BYTES = TS_NB * SLOT_BYTES + 1024 + 512;
-constexpr int TS_ACOL = 448;                               // first TMEM column of the A buffers
-
-__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-               ::"r"(tmem_c), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-               "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
-                 "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
-                 "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
-}
-
-struct ArgsTS {
-  Args g;                  // shapes / outputs as for k_gemm_tc
-  const uint8_t* planesA;  // [NS][nvecA][KpA]
-  int nvecA, KpA;
-};
-
-__global__ void __launch_bounds__(TS_THREADS, 1)
-k_gemm_ts(const __grid_constant__ CUtensorMap tmB, const ArgsTS p) {
-  const Args& a = p.g;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* ringB = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_b = (uint64_t*)(ringB + TS_NB * SLOT_BYTES);
-  uint64_t* empty_b = full_b + TS_NB;
-  uint64_t* a_full = empty_b + TS_NB;
-  uint64_t* a_empty = a_full + 2;
-  uint64_t* tmem_full = a_empty + 2;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * a.BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
-  if (a.lower_only && n0 > m0 + BM - 1) return;
-  const int NS = a.NS, BN = a.BN;
-  const int ngroups = (NS + GROUP - 1) / GROUP;
-  const int kbase = a.kz_stride > 0 ? a.k0 + bz * a.kz_stride : a.k0;
-  const int Kp = a.kz_stride > 0 ? min(a.kz_stride, a.Kp_total - bz * a.kz_stride) : a.Kp;
-  const int nkc = (Kp + KC - 1) / KC;
-  const int brow_z = a.kz_stride > 0 ? 0 : bz;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TS_NB; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], NMMA); }
-    for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], NMMA); }
-    mbar_init(tmem_full, NMMA); mbar_init(tmem_empty, 128);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer (right operand) =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
-      uint32_t cb = 0; const int brow = brow_z * a.b_bvec + n0; const uint32_t bbytes = (uint32_t)BN * KC;
-      for (int g = ngroups - 1; g >= 0; g--) {
-        const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1);
-        for (int kc = 0; kc < nkc; kc++) for (int sp = 0; sp <= d1; sp++) {
-          const uint32_t slot = cb & (TS_NB - 1);
-          mbar_wait(&empty_b[slot], ((cb >> 3) & 1) ^ 1);
-          mbar_expect_tx(&full_b[slot], bbytes);
-          tma_load_3d(ringB + slot * SLOT_BYTES, &tmB, &full_b[slot], kbase + kc * KC, brow, d1 - sp);
-          cb++;
-        }
-        (void)d0;
-      }
-    }
-  } else if (warp <= NMMA) {
-    // ===================== MMA issuers (warp 1+k owns window offset k, see k_gemm_tc) =====================
-    const int koff = warp - 1;
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint64_t descB0 = make_desc(smem_u32(ringB));
-    const bool leader = (lane == 0);
-    uint32_t ca = 0, cbase = 0, epi_parity = 0;
-    for (int g = ngroups - 1; g >= 0; g--) {
-      const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
-      const bool carry_in = (g != ngroups - 1);
-      if (carry_in) { mbar_wait(tmem_empty, epi_parity); epi_parity ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-      const uint32_t tcol = tmem_base + (uint32_t)((w - koff) * BN);
-      for (int kc = 0; kc < nkc; kc++) {
-        const int ninstr = min(KC / 32, (Kp - kc * KC) / 32);
-        uint32_t cbw = cbase;
-        for (int i = 0; i <= d1; i++) {
-          const int sp = i + koff;
-          const bool active = koff <= w && sp <= d1;
-          const uint32_t buf = ca & 1;
-          mbar_wait(&a_full[buf], (ca >> 1) & 1);                        // all warps, every step (keeps them in phase)
-          if (active) {
-            while (cbw <= cbase + (uint32_t)sp) { mbar_wait(&full_b[cbw & (TS_NB - 1)], (cbw >> 3) & 1); cbw++; }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ta = tmem_base + (uint32_t)(TS_ACOL + buf * 32);
-            const uint64_t dB = descB0 + (uint64_t)(((cbase + (uint32_t)sp) & (TS_NB - 1)) * (SLOT_BYTES >> 4));
-            const uint32_t acc0 = (kc == 0 && i == 0) ? ((carry_in && koff == 0) ? 1u : 0u) : 1u;
-            if (leader) {
-              if (ninstr == 4) {
-                umma_i8_ts(tcol, ta, dB, idesc, acc0); umma_i8_ts(tcol, ta + 8, dB + 2, idesc, 1u);
-                umma_i8_ts(tcol, ta + 16, dB + 4, idesc, 1u); umma_i8_ts(tcol, ta + 24, dB + 6, idesc, 1u);
-              } else {
-                for (int kk = 0; kk < ninstr; kk++) umma_i8_ts(tcol, ta + (uint32_t)(8 * kk), dB + (uint64_t)(2 * kk), idesc, kk == 0 ? acc0 : 1u);
-              }
-            }
-          }
-          if (leader) { umma_commit(&a_empty[buf]); umma_commit(&empty_b[(cbase + (uint32_t)i) & (TS_NB - 1)]); }
-          __syncwarp();
-          ca++;
-        }
-        cbase += (uint32_t)(d1 + 1);
-      }
-      if (leader) umma_commit(tmem_full);
-      __syncwarp();
-    }
-  } else if (warp < 9) {
-    // ===================== A feeders: global -> registers -> TMEM, one row per thread =====================
-    const int quad = warp & 3, row = quad * 32 + lane;
-    const int arow = brow_z * a.a_bvec + m0 + row;
-    const bool row_ok = (m0 + row) < a.M && arow < p.nvecA;
-    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)TS_ACOL;
-    uint32_t ca = 0;
-    for (int g = ngroups - 1; g >= 0; g--) {
-      const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1); (void)d0;
-      for (int kc = 0; kc < nkc; kc++) {
-        const int kcoord = kbase + kc * KC;
-        const int nv16 = min(8, (p.KpA - kcoord) / 16);                    // 16-byte pieces of this chunk that exist in the row
-        for (int i = 0; i <= d1; i++) {
-          uint32_t v[32];
-          const uint4* src = (const uint4*)(p.planesA + ((size_t)i * p.nvecA + (row_ok ? arow : 0)) * p.KpA + kcoord);
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            uint4 t = make_uint4(0, 0, 0, 0);
-            if (row_ok && q < nv16) t = __ldg(src + q);
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-          }
-          const uint32_t buf = ca & 1;
-          mbar_wait(&a_empty[buf], ((ca >> 1) & 1) ^ 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          tmem_st32(tlane + buf * 32, v);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&a_full[buf]);
-          ca++;
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue: 4 warps, one output row per thread =====================
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int m = m0 + row;
-    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const size_t plane = (size_t)a.batch * a.M * a.Npitch;
-    const size_t rowoff = ((size_t)bz * a.M + m) * a.Npitch;
-    uint32_t full_parity = 0;
-    for (int g = ngroups - 1; g >= 0; g--) {
-      const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
-      mbar_wait(tmem_full, full_parity); full_parity ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        int32_t carry[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) carry[q] = 0;
-        const bool store_ok = (m < a.M) && (n0 + c0 < a.Npitch);
-        for (int acc = w; acc >= 0; acc--) {
-          uint32_t v[16];
-          tmem_ld16(tlane + (uint32_t)(acc * BN + c0), v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          uint32_t packed[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int q = 0; q < 16; q++) {
-            const int32_t t = (int32_t)v[q] + carry[q];
-            packed[q >> 2] |= (uint32_t)(t & 255) << (8 * (q & 3));
-            carry[q] = t >> 8;
-          }
-          if (store_ok) *(uint4*)(a.obytes + (size_t)(d0 + acc) * plane + rowoff + n0 + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        }
-        if (g > 0) {
-          uint32_t cv[16];
-#pragma unroll
-          for (int q = 0; q < 16; q++) cv[q] = (uint32_t)carry[q];
-          tmem_st16(tlane + (uint32_t)((GROUP - 1) * BN + c0), cv);
-        } else if (store_ok) {
-          int4* dst = (int4*)(a.otop + rowoff + n0 + c0);
-          dst[0] = make_int4(carry[0], carry[1], carry[2], carry[3]); dst[1] = make_int4(carry[4], carry[5], carry[6], carry[7]);
-          dst[2] = make_int4(carry[8], carry[9], carry[10], carry[11]); dst[3] = make_int4(carry[12], carry[13], carry[14], carry[15]);
-        }
-      }
-      if (g > 0) {
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(tmem_empty);
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-}
 
 }  // namespace tc
 
@@ -592,4 +405,31 @@ template <int NL> __global__ void k_tc_recombine(int M, int N, int Npitch, int b
   if (mode == 1 || mode == 2) { mpn<NL> d = D[(int64_t)bz * d_bs + (int64_t)cr * ldd + cc]; if (mode == 1) mp_sub(r, d, r); else mp_add(r, d, r); }
   else if (mode == 3) r.sign = -r.sign;
   C[(int64_t)bz * c_bs + (int64_t)cr * ldc + cc] = r;
+}
+
+// dsplit products: raw int32 slice-pair sums [NS][M][Npitch] (all K ranges and diagonal groups already added by the
+// product kernel) -> carry-normalised digits -> multi-limb C (op with D); one thread per output, plane reads coalesce along n
+template <int NL> __global__ void k_tc_recombine_raw(int M, int N, int Npitch, const int32_t* oraw, const int32_t* EA, const int32_t* EB,
+                                                     mpn<NL>* C, int ldc, const mpn<NL>* D, int ldd, int mode, int lower_only, int trans) {
+  constexpr int NS = I8Cfg<NL>::NS;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * N) return;
+  const int n = (int)(idx % N), m = (int)(idx / N);
+  if (lower_only && n > m) return;
+  const size_t plane = (size_t)M * Npitch, off = (size_t)m * Npitch + n;
+  const int32_t ea = EA[m], eb = EB[n];
+  mpn<NL> r;
+  if (ea == I8_EXP_NONE || eb == I8_EXP_NONE) mp_zero(r);
+  else {
+    uint32_t dg[NS]; int64_t carry = 0;
+#pragma unroll
+    for (int s = NS - 1; s >= 1; s--) { const int64_t t = (int64_t)oraw[(size_t)s * plane + off] + carry; dg[s] = (uint32_t)(t & 255); carry = t >> 8; }
+    dg[0] = 0;
+    const int64_t top = (int64_t)oraw[off] + carry;
+    i8_recombine<NL>(r, top, dg, ea + eb);
+  }
+  const int cr = trans ? n : m, cc = trans ? m : n;
+  if (mode == 1 || mode == 2) { mpn<NL> d = D[(int64_t)cr * ldd + cc]; if (mode == 1) mp_sub(r, d, r); else mp_add(r, d, r); }
+  else if (mode == 3) r.sign = -r.sign;
+  C[(int64_t)cr * ldc + cc] = r;
 }

@@ -5,6 +5,7 @@
 #include <vector>
 #include "wire_host.h"
 #include "i8split.cuh"
+#include "lanes.cuh"
 typedef mpn<8> N8;
 static const size_t WS = 16 + 32;
 extern "C" {
@@ -23,6 +24,12 @@ int hc_wire_convert(int W, const void* in, int W2, void* out) { N8 x; wire_to_mp
 double hc_to_double(const void* a) { N8 x; wire_to_mpn(x, a); return mp_to_double(x); }
 void hc_from_double(double d, void* r) { N8 x; mp_from_double(x, d); mpn_to_wire(r, x); }
 int hc_cmp(const void* a, const void* b) { N8 x, y; wire_to_mpn(x, a); wire_to_mpn(y, b); return mp_cmp(x, y); }
+// the three local steps of the cross-rank sum (lanes.cuh); the reductions between them are the caller's (gloo in the CPU tests)
+void hc_lane_exp(int n, const void* v, int32_t* E) { for (int i = 0; i < n; i++) { N8 x; wire_to_mpn(x, (const char*)v + i * WS); E[i] = mp_lane_exp(x); } }
+void hc_to_lanes(int n, const void* v, const int32_t* E, long long* lanes) {       // lanes[i][9]
+  for (int i = 0; i < n; i++) { N8 x; wire_to_mpn(x, (const char*)v + i * WS); long long t[9]; mp_to_lanes<8>(x, E[i], t); for (int k = 0; k < 9; k++) lanes[(size_t)i * 9 + k] = t[k]; } }
+void hc_from_lanes(int n, const long long* lanes, const int32_t* E, void* out) {
+  for (int i = 0; i < n; i++) { long long t[9]; for (int k = 0; k < 9; k++) t[k] = lanes[(size_t)i * 9 + k]; N8 r; mp_from_lanes<8>(r, t, E[i]); mpn_to_wire((char*)out + i * WS, r); } }
 // C = A*B through split -> exact integer slice-pair sums -> recombine (what the int8 GEMM kernels compute)
 int hc_gemm(int M, int N, int K, const void* A, const void* B, void* C) {
   constexpr int NS = I8Cfg<8>::NS;

@@ -5,6 +5,7 @@ oracle and the device library can be fed identical inputs without Julia:
 
   maxcut          README.md:39-65           (config 2, dense constraint path)
   polyopt         examples/PolyOpt.jl:7-30  (config 1)
+  min_f           examples/PolyOpt.jl:32-87 (the reference's documented solver log)
   delsarte        examples/Delsarte.jl:7-49 (config 3)
   sphere_packing  examples/SpherePacking.jl:13-115 (config 5)
 
@@ -91,16 +92,18 @@ def sample_points_rescaled_laguerre(d):
 
 
 def approximatefekete(V, samples, s=3):
-    """Orthogonalise the basis w.r.t. the samples (src/approximate_fekete.jl:6-22,51-80).
+    """Orthogonalise the basis w.r.t. the samples and keep a unisolvent subset of them
+    (src/approximate_fekete.jl:6-22,51-80, the default :Arb variant).
 
-    V[i][k] = basis_k(sample_i).  QR in Float64, basis change in high precision.
-    With as many samples as basis functions every point is kept; rows are
+    V[i][k] = basis_k(sample_i), with at least as many samples as basis functions.  s rounds of
+    "QR in Float64, basis change in high precision" on all samples, a column-pivoted QR of V^T to pick
+    as many samples as there are basis functions, one more basis change on the chosen rows; rows are
     returned sorted by sample.  Returns (V', samples').
     """
     V = mpmath.matrix(V)
     n = V.cols
-    assert V.rows == n, "only the square (univariate) case is needed for the configs"
-    for _ in range(s + 1):
+
+    def basis_change(V):
         F = np.array([[float(V[i, j]) for j in range(n)] for i in range(V.rows)])
         R = np.linalg.qr(F, mode="r")
         U = np.linalg.solve(R, np.eye(n))
@@ -108,7 +111,20 @@ def approximatefekete(V, samples, s=3):
         for i in range(n):
             for j in range(i, n):
                 Um[i, j] = mpf(float(U[i, j]))
-        V = V * Um
+        return V * Um
+
+    for _ in range(s):
+        V = basis_change(V)
+    if V.rows > n:                                  # F2 = qr(Float64.(V'), ColumnNorm()); point_indices = F2.p[1:n]
+        import scipy.linalg
+        F = np.array([[float(V[i, j]) for j in range(n)] for i in range(V.rows)])
+        piv = scipy.linalg.qr(F.T, mode="r", pivoting=True)[1][:n]
+        Vs = mpmath.matrix(n, n)
+        for ii, i in enumerate(piv):
+            for j in range(n):
+                Vs[ii, j] = V[int(i), j]
+        V, samples = Vs, [samples[int(i)] for i in piv]
+    V = basis_change(V)
     order = sorted(range(len(samples)), key=lambda i: samples[i])
     Vs = mpmath.matrix(V.rows, n)
     for ii, i in enumerate(order):
@@ -254,6 +270,50 @@ def polyopt_random(d=20, seed=0, prec=256):
         return mpmath.fsum(mpf(cf) * t for cf, t in zip(coef, T))
 
     return polyopt(f, d, prec, name=f"polyopt_random(d={d},seed={seed})")
+
+
+def min_f(d=2, prec=256):
+    """The S_3-invariant trivariate example of the reference, `min_f(d)` (examples/PolyOpt.jl:32-87):
+    maximize M s.t. x^4 + y^4 + z^4 - 4xyz + x + y + z - M is a sum of squares written in the invariant ring
+    (one block per irreducible representation with low degree enough equivariants).  The reference prints its
+    solver log for d = 2 in docs/src/solving.md:38-52 (56 iterations, objective -2.1129138814236...), which
+    tests/test_oracle_pins.py uses to pin the oracle's TRAJECTORY, not only its optimum.
+    d = 2: one cluster, P = 11 samples, blocks of size 4 (rank 1) and 3 (rank 2), one free variable."""
+    with mpmath.workprec(prec + 64):
+        # invariant basis e1^(deg-2i-3j) e2^i e3^j, deg = 0..2d  (examples/PolyOpt.jl:33-36)
+        expo = [(deg - 2 * i - 3 * j, i, j, deg) for deg in range(2 * d + 1) for j in range(deg // 3 + 1) for i in range((deg - 3 * j) // 2 + 1)]
+        degrees = [e[3] for e in expo]
+        cheb = [sample_points_chebyshev(2 * d + k) for k in range(3)]
+        grid = [(cheb[0][i], cheb[1][j], cheb[2][k]) for i in range(2 * d + 1) for j in range(2 * d + 2) for k in range(2 * d + 3)]
+
+        def inv_basis(pt):
+            x, y, z = pt
+            e1, e2, e3 = x + y + z, x * y + y * z + z * x, x * y * z
+            return [e1 ** a * e2 ** b * e3 ** c for (a, b, c, _) in expo]
+        V, samples = approximatefekete([inv_basis(pt) for pt in grid], grid)
+        P = len(samples)
+        # equivariants per irreducible representation of S_3, with their degrees (examples/PolyOpt.jl:61-63)
+        equivariants = [[[(lambda x, y, z: mpf(1), 0)]],
+                        [[(lambda x, y, z: (x - y) * (y - z) * (z - x), 3)]],
+                        [[(lambda x, y, z: 2 * x - y - z, 1), (lambda x, y, z: 2 * y * z - x * z - x * y, 2)],
+                         [(lambda x, y, z: y - z, 1), (lambda x, y, z: x * z - x * y, 2)]]]
+        factors = [[1], [1], [Fraction(1, 2), Fraction(3, 2)]]
+        blocks = []
+        for eqi, rows in enumerate(equivariants):
+            sel = [[(eq, k) for (eq, edeg) in row for k, qdeg in enumerate(degrees) if 2 * edeg + 2 * qdeg <= 2 * d] for row in rows]
+            sel = [v for v in sel if v]
+            if not sel:
+                continue
+            n = len(sel[0])
+            blk = PSDBlock(m=1, delta=n, high_rank=False, C=wire.wire_zeros((n, n), prec), name=("trivariatesos", eqi + 1))
+            lam = [mpf(f.numerator) / f.denominator if isinstance(f, Fraction) else mpf(f) for f in factors[eqi]]
+            for p, pt in enumerate(samples):
+                vecs = [[eq(*pt) * V[p, k] for (eq, k) in row] for row in sel]
+                blk.lowrank.append(LowRankTerm(0, 0, p, _w(lam[:len(vecs)], prec), _w(vecs, prec), _w(vecs, prec)))
+            blocks.append(blk)
+        f = lambda x, y, z: x ** 4 + y ** 4 + z ** 4 - 4 * x * y * z + x + y + z
+        cl = Cluster(B=_w([[1]] * P, prec), c=_w([f(*pt) for pt in samples], prec), blocks=blocks)
+        return ClusteredSDP(prec=prec, maximize=True, constant=_w(0, prec), b=_w([1], prec), clusters=[cl], name=f"min_f(d={d})")
 
 
 # ---------------------------------------------------------------------------

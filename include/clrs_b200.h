@@ -219,8 +219,13 @@ void clrs_profile_get(clrs_handle* h, double* out10);
 /* Kernel benchmark of C = A*B (M x K times K x N) on device-generated operands.
  * out3 = { split ms, ms per product (kernel + recombine), ms per tcgen05 kernel launch alone }. */
 int clrs_bench_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, int32_t reps, int32_t path, double* out3);
-/* device time of the last clrs_iterate (CUDA events on the library's stream), ms */
+/* device time of the last clrs_iterate (CUDA events on the library's stream), ms; 0 when the call did not run an iteration
+ * (loop-top terminate fired, or a factorisation failed) */
 double clrs_last_iteration_ms(clrs_handle* h);
+/* From its second iteration on a handle replays the iteration as a CUDA graph (the loop body is pure stream work: all
+ * scalar decisions are taken on the device).  enable = 0 returns to eager launches (parity tests; the environment
+ * variable CLRS_GRAPH=0 does the same for every handle).  Default: enabled. */
+void clrs_use_graph(clrs_handle* h, int32_t enable);
 
 #ifdef __cplusplus
 }

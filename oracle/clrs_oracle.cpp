@@ -19,6 +19,7 @@
 // (Arb's approx_* kernels are floating point at prec bits with unspecified
 // last-bit rounding).  MPFR headers are not installed;
 // the few prototypes used are declared by hand against libmpfr.so.6 (4.2.1).
+#include <omp.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -707,6 +708,9 @@ int clrs_oracle_get_objectives(Oracle* h, void* d_obj, void* p_obj, void* gap) {
   h->dual_objective(h->d_obj.p()); h->primal_objective(h->p_obj.p()); h->duality_gap(h->gap.p(), h->d_obj.p(), h->p_obj.p());
   to_wire(d_obj, h->d_obj.p()); to_wire(p_obj, h->p_obj.p()); to_wire(gap, h->gap.p()); return 0;
 }
+// OpenMP threads of the oracle's loops (torchrun exports OMP_NUM_THREADS=1: bench.py sets the count explicitly and reports it)
+void clrs_oracle_set_threads(int32_t n) { if (n > 0) omp_set_num_threads(n); }
+int32_t clrs_oracle_get_threads() { return (int32_t)omp_get_max_threads(); }
 void clrs_oracle_set_dense_p_limit(Oracle* h, int32_t lim) { h->dense_p_limit = lim; }
 void clrs_oracle_set_dense_skip_zeros(Oracle* h, int32_t on) { h->dense_skip_zeros = on != 0; }
 void clrs_oracle_set_sample_limit(Oracle* h, int32_t lim) { h->sample_limit = lim; h->t_plain = h->t_skip = 0; }

@@ -199,9 +199,12 @@ def test_gemm_tcgen05_bitexact_vs_host_arithmetic(tiny, M, N, K):
     assert Cd.tobytes() == Ch.tobytes()
 
 
-@pytest.mark.parametrize("M,N,K,spread", [(19200, 112, 100, 5), (1, 1, 1, 0), (129, 17, 33, 3), (200, 64, 224, 10)])
+@pytest.mark.parametrize("M,N,K,spread", [(19200, 112, 100, 5), (1, 1, 1, 0), (129, 17, 33, 3), (200, 64, 224, 10),
+                                          (19200, 300, 100, 5),      # 160 + 144 column tiles, three diagonals per group
+                                          (300, 300, 300, 5), (130, 290, 140, 30), (257, 160, 128, 3), (128, 128, 3500, 8)])   # few tiles: one CTA per (tile, K range, diagonal group), raw sums added exactly
 def test_gemm_tcgen05_equals_cuda_core_path(tiny, M, N, K, spread):
-    """Both GEMM paths compute the same exact integer slice-pair sums: identical bits (shapes that are not split along K)."""
+    """Both GEMM paths compute the same exact integer slice-pair sums: identical bits (shapes whose K ranges are combined
+    exactly: one K range per tile, or the raw-sum mode of products with few tiles)."""
     A = rand_wire(1, (M, K), spread); B = rand_wire(2, (K, N), spread)
     C1, _ = tiny.mp_gemm(A, B, path=1)
     C2, _ = tiny.mp_gemm(A, B, path=2)
@@ -408,8 +411,45 @@ def test_indefinite_iterate_raises_the_same_solver_failure_as_the_oracle():
         with pytest.raises(clrs_b200.SolverFailure) as e:
             s.iterate()
         msgs.append(str(e.value))
+        # the reference throws before the step (src/solver.jl:394-398) and hands back the last good iterate (:594-628):
+        # the state after the failed call is the state that was set, bit for bit
+        x2, X2, y2, Y2 = s.get_state()
+        assert X2.tobytes() == X.tobytes() and Y2.tobytes() == Y.tobytes() and x2.tobytes() == x.tobytes() and y2.tobytes() == y.tobytes(), lib
         s.close()
     assert msgs[0][:4] == msgs[1][:4] and msgs[0].startswith("[1"), msgs      # same failure site code
+
+
+def test_failed_schur_factorisation_takes_no_step():
+    """A Cholesky failure later in the iteration (of S or Q: sphere packing (4,31) cannot be solved at 256 bit, the oracle
+    stops with "Q was not decomposed correctly" too) must not apply the step built from the broken factor: the iterate
+    stays the one before the call."""
+    sdp = workloads.sphere_packing(8, 31, [Fraction(1, 2), Fraction(1, 2), Fraction(3, 4), Fraction(1)], prec=256)
+    s = Solver(sdp, lib="device")
+    before = None
+    with pytest.raises(clrs_b200.SolverFailure):
+        for _ in range(200):
+            before = s.get_state()
+            s.iterate()
+    after = s.get_state()
+    for a, b in zip(before, after):
+        assert a.tobytes() == b.tobytes()
+    s.close()
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager_launches():
+    """From its second iteration on a handle replays the iteration as a CUDA graph; the numbers must not depend on it."""
+    for make in (lambda: workloads.sphere_packing(8, 5, [Fraction(1, 2), Fraction(1, 2)]), lambda: workloads.maxcut(workloads.laplacian_cycle(7)),
+                 lambda: workloads.maxcut(workloads.laplacian_complete(130))):
+        sdp = make()
+        a = Solver(sdp, lib="device"); b = Solver(sdp, lib="device"); b.use_graph(False)
+        for _ in range(7):
+            ia, ib = a.iterate(), b.iterate()
+            assert ia.stop == ib.stop == 0
+            assert ia.p_obj_new == ib.p_obj_new and ia.d_obj_new == ib.d_obj_new and ia.alpha_p == ib.alpha_p and ia.alpha_d == ib.alpha_d and ia.mu == ib.mu
+        for u, v in zip(a.get_state(), b.get_state()):
+            assert u.tobytes() == v.tobytes()
+        assert all(t >= 0 for t in ia.phase_ms) and sum(ia.phase_ms[12:17]) > 0          # the phase timers survive the replay
+        a.close(); b.close()
 
 
 def test_warm_start_continues_identically_on_the_device():
@@ -458,3 +498,21 @@ def test_lovasz_theta_cycles_on_device():
         n = 41
         dev = solvesdp(workloads.lovasz_theta_cycle(n), lib="device", duality_gap_threshold=1e-30)
         assert dev.status == "Optimal" and abs(dev.p_obj - n * mpmath.cos(mpmath.pi / n) / (1 + mpmath.cos(mpmath.pi / n))) < mpmath.mpf(10) ** -24
+
+
+@pytest.mark.gpu
+def test_device_reproduces_the_reference_solver_log_of_min_f_2():
+    """The same comparison as tests/test_oracle_pins.py, on the device: 56 iterations, the printed rows 1-3 and 55-56 of
+    docs/src/solving.md:38-52 and the reference's final objectives."""
+    from test_oracle_pins import check_against_reference_log
+    r = solvesdp(workloads.min_f(2), lib="device")
+    check_against_reference_log(r)
+
+
+@pytest.mark.gpu
+def test_two_radii_sphere_packing_d15_prec300_reference_test_on_device():
+    """test/runtests_solver.jl:21-22 on the device (10 limbs): pi^4/384 to 1e-4."""
+    r = solvesdp(workloads.sphere_packing(8, 15, [Fraction(1, 2), Fraction(1, 2)], prec=300), lib="device")
+    with mpmath.workprec(200):
+        assert r.status == "Optimal" and 0 < r.p_obj - mpmath.pi ** 4 / 384 < mpmath.mpf(10) ** -4
+        assert abs(r.p_obj - mpmath.pi ** 4 / 384 - mpmath.mpf("7.0919e-5")) < mpmath.mpf(10) ** -8
