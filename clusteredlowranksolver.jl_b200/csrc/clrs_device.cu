@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <unordered_map>
 #include <tuple>
 #include <algorithm>
 #include <stdexcept>
@@ -32,14 +33,14 @@ struct NcclUid { char b[128]; };
 struct NcclApi {
   void* lib = nullptr;
   int (*GetUniqueId)(void*) = nullptr; int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
-  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr; int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr; int (*CommDestroy)(void*) = nullptr; const char* (*GetErrorString)(int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr; int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr; int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr; int (*CommDestroy)(void*) = nullptr; const char* (*GetErrorString)(int) = nullptr;
   bool load(std::string& err) {
     if (lib) return true;
     for (const char* n : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
     if (!lib) { err = "libnccl.so.2 not found"; return false; }
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId"); CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
-    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather"); AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce"); CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy"); GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !AllGather || !AllReduce || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather"); AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce"); Broadcast = (decltype(Broadcast))dlsym(lib, "ncclBroadcast"); CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy"); GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllGather || !AllReduce || !Broadcast || !CommDestroy) { err = "NCCL symbols missing"; return false; }
     return true;
   }
 };
@@ -63,6 +64,23 @@ enum { INFO_MU, INFO_DOBJ, INFO_POBJ, INFO_GAP, INFO_ERRP, INFO_ERRp, INFO_ERRd,
 
 struct ScalarCfg { int correctoronly, safe_step, maximize; };
 
+// out-of-line arithmetic for the one-thread scalar kernel: inlined, its ~20 k straight-line instructions (306 KB at 8 limbs)
+// are fetched from L2 on every launch (20 us per launch, nine launches per iteration); as calls the code is a few KB
+template <int NL> __device__ __noinline__ void mpc_mul(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>& b) { mpn<NL> t; mp_mul(t, a, b); r = t; }
+template <int NL> __device__ __noinline__ void mpc_add(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>& b) { mpn<NL> t; mp_add(t, a, b); r = t; }
+template <int NL> __device__ __noinline__ void mpc_sub(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>& b) { mpn<NL> t; mp_sub(t, a, b); r = t; }
+// mp_div (mpf.cuh: Newton reciprocal from a double-double seed, one correction step on the quotient) with its
+// multiplications out of line: same operations, same bits
+template <int NL> __device__ __noinline__ void mpc_div(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>& b) {
+  if (b.sign == 0) { mp_zero(r); return; }
+  mpn<NL> m = b; m.exp = 0; m.sign = 1;
+  double mh, ml, x0, c; mp_mant_dd(b.l[NL - 1], b.l[NL - 2], b.l[NL - 3], 0, mh, ml); dd_recip_seed(mh, ml, x0, c);
+  mpn<NL> x, t, q, two; mp_from_double(x, x0); mp_from_double(t, c); mpc_add<NL>(x, x, t); mp_set_i32(two, 2);
+#pragma unroll 1
+  for (int it = 0; it < mp_newton_steps<NL>(); it++) { mpc_mul<NL>(t, m, x); mpc_sub<NL>(t, two, t); mpc_mul<NL>(x, x, t); }
+  x.exp -= b.exp; x.sign = b.sign;
+  mpc_mul<NL>(q, a, x); mpc_mul<NL>(t, q, b); mpc_sub<NL>(t, a, t); mpc_mul<NL>(t, t, x); mpc_add<NL>(r, q, t);
+}
 // the scalar logic of the loop body, one thread
 template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, double* info, ScalarCfg cfg,
                                            int nblocks, const int32_t* bn, const int64_t* boff, const mpn<NL>* M, const mpn<NL>* dM,
@@ -70,20 +88,20 @@ template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, doub
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   typedef mpn<NL> num;
   if (phase == 0) {            // mu, mu_p  (src/solver.jl:369-380)
-    num mu; mp_div(mu, sc[SC_D0], sc[SC_K]); sc[SC_MU] = mu;
+    num mu; mpc_div<NL>(mu, sc[SC_D0], sc[SC_K]); sc[SC_MU] = mu;
     num mup; mp_zero(mup);
-    if (cfg.correctoronly) mup = mu; else if (!fl[FL_PDFEAS]) mp_mul(mup, sc[SC_BETA_INF], mu);
+    if (cfg.correctoronly) mup = mu; else if (!fl[FL_PDFEAS]) mpc_mul<NL>(mup, sc[SC_BETA_INF], mu);
     sc[SC_MUP] = mup;
     info[INFO_MU] = mp_to_double(mu);
     if (mp_cmp(mu, sc[SC_MAXGAP]) > 0) fl[FL_STOP] = CLRS_STOP_MAX_COMPLEMENTARY_GAP;
   } else if (phase == 1) {     // beta, beta_c, mu_c with the STALE pd_feas, then the fresh errors/pd_feas (src/solver.jl:429-447)
     num s, t, r, beta, betac;
-    mp_add(s, sc[SC_D0], sc[SC_D1]); mp_add(s, s, sc[SC_D2]); mp_add(s, s, sc[SC_D3]);
-    mp_mul(t, sc[SC_MU], sc[SC_K]); mp_div(r, s, t);
-    if (mp_cmp(r, sc[SC_ONE]) < 0) mp_mul(beta, r, r); else beta = r;
+    mpc_add<NL>(s, sc[SC_D0], sc[SC_D1]); mpc_add<NL>(s, s, sc[SC_D2]); mpc_add<NL>(s, s, sc[SC_D3]);
+    mpc_mul<NL>(t, sc[SC_MU], sc[SC_K]); mpc_div<NL>(r, s, t);
+    if (mp_cmp(r, sc[SC_ONE]) < 0) mpc_mul<NL>(beta, r, r); else beta = r;
     if (fl[FL_PDFEAS]) { betac = mp_cmp(sc[SC_BETA_FEAS], beta) > 0 ? sc[SC_BETA_FEAS] : beta; if (mp_cmp(betac, sc[SC_ONE]) > 0) betac = sc[SC_ONE]; }
     else betac = mp_cmp(sc[SC_BETA_INF], beta) > 0 ? sc[SC_BETA_INF] : beta;
-    sc[SC_BETA] = beta; sc[SC_BETAC] = betac; num muc; mp_mul(muc, betac, sc[SC_MU]); sc[SC_MUC] = muc;
+    sc[SC_BETA] = beta; sc[SC_BETAC] = betac; num muc; mpc_mul<NL>(muc, betac, sc[SC_MU]); sc[SC_MUC] = muc;
     num de = mp_cmp_abs(sc[SC_ERRP], sc[SC_ERRp]) > 0 ? sc[SC_ERRP] : sc[SC_ERRp];
     fl[FL_PDFEAS] = (mp_cmp(de, sc[SC_DERRTHR]) < 0) && (mp_cmp(sc[SC_ERRd], sc[SC_PERRTHR]) < 0);
     info[INFO_BETAC] = mp_to_double(betac);
@@ -92,8 +110,8 @@ template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, doub
     num mn; bool have = false;
     for (int b = 0; b < nblocks; b++) {
       num ev;
-      if (bn[b] == 1) mp_div(ev, dM[boff[b]], M[boff[b]]);
-      else { num c; mp_from_double(ev, lam[b]); mp_from_double(c, 1e-5); mp_sub(ev, ev, c); }
+      if (bn[b] == 1) mpc_div<NL>(ev, dM[boff[b]], M[boff[b]]);
+      else { num c; mp_from_double(ev, lam[b]); mp_from_double(c, 1e-5); mpc_sub<NL>(ev, ev, c); }
       if (!have || mp_cmp(ev, mn) < 0) { mn = ev; have = true; }
     }
     if (!have) { mp_set_i32(mn, 1); mn.exp = 1 << 28; }        // a rank without blocks does not constrain the step
@@ -102,7 +120,7 @@ template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, doub
     num mn = sc[SC_TMP];
     num ng = sc[SC_GAMMA]; ng.sign = -ng.sign; num alpha;
     const bool unsafe_step = fl[FL_PDFEAS] && !cfg.safe_step;
-    if (mp_cmp(mn, ng) > 0 && !unsafe_step) alpha = sc[SC_ONE]; else mp_div(alpha, ng, mn);
+    if (mp_cmp(mn, ng) > 0 && !unsafe_step) alpha = sc[SC_ONE]; else mpc_div<NL>(alpha, ng, mn);
     sc[which] = alpha;
   } else if (phase == 3) {     // threshold test and the safe-step rule (src/solver.jl:470-483)
     num ad = sc[SC_ALPHAD], ap = sc[SC_ALPHAP];
@@ -112,11 +130,11 @@ template <int NL> __global__ void k_scalar(int phase, mpn<NL>* sc, int* fl, doub
     else if (fl[FL_PDFEAS] && cfg.safe_step) { sc[SC_ALPHAD] = mn; sc[SC_ALPHAP] = mn; }
     if (fl[FL_STOP] == CLRS_STOP_MAX_COMPLEMENTARY_GAP || fl[FL_STATUS] != 0) { mp_zero(sc[SC_ALPHAD]); mp_zero(sc[SC_ALPHAP]); }   // the reference throws before the step (:394,1248,1276,1645): the last good iterate is kept
   } else if (phase == 4) {     // objectives and gap (src/solver.jl:792-847)
-    num d = sc[SC_CX]; if (!cfg.maximize) d.sign = -d.sign; mp_add(d, d, sc[SC_CONSTANT]);
-    num p; mp_add(p, sc[SC_CY], sc[SC_BY]); mp_add(p, p, sc[SC_CONSTANT]);
-    num a, b; mp_sub(a, d, p); a.sign = a.sign ? 1 : 0; mp_add(b, d, p); b.sign = b.sign ? 1 : 0;
+    num d = sc[SC_CX]; if (!cfg.maximize) d.sign = -d.sign; mpc_add<NL>(d, d, sc[SC_CONSTANT]);
+    num p; mpc_add<NL>(p, sc[SC_CY], sc[SC_BY]); mpc_add<NL>(p, p, sc[SC_CONSTANT]);
+    num a, b; mpc_sub<NL>(a, d, p); a.sign = a.sign ? 1 : 0; mpc_add<NL>(b, d, p); b.sign = b.sign ? 1 : 0;
     if (mp_cmp(b, sc[SC_ONE]) < 0) b = sc[SC_ONE];
-    num g; mp_div(g, a, b);
+    num g; mpc_div<NL>(g, a, b);
     sc[SC_DOBJ] = d; sc[SC_POBJ] = p; sc[SC_GAP] = g;
     info[INFO_DOBJ + 10] = mp_to_double(d); info[INFO_POBJ + 10] = mp_to_double(p); info[INFO_GAP + 10] = mp_to_double(g);
   } else if (phase == 5) {     // pd_feas from the current errors (initialisation, src/solver.jl:326-333)
@@ -174,6 +192,11 @@ __global__ void k_combine_flags(int n, int R, const int* gathered, int* out) {
   int i = threadIdx.x; if (i >= n) return; int m = gathered[i]; for (int r = 1; r < R; r++) m = max(m, gathered[r * n + i]); out[i] = m;
 }
 
+// Q[r][c] += Qs[r][c] for the first `cols` columns of an N-row slab (row pitches lds, ldq)
+template <int NL> __global__ void k_add_slab(int N, int cols, const mpn<NL>* Qs, int lds, mpn<NL>* Q, int ldq) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)N * cols; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols); mpn<NL> a = Q[(int64_t)r * ldq + c], b = Qs[(int64_t)r * lds + c]; mp_add(a, a, b); Q[(int64_t)r * ldq + c] = a; }
+}
 // pseudo-random multi-limb numbers for kernel benchmarks (splitmix-style hash)
 template <int NL> __global__ void k_fill_random(int64_t n, mpn<NL>* a, uint64_t seed, int spread) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -221,6 +244,7 @@ template <int NL> struct Solver : SolverBase {
   std::vector<void*> allocs;
 
   template <class T> T* dalloc(size_t n) { void* p = nullptr; if (n == 0) n = 1; CK(cudaMalloc(&p, n * sizeof(T))); CK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); allocs.push_back(p); return (T*)p; }
+  void release(void* p) { for (size_t i = 0; i < allocs.size(); i++) if (allocs[i] == p) { allocs[i] = allocs.back(); allocs.pop_back(); break; } cudaFree(p); }
   template <class T> T* upload(const std::vector<T>& v) { T* p = dalloc<T>(v.size()); if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); return p; }
   int W() const { return (prec + 63) / 64; }
   void w2m(num& r, const void* src) const { wire_to_mpn<NL>(r, src, W()); }
@@ -261,16 +285,29 @@ template <int NL> struct Solver : SolverBase {
   std::vector<Sliced*> owned_sliced;
   static VecView rows_view(const num* A, int lda, int M, int K) { VecView v; v.base = A; v.bstride = 0; v.vper = M > 0 ? M : 1; v.sv = lda; v.sk = 1; v.nvec = M; v.K = K; return v; }
   static VecView cols_view(const num* B, int ldb, int K, int N) { VecView v; v.base = B; v.bstride = 0; v.vper = N > 0 ? N : 1; v.sv = 1; v.sk = ldb; v.nvec = N; v.K = K; return v; }
+  // E[vec] = largest exponent among the entries of each vector
+  void vec_exponents(const VecView& v, int32_t* E) {
+    if (v.K >= 8192 && (int64_t)v.nvec * 32 < 148 * 2048) {           // few long vectors: several CTAs per vector
+      const int ny = std::max(1, std::min((v.K + 2047) / 2048, (148 * 16 + v.nvec - 1) / v.nvec));
+      nlaunch++, k_fill_i32<<<(v.nvec + 255) / 256, 256, 0, st>>>(v.nvec, E, I8_EXP_NONE);
+      nlaunch++, k_vec_exp_long<NL><<<dim3(v.nvec, ny), 256, 0, st>>>(v, E);
+    } else
+    nlaunch++, k_vec_exp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 255) / 256), 256, 0, st>>>(v, E);
+  }
+  // panel over the packed upper triangles of `cnt` n x n matrices at M (stride n^2): vectors [v0, v0 + cnt) of the tensor-core
+  // panel s (already sized); sym: entries M[a][b] + M[b][a]
+  void split_tri(Sliced& s, int v0, const num* M, int cnt, int n, bool sym) {
+    VecView v; v.base = M; v.bstride = 0; v.vper = std::max(cnt, 1); v.sv = (int64_t)n * n; v.sk = 1; v.nvec = cnt; v.K = n * n;
+    vec_exponents(v, s.E + v0);
+    const int64_t tot_ = (int64_t)cnt * (s.Kp / 4);
+    if (sym) nlaunch++, k_exp_add<<<(cnt + 127) / 128, 128, 0, st>>>(cnt, s.E + v0, 1);
+    nlaunch++, k_split_tc_tri<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, (int64_t)n * n, cnt, n, sym ? 1 : 0, s.E + v0, s.Kp, s.pitch(), s.planes + (size_t)v0 * s.Kp);
+  }
   void split(Sliced& s, const VecView& v, bool kfast, int lay = 0, bool is_view = false) {
     if (!is_view) ensure(s, v.nvec, v.K, lay);
     if (v.nvec == 0 || v.K == 0) return;
     if (lay == 0 && v.K <= 512) { nlaunch++, k_split_warp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl); return; }
-    if (v.K >= 8192 && (int64_t)v.nvec * 32 < 148 * 2048) {           // few long vectors: several CTAs per vector
-      const int ny = std::max(1, std::min((v.K + 2047) / 2048, (148 * 16 + v.nvec - 1) / v.nvec));
-      nlaunch++, k_fill_i32<<<(v.nvec + 255) / 256, 256, 0, st>>>(v.nvec, s.E, I8_EXP_NONE);
-      nlaunch++, k_vec_exp_long<NL><<<dim3(v.nvec, ny), 256, 0, st>>>(v, s.E);
-    } else
-    nlaunch++, k_vec_exp<NL><<<(unsigned)(((int64_t)v.nvec * 32 + 255) / 256), 256, 0, st>>>(v, s.E);
+    vec_exponents(v, s.E);
     if (lay == 0) { int64_t tot_ = (int64_t)v.nvec * s.K4;
       nlaunch++, k_split<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(v, s.E, s.K4, s.sl, kfast ? 1 : 0); }
     else if (kfast) { int64_t tot_ = (int64_t)v.nvec * (s.Kp / 4);
@@ -321,19 +358,24 @@ template <int NL> struct Solver : SolverBase {
   // tiles of up to 160 columns with three (both fill the 512 TMEM columns).  The slice-pair count is the same either way,
   // so the choice minimises the summed MMA time of the tiles of one row block: an M=128, K=32 int8 MMA costs
   // max(operand bytes / 128 B per clock of shared memory, tensor work) cycles (+ issue overhead).
-  static double mma_cycles(int bn) { return std::max((4096.0 + 32.0 * bn) / 128.0, 0.53 * bn) + 6.0; }
-  static void pick_tiles(int N, int& BN, int& group) {
+  static double mma_cycles(int bn) { return std::max((4096.0 + 32.0 * bn) / 128.0, 0.73 * bn) + 10.0; }    // 0.73 cycles per column at the measured int8 rate (2 x 1.6 PFLOP/s bf16)
+  static void pick_tiles(int N, int& BN, int& group, int M = 0, int lower_only = 0) {
     const int N16 = (N + 15) & ~15;
-    auto cost = [&](int bn) { double c = 0; for (int n0 = 0; n0 < N; n0 += bn) c += mma_cycles(std::min(bn, (N - n0 + 15) & ~15)); return c; };
+    // summed MMA time of the tiles that are computed (all of them, or for a lower-triangular output those touching i >= j)
+    auto cost = [&](int bn) { double c = 0; const int nbm = M > 0 ? (M + tc::BM - 1) / tc::BM : 1;
+      for (int by = 0; by < nbm; by++) for (int n0 = 0; n0 < N; n0 += bn) if (!lower_only || n0 <= by * tc::BM + tc::BM - 1) c += mma_cycles(std::min(bn, (N - n0 + 15) & ~15));
+      return c; };
     const int bnA = std::min(128, N16);
     const int ntB = (N16 + tc::BNMAX - 1) / tc::BNMAX; int bnB = (((N16 + ntB - 1) / ntB) + 15) & ~15; if (bnB > tc::BNMAX) bnB = tc::BNMAX;
     static const int force = getenv("CLRS_TC_GROUP") ? atoi(getenv("CLRS_TC_GROUP")) : 0;
-    if (force == 4 || bnB <= 128 || (force != 3 && cost(bnA) <= cost(bnB) * 1.02)) { BN = bnA; group = 4; } else { BN = bnB; group = 3; }
+    // measured (profiles/r02_tile_bench.md): 90000 x 300 x 300 gains 7.6 % from 160 + 144 over 128 + 128 + 48, while with many
+    // column tiles (N = 641) the three-diagonal groups lose to wave quantisation: wide tiles only for one or two of them
+    if (force == 4 || bnB <= 128 || (force != 3 && (ntB > 2 || cost(bnA) <= cost(bnB) * 1.02))) { BN = bnA; group = 4; } else { BN = bnB; group = 3; }
   }
   void gemm_tc(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode, const num* D, int ldd,
                int batch, int64_t a_bvec, int64_t b_bvec, int64_t c_bs, int64_t d_bs, int lower_only, int trans = 0) {
     if (a0 != 0 || b0 != 0) throw CudaError("gemm_tc: panel offsets are not supported");
-    int BN, group; pick_tiles(N, BN, group);
+    int BN, group; pick_tiles(N, BN, group, M, lower_only);
     const int Npitch = (N + 15) & ~15;
     CUtensorMap mA = make_map(A, tc::BM), mB = make_map(B, BN);
     // K longer than the int32 headroom (35 slices * K * 2^14 < 2^31), or few tiles with a long K: split K over
@@ -481,6 +523,7 @@ template <int NL> struct Solver : SolverBase {
   // (k_potrf_diag), solves the rows below it and updates only the REST OF THE PANEL (K = 32, CUDA cores); the trailing
   // matrix is updated once per panel with K = 128, which is a tensor-core shape (src/tools.jl:69-107 is the unblocked loop).
   static constexpr int PNL = 128;
+  long long* potrf_dbg = nullptr;   // kernel tuning only: clock64 timeline of the first diagonal-block factorisation (CLRS_POTRF_TIMELINE)
   void chol(num* A, int lda, int n, num* Minv, int ldm, int code, bool full_inverse = true) {
     if (n == 0) return;
     if (ldm == n) zero(Minv, (int64_t)n * n); else for (int r = 0; r < n; r++) zero(Minv + (int64_t)r * ldm, n);
@@ -490,7 +533,7 @@ template <int NL> struct Solver : SolverBase {
       const int KE = std::min(n, K0 + pnl);
       for (int k0 = K0; k0 < KE; k0 += 32) {
         const int nb = std::min(32, KE - k0), rem = n - k0 - nb;
-        nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code, full_inverse ? 1 : 0);
+        nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code, full_inverse ? 1 : 0, k0 == 0 ? potrf_dbg : nullptr);
         if (rem <= 0) continue;
         num* A21 = A + (int64_t)(k0 + nb) * lda + k0;
         if (full_inverse) { split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);
@@ -566,8 +609,8 @@ template <int NL> struct Solver : SolverBase {
     int64_t goff = 0;                                                                      // offset in the global (all ranks) block order
     std::vector<num> hC;
     // dense
-    std::vector<int> dense_p; std::vector<std::vector<num>> dense_A;
-    int np = 0; int32_t* d_plist = nullptr; num* Aall = nullptr; int32_t* nz_start = nullptr; int32_t* nz_idx = nullptr; int32_t* nzT_start = nullptr; int32_t* nzT_p = nullptr; int64_t nnz = 0; Sliced AallB, AallV; num* T1 = nullptr; num* T2 = nullptr; num* Sd = nullptr; Sliced T1S, T2V;
+    std::vector<int> dense_p; size_t Aall_cap = 0;
+    int np = 0; int32_t* d_plist = nullptr; num* Aall = nullptr; int32_t* nz_start = nullptr; int32_t* nz_idx = nullptr; int32_t* nzT_start = nullptr; int32_t* nzT_p = nullptr; int64_t nnz = 0; Sliced AallB, AallV; num* T1 = nullptr; num* T2 = nullptr; num* Sd = nullptr; Sliced T1S, T2V; bool tri = false;   /* tri: Schur inner products over the packed upper triangle (all A_p symmetric) */
     // low rank
     std::vector<HTerm> lr;
     int nP = 0; int32_t* lr_plist = nullptr; int32_t* lr_tstart = nullptr; LRTermDev* lr_terms = nullptr; num* lr_lam = nullptr;
@@ -579,14 +622,15 @@ template <int NL> struct Solver : SolverBase {
     // per-iteration cached panels (layout `lay`: 1 = tensor-core panels for large blocks)
     Sliced YS, XiS, MS, MSY; int lay = 0;
   };
-  struct Clu { int owner = 0; bool owned = true; int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; unsigned* ready = nullptr; int off = 0; };
+  struct Clu { int owner = 0; bool owned = true; int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; unsigned* ready = nullptr; int off = 0;
+               bool big = false; num *Bc = nullptr, *Gc = nullptr, *Qs = nullptr; };   /* big: L^-1 B and its Q contribution are split by COLUMNS over all ranks: Bc = this rank's columns of B (P x ncr), Gc = all column chunks of L^-1 B ([rank][P][ncr]), Qs = this rank's N x ncr slab of G^T G */
   std::vector<Clu> cl; std::vector<Block*> blk;   // blk: all blocks in (j,l) order
   int N = 0, Ptot = 0, Ksum = 0, maximize = 1; std::vector<num> hb; num hconst;
   int64_t tot = 0;   // numbers in the flat block storage of the blocks this rank owns
   int64_t gtot = 0;  // numbers in all blocks of the SDP
   // device state
   num *X = nullptr, *Y = nullptr, *Cm = nullptr, *L = nullptr, *Minv = nullptr, *Xi = nullptr, *R = nullptr, *P = nullptr, *dX = nullptr, *dY = nullptr, *T1 = nullptr, *TXY = nullptr, *U = nullptr;
-  num* tmpU = nullptr; num* LinvBall = nullptr; int Pown = 0; unsigned* q_ready = nullptr;
+  num* tmpU = nullptr; num* LinvBall = nullptr; int Pown = 0; unsigned* q_ready = nullptr; int ncr = 0;   /* ncr: columns of B per rank for big clusters */
   num *x = nullptr, *y = nullptr, *c = nullptr, *b = nullptr, *d = nullptr, *p = nullptr, *dx = nullptr, *dy = nullptr, *tr = nullptr, *Q = nullptr, *QMinv = nullptr, *tmpN = nullptr;
   num* sc = nullptr; int* flags = nullptr; double* dinfo = nullptr; double* Td = nullptr; double* lamX = nullptr; double* lamY = nullptr; double* eigV = nullptr; EigTask* eigT = nullptr;
   int64_t* d_boff = nullptr; int32_t* d_bn = nullptr; BlockTab bt;
@@ -650,8 +694,15 @@ template <int NL> struct Solver : SolverBase {
     if (j < 0 || j >= (int)cl.size() || l < 0 || l >= (int)cl[j].blocks.size()) { err = "clrs_add_dense_term: no such block"; return CLRS_ERR_ARG; }
     if (p_ < 0 || p_ >= cl[j].P) { err = "clrs_add_dense_term: constraint row out of range"; return CLRS_ERR_ARG; }
     Block& b0 = cl[j].blocks[l]; if (!b0.high_rank) { err = "dense term on a low-rank block"; return CLRS_ERR_ARG; }
-    b0.dense_p.push_back(p_); b0.dense_A.emplace_back((size_t)b0.n * b0.n); auto& v = b0.dense_A.back();
-    for (size_t i = 0; i < v.size(); i++) w2m(v[i], (const char*)A + i * wire_size());
+    // the matrix goes to the device as raw wire bytes and is converted there (27e6 numbers for the BASELINE workload: a host
+    // loop over them cost more than the whole upload); the buffer of the block grows geometrically
+    const size_t nn = (size_t)b0.n * b0.n, have = b0.dense_p.size();
+    if (have + 1 > b0.Aall_cap) { const size_t cap = std::max<size_t>(8, std::min<size_t>(2 * b0.Aall_cap, (size_t)cl[j].P)); const size_t ncap = std::max(cap, have + 1);
+      num* nb_ = nullptr; CK(cudaMalloc((void**)&nb_, ncap * nn * sizeof(num))); allocs.push_back(nb_);
+      if (b0.Aall) { CK(cudaMemcpyAsync(nb_, b0.Aall, have * nn * sizeof(num), cudaMemcpyDeviceToDevice, st)); CK(cudaStreamSynchronize(st)); release(b0.Aall); }
+      b0.Aall = nb_; b0.Aall_cap = ncap; }
+    wire_to_device(b0.Aall + have * nn, A, nn);
+    b0.dense_p.push_back(p_);
     return 0;
   }
   int add_lowrank_term(int j, int l, int r, int s, int p_, int rank, const void* lam, const void* vs, const void* ws) override {
@@ -667,6 +718,10 @@ template <int NL> struct Solver : SolverBase {
     for (size_t i = 0; i < a.size(); i++) { if (a[i].sign != b[i].sign) return false; if (a[i].sign == 0) continue; if (a[i].exp != b[i].exp || memcmp(a[i].l, b[i].l, sizeof(a[i].l))) return false; }
     return true;
   }
+  static uint64_t vec_hash(const std::vector<num>& a) {       // FNV-1a over sign, exponent and limbs (zeros hash alike whatever their other fields)
+    uint64_t h = 1469598103934665603ull; auto mix = [&](uint32_t w) { h ^= w; h *= 1099511628211ull; };
+    for (auto& x : a) { mix((uint32_t)x.sign); if (x.sign == 0) continue; mix((uint32_t)x.exp); for (int q = 0; q < NL; q++) mix(x.l[q]); }
+    return h; }
   Sliced& own(Sliced& s) { owned_sliced.push_back(&s); return s; }
 
   // ---- finalize: build tables (precompute_matrices_bilinear_pairings, src/solver.jl:985-1059), allocate, initialise ----
@@ -691,11 +746,23 @@ template <int NL> struct Solver : SolverBase {
       Td2 = dalloc<double>(tot); eigV2 = dalloc<double>(vtot); U2 = dalloc<num>(tot); T1b = dalloc<num>(tot);
       for (auto& t : et) { t.T = Td2 + (t.T - Td); t.V = eigV2 + (t.V - eigV); } eigT2 = upload(et); }
     // the L_j^-1 B_j of the owned clusters are the row blocks of ONE matrix, so Q = (vcat LinvB)^T (vcat LinvB) is one product (:1268-1269)
-    Pown = 0; for (auto& c0 : cl) if (c0.owned) Pown += c0.P;
+    // Big clusters of a multi-rank solve: the owner factors S_j and broadcasts L_j; every rank solves
+    // L_j^-1 B_j for ITS columns of B_j, the column chunks are all-gathered, and every rank forms its N x ncr slab of
+    // G_j^T G_j, which it adds into its partial Q before the one all-reduce of Q.  No collective beyond broadcast + all-gather.
+    static const int bigp = getenv("CLRS_BIG_CLUSTER") ? atoi(getenv("CLRS_BIG_CLUSTER")) : 512;
+    ncr = nranks > 1 ? (N + nranks - 1) / nranks : N;
+    for (auto& c0 : cl) c0.big = nranks > 1 && N > 0 && bigp > 0 && c0.P >= bigp;
+    Pown = 0; for (auto& c0 : cl) if (c0.owned && !c0.big) Pown += c0.P;
     LinvBall = dalloc<num>((size_t)Pown * N);
-    { int64_t o = 0; for (auto& c0 : cl) if (c0.owned) { c0.LinvB = LinvBall + o * N; o += c0.P; } }
+    { int64_t o = 0; for (auto& c0 : cl) if (c0.owned && !c0.big) { c0.LinvB = LinvBall + o * N; o += c0.P; } }
     for (auto& c0 : cl) {
-      if (!c0.owned) continue;
+      if (c0.big) {                                                    // on every rank: the factor, this rank's columns of B, all chunks of G, the Q slab
+        std::vector<num> hBc((size_t)c0.P * ncr); num z; mp_zero(z);
+        for (int i = 0; i < c0.P; i++) for (int c = 0; c < ncr; c++) { const int col = rank * ncr + c; hBc[(size_t)i * ncr + c] = col < N ? c0.hB[(size_t)i * N + col] : z; }
+        c0.Bc = upload(hBc); c0.Gc = dalloc<num>((size_t)nranks * c0.P * ncr); c0.Qs = dalloc<num>((size_t)nranks * ncr * ncr);
+        if (!c0.owned) { c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); }
+      }
+      if (!c0.owned) { for (auto& b0 : c0.blocks) if (b0.Aall) { release(b0.Aall); b0.Aall = nullptr; } continue; }   // uploaded before the partition was known
       c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.t = dalloc<num>(c0.P); c0.ready = dalloc<unsigned>((size_t)(c0.P + 31) / 32 + 1);
       for (auto& b0 : c0.blocks) if (int rc = finalize_block(c0, b0)) return rc;
     }
@@ -718,19 +785,32 @@ template <int NL> struct Solver : SolverBase {
       b0.np = (int)b0.dense_p.size();
       if (use_tc(b0.np * n, n, n)) b0.lay = 1;          // the (np n) x n x n Schur products decide the panel layout of a dense block (n = 100: 7.1 ms on the CUDA cores -> 5.0 ms)
       std::vector<int32_t> pl(b0.dense_p.begin(), b0.dense_p.end()); b0.d_plist = upload(pl);
-      std::vector<num> all((size_t)b0.np * n * n); for (int i = 0; i < b0.np; i++) std::copy(b0.dense_A[i].begin(), b0.dense_A[i].end(), all.begin() + (size_t)i * n * n);
-      { // nonzero structure of the A_p (their zero entries contribute exact zeros to <A_p,Z> and sum_p x_p A_p):
-        // per p the list of nonzero positions, and per position the list of p that are nonzero there
-        std::vector<int32_t> st(b0.np + 1, 0), idx; std::vector<std::vector<int32_t>> byel((size_t)n * n);
-        for (int i = 0; i < b0.np; i++) { for (int e = 0; e < n * n; e++) if (all[(size_t)i * n * n + e].sign != 0) { idx.push_back(e); byel[e].push_back(i); } st[i + 1] = (int32_t)idx.size(); }
-        std::vector<int32_t> tst((size_t)n * n + 1, 0), tp; for (int e = 0; e < n * n; e++) { for (int i : byel[e]) tp.push_back(i); tst[e + 1] = (int32_t)tp.size(); }
-        b0.nnz = (int64_t)idx.size(); b0.nz_start = upload(st); b0.nz_idx = upload(idx); b0.nzT_start = upload(tst); b0.nzT_p = upload(tp); }
-      b0.Aall = upload(all); b0.dense_A.clear(); b0.dense_A.shrink_to_fit();
+      { // nonzero structure of the A_p (their zero entries contribute exact zeros to <A_p,Z> and sum_p x_p A_p): per p the list of
+        // nonzero positions, and per position the list of p that are nonzero there.  The mask is computed on the device; the host only
+        // turns the bytes into the two index lists.
+        const size_t nn = (size_t)n * n, cnt = (size_t)b0.np * nn; std::vector<uint8_t> mask(cnt);
+        if (cnt) { uint8_t* dm = nullptr; CK(cudaMalloc((void**)&dm, cnt)); nlaunch++, k_nonzero_mask<NL><<<grid_for((int64_t)cnt), 256, 0, st>>>((int64_t)cnt, b0.Aall, dm);
+          CK(cudaMemcpyAsync(mask.data(), dm, cnt, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaFree(dm)); }
+        std::vector<int32_t> st_(b0.np + 1, 0), idx, tcount(nn + 1, 0);
+        for (int i = 0; i < b0.np; i++) { const uint8_t* mrow = mask.data() + (size_t)i * nn; for (size_t e = 0; e < nn; e++) if (mrow[e]) { idx.push_back((int32_t)e); tcount[e + 1]++; } st_[i + 1] = (int32_t)idx.size(); }
+        for (size_t e = 0; e < nn; e++) tcount[e + 1] += tcount[e];
+        std::vector<int32_t> tp(idx.size()), fill(tcount.begin(), tcount.end() - 1);
+        for (int i = 0; i < b0.np; i++) for (int32_t q = st_[i]; q < st_[i + 1]; q++) tp[fill[idx[q]]++] = i;       // ascending p per position
+        b0.nnz = (int64_t)idx.size(); b0.nz_start = upload(st_); b0.nz_idx = upload(idx); b0.nzT_start = upload(tcount); b0.nzT_p = upload(tp); }
+      if (!b0.Aall) b0.Aall = dalloc<num>(1);
       b0.T1 = dalloc<num>((size_t)b0.np * n * n); b0.T2 = dalloc<num>((size_t)b0.np * n * n); b0.Sd = dalloc<num>((size_t)b0.np * b0.np);
       own(b0.AallB); own(b0.AallV); own(b0.T1S); own(b0.T2V);
       if (b0.np > 0) {
         VecView v; v.base = b0.Aall; v.bstride = (int64_t)n * n; v.vper = n; v.sv = 1; v.sk = n; v.nvec = b0.np * n; v.K = n; split(b0.AallB, v, false, b0.lay);   // columns of every A_p
-        VecView w; w.base = b0.Aall; w.bstride = 0; w.vper = b0.np; w.sv = (int64_t)n * n; w.sk = 1; w.nvec = b0.np; w.K = n * n; split(b0.AallV, w, true, use_tc(b0.np, b0.np, n * n) ? 1 : 0);   // A_q flattened
+        // A_q flattened for the inner products <A_q, T_p>.  The reference requires symmetric constraint matrices (src/checks.jl); when
+        // they are (checked bit for bit here) and the product is a tensor-core shape, the inner products run over the packed
+        // upper triangle with T_p symmetrised on the fly: K = n (n + 1) / 2 instead of n^2
+        static const int tri_off = getenv("CLRS_SCHUR_TRI") ? atoi(getenv("CLRS_SCHUR_TRI")) == 0 : 0;
+        const bool tcv = use_tc(b0.np, b0.np, n * n);
+        if (tcv && !tri_off) { int* fl = dalloc<int>(1); nlaunch++, k_check_symmetric<NL><<<grid_for((int64_t)b0.np * n * n), 256, 0, st>>>(b0.Aall, b0.np, n, fl);
+          int h = 1; CK(cudaMemcpyAsync(&h, fl, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); b0.tri = (h == 0); }
+        if (b0.tri) { ensure(b0.AallV, b0.np, n * (n + 1) / 2, 1); split_tri(b0.AallV, 0, b0.Aall, b0.np, n, false); }
+        else { VecView w; w.base = b0.Aall; w.bstride = 0; w.vper = b0.np; w.sv = (int64_t)n * n; w.sk = 1; w.nvec = b0.np; w.K = n * n; split(b0.AallV, w, true, tcv ? 1 : 0); }
       }
       return 0;
     }
@@ -740,11 +820,17 @@ template <int NL> struct Solver : SolverBase {
     b0.u_r.assign(m, 0); b0.ul_r.assign(m, 0); b0.V.assign(m, nullptr); b0.W.assign(m, nullptr); b0.Vs.resize(m); b0.Ws.resize(m);
     for (int r = 0; r < m; r++) {
       std::vector<int> uv, uw;
+      // unique vectors in order of first appearance (unique_idx, src/tools.jl:128-145), found through a hash of the limbs
+      std::unordered_multimap<uint64_t, int> hv, hw;
+      auto find_or_add = [&](std::unordered_multimap<uint64_t, int>& tab, std::vector<int>& uniq, const std::vector<num>& vec, bool isv) {
+        const uint64_t key = vec_hash(vec); auto range = tab.equal_range(key);
+        for (auto it = range.first; it != range.second; ++it) if (same_vec(isv ? b0.lr[uniq[it->second]].v : b0.lr[uniq[it->second]].w, vec)) return it->second;
+        return -1; };
       for (int s = 0; s < m; s++) for (size_t e = 0; e < b0.lr.size(); e++) { auto& t = b0.lr[e]; if (t.r != r || t.s != s) continue;
-        int f = -1; for (size_t u = 0; u < uv.size(); u++) if (same_vec(b0.lr[uv[u]].v, t.v)) { f = (int)u; break; }
-        if (f < 0) { f = (int)uv.size(); uv.push_back((int)e); } t.colV = f;
-        f = -1; for (size_t u = 0; u < uw.size(); u++) if (same_vec(b0.lr[uw[u]].w, t.w)) { f = (int)u; break; }
-        if (f < 0) { f = (int)uw.size(); uw.push_back((int)e); } t.rowW = f; }
+        int f = find_or_add(hv, uv, t.v, true);
+        if (f < 0) { f = (int)uv.size(); uv.push_back((int)e); hv.emplace(vec_hash(t.v), f); } t.colV = f;
+        f = find_or_add(hw, uw, t.w, false);
+        if (f < 0) { f = (int)uw.size(); uw.push_back((int)e); hw.emplace(vec_hash(t.w), f); } t.rowW = f; }
       b0.u_r[r] = (int)uv.size(); b0.ul_r[r] = (int)uw.size(); b0.umax = std::max(b0.umax, std::max(b0.u_r[r], b0.ul_r[r]));
       std::vector<num> hV((size_t)dl * uv.size()), hW((size_t)uw.size() * dl);
       for (size_t u = 0; u < uv.size(); u++) for (int a = 0; a < dl; a++) hV[(size_t)a * uv.size() + u] = b0.lr[uv[u]].v[a];
@@ -900,7 +986,7 @@ template <int NL> struct Solver : SolverBase {
     if (nchunk > 1) {
       // the constraints are processed in chunks on different execution contexts: while one chunk's products occupy the
       // tensor pipe, the other's recombination / exponent / split kernels (HBM and load-store bound) run beside them
-      ensure(b0.T1S, np * n, n, 1); ensure(b0.T2V, np, n * n, 1);
+      ensure(b0.T1S, np * n, n, 1); ensure(b0.T2V, np, b0.tri ? n * (n + 1) / 2 : n * n, 1);
       par_for(nchunk, [&](int c) {
         const int p0 = c * pc, cnt = std::min(pc, np - p0); if (cnt <= 0) return;
         Sliced Ac = view(b0.AallB, p0 * n, cnt * n), T1c = view(b0.T1S, p0 * n, cnt * n), T2c = view(b0.T2V, p0, cnt);
@@ -908,7 +994,8 @@ template <int NL> struct Solver : SolverBase {
         gemm(Ac, 0, b0.XiS, 0, cnt * n, n, T1p, n);
         { VecView v; v.base = T1p; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = cnt * n; v.K = n; split(T1c, v, false, 1, true); }
         gemm(T1c, 0, b0.YS, 0, cnt * n, n, T2p, n);
-        { VecView v; v.base = T2p; v.bstride = 0; v.vper = cnt; v.sv = nn; v.sk = 1; v.nvec = cnt; v.K = n * n; split(T2c, v, true, 1, true); }
+        if (b0.tri) split_tri(b0.T2V, p0, T2p, cnt, n, true);
+        else { VecView v; v.base = T2p; v.bstride = 0; v.vper = cnt; v.sv = nn; v.sk = 1; v.nvec = cnt; v.K = n * n; split(T2c, v, true, 1, true); }
       });
     } else {
     // T1t[(p,j)][i] = sum_k A_p[k][j] X^-1[i][k]   (= (X^-1 A_p)^T; the 90000-row operand sits on the 128-lane M side)
@@ -916,7 +1003,8 @@ template <int NL> struct Solver : SolverBase {
     // T2[(p,i)][b] = sum_j T1_p[i][j] Y[j][b]
     { VecView v; v.base = b0.T1; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = np * n; v.K = n; split(b0.T1S, v, false, b0.lay); }
     gemm(b0.T1S, 0, b0.YS, 0, np * n, n, b0.T2, n);
-    { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true, b0.AallV.lay); }
+    if (b0.tri) { ensure(b0.T2V, np, n * (n + 1) / 2, 1); split_tri(b0.T2V, 0, b0.T2, np, n, true); }
+    else { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true, b0.AallV.lay); }
     }
     // S[p,q] += sum_ab T2_p[ab] A_q[ab]
     gemm(b0.AallV, 0, b0.T2V, 0, np, np, b0.Sd, np, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);          // Sd[q][p], q >= p only
@@ -934,12 +1022,27 @@ template <int NL> struct Solver : SolverBase {
     par_clusters([&](Clu& c0) { chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S, false); });
     rec(ev[e0 + 1]);
     if (N > 0) {
-      par_clusters([&](Clu& c0) { if (c0.P) trsm_lower(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.B, N, N, c0.LinvB, N); });     // LinvB = L^-1 B  (:1258)
+      // big clusters: the factor goes to every rank (the stream order of the collectives is the cluster order on every rank)
+      for (auto& c0 : cl) if (c0.big) { const size_t bytes = (size_t)c0.P * c0.P * sizeof(num);
+        if (g_nccl.Broadcast(c0.S, c0.S, bytes, /*ncclChar*/ 0, c0.owner, comm, st) != 0 || g_nccl.Broadcast(c0.Minv, c0.Minv, bytes, 0, c0.owner, comm, st) != 0) throw CudaError("ncclBroadcast failed"); }
+      par_clusters([&](Clu& c0) { if (c0.P && !c0.big) trsm_lower(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.B, N, N, c0.LinvB, N); });     // LinvB = L^-1 B  (:1258)
+      for (auto& c0 : cl) if (c0.big) {                                                                  // this rank's columns of L_j^-1 B_j, then all chunks
+        num* mine = c0.Gc + (size_t)rank * c0.P * ncr;
+        trsm_lower(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.Bc, ncr, ncr, mine, ncr);
+        if (g_nccl.AllGather(mine, c0.Gc, (size_t)c0.P * ncr * sizeof(num), 0, comm, st) != 0) throw CudaError("ncclAllGather failed"); }
       rec(ev[e0 + 2]);
       if (Pown == 0) zero(Q, (int64_t)N * N);
       else { split_cols(tA, LinvBall, N, Pown, N, use_tc(N, N, Pown) ? 1 : 0);
         gemm(tA, 0, tA, 0, N, N, Q, N, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);                                  // Q = (vcat LinvB)^T (vcat LinvB), lower triangle  (:1268-1269)
         nlaunch++, k_mirror<NL><<<grid_for((int64_t)N * N), 256, 0, st>>>(N, Q, N, 0); }
+      for (auto& c0 : cl) if (c0.big) {                                                                  // Q[:, my columns] += G_j^T G_j[:, my columns]
+        const int lay = use_tc(N, ncr, c0.P) ? 1 : 0;
+        VecView va; va.base = c0.Gc; va.bstride = (int64_t)c0.P * ncr; va.vper = ncr; va.sv = 1; va.sk = ncr; va.nvec = nranks * ncr; va.K = c0.P;     // all columns of G_j, chunk by chunk
+        split(tA, va, false, lay);
+        split_cols(tB, c0.Gc + (size_t)rank * c0.P * ncr, ncr, c0.P, ncr, lay);
+        gemm(tA, 0, tB, 0, nranks * ncr, ncr, c0.Qs, ncr);
+        const int mine = std::min(ncr, N - rank * ncr);
+        if (mine > 0) nlaunch++, k_add_slab<NL><<<grid_for((int64_t)N * mine), 256, 0, st>>>(N, mine, c0.Qs, ncr, Q + (size_t)rank * ncr, N); }
       allreduce(Q, (int64_t)N * N, 0);                                                                  // the only cross-cluster coupling
       rec(ev[e0 + 3]);
       chol(Q, N, N, QMinv, N, CLRS_ERR_CHOL_Q, false);
@@ -961,11 +1064,13 @@ template <int NL> struct Solver : SolverBase {
     if (N > 0) zero(tmpU, N);
     par_clusters([&](Clu& c0) { if (c0.P) { copy(c0.t, dx + c0.off, c0.P); trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, false, c0.ready); } });                 // t_j = L_j^-1 rhs_j
     if (N > 0) for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
+      if (c0.big) { for (int s = 0; s < nranks; s++) { const int ncs = std::min(ncr, N - s * ncr); if (ncs > 0) nlaunch++, k_gemv_t<NL><<<(ncs + 31) / 32, 256, 0, st>>>(c0.P, ncs, c0.Gc + (size_t)s * c0.P * ncr, ncr, c0.t, tmpU + s * ncr, 1, 1); } continue; }
       nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                                        // u += LinvB_j^T t_j
     if (N > 0) { allreduce(tmpU, N, 0); addsub(dy, p, 1, tmpU, -1, N);                                                                       // dy = p - sum_j u_j
       trsv(Q, N, N, QMinv, N, dy, false, q_ready); trsv(Q, N, N, QMinv, N, dy, true, q_ready); }                                                              // dy = Q^-1 dy
     par_clusters([&](Clu& c0) { if (c0.P == 0) return;
-      if (N > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
+      if (N > 0 && c0.big) { for (int s = 0; s < nranks; s++) { const int ncs = std::min(ncr, N - s * ncr); if (ncs > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, ncs, c0.Gc + (size_t)s * c0.P * ncr, ncr, dy + s * ncr, c0.t, 1, 1); } }
+      else if (N > 0) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.LinvB, N, dy, c0.t, 1, 1);                                 // t_j += LinvB_j dy
       trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, true, c0.ready); copy(dx + c0.off, c0.t, c0.P); });                                                 // dx_j = L_j^-T t_j
     rec(evD[which][3]);
     weighted_A(dX, dx); addsub(dX, dX, 1, P, 1, tot);                                                                                       // dX = P + sum dx_p A_p
@@ -1065,7 +1170,10 @@ template <int NL> struct Solver : SolverBase {
   void drop_graph() { if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; } }
   void run_iteration() {
     static const int env_graph = getenv("CLRS_GRAPH") ? atoi(getenv("CLRS_GRAPH")) : 1;
-    if (!env_graph || graph_off || prof_on || eager_iters < 1) { enqueue_iteration(); eager_iters++; return; }
+    // multi-rank handles launch eagerly: replaying a graph that contains the NCCL collectives of two processes hung on the
+    // first replay (2 x B200, NCCL 2.28.9; profiles/README.md), while the eager sharded path is the one validated in round 1
+    static const int env_graph_mr = getenv("CLRS_GRAPH_MULTIRANK") ? atoi(getenv("CLRS_GRAPH_MULTIRANK")) : 0;
+    if (!env_graph || graph_off || prof_on || eager_iters < 1 || (nranks > 1 && !env_graph_mr)) { enqueue_iteration(); eager_iters++; return; }
     if (gexec && graph_gen != alloc_gen) drop_graph();
     if (!gexec) {
       const long gen0 = alloc_gen, nl0 = nlaunch; cudaGraph_t g = nullptr;
@@ -1173,7 +1281,13 @@ template <int NL> struct Solver : SolverBase {
     Scratch tmp; num* dA = talloc<num>(tmp, (size_t)n * n); num* dM = talloc<num>(tmp, (size_t)n * n);
     wire_to_device(dA, A, (size_t)n * n);
     CK(cudaMemsetAsync(flags, 0, FL_COUNT * sizeof(int), st));
-    chol(dA, n, n, dM, n, CLRS_ERR_CHOL_X);
+    const char* tl = getenv("CLRS_POTRF_TIMELINE");
+    if (tl) potrf_dbg = talloc<long long>(tmp, 300);
+    chol(dA, n, n, dM, n, CLRS_ERR_CHOL_X, !tl || atoi(tl) != 2);       // CLRS_POTRF_TIMELINE=2: the variant without the inverse (S and Q blocks)
+    if (tl) { long long hh[300]; CK(cudaMemcpyAsync(hh, potrf_dbg, sizeof(hh), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); potrf_dbg = nullptr;
+      fprintf(stderr, "potrf timeline (cycles): col  pivot  update  diag  | column total\n");
+      for (int c = 0; c < 32; c++) { long long* q = hh + 1 + c * 8; fprintf(stderr, "%2d: %7lld %7lld %7lld | %7lld\n", c, q[1] - q[0], q[3] - q[2], q[5] - q[4], q[6] - (c ? q[-2] : hh[0])); }
+      fprintf(stderr, "phase A %lld  phase B %lld  store %lld\n", hh[1 + 256] - hh[0], hh[2 + 256] - hh[1 + 256], hh[3 + 256] - hh[2 + 256]); }
     int f[FL_COUNT]; CK(cudaMemcpyAsync(f, flags, sizeof(f), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
     download_wire(Lw, dA, (size_t)n * n);
     if (f[FL_STATUS]) { err = "non-positive pivot"; return f[FL_STATUS]; }
@@ -1191,7 +1305,12 @@ template <int NL> struct Solver : SolverBase {
     const int n = 4096; mpn<WL>* a = dalloc<mpn<WL>>(n); mpn<WL>* b2 = dalloc<mpn<WL>>(n); int* mm = dalloc<int>(1);
     nlaunch++, k_fill_random<WL><<<16, 256, 0, st>>>(n, a, 77, 40); nlaunch++, k_fill_random<WL><<<16, 256, 0, st>>>(n, b2, 5, 40);
     nlaunch++, k_selftest_mpw<WL><<<n * 32 / 256, 256, 0, st>>>(n, a, b2, mm);
-    int h = -1; CK(cudaMemcpyAsync(&h, mm, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); return h;
+    int h = -1; CK(cudaMemcpyAsync(&h, mm, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+    if (getenv("CLRS_WOPS_BENCH")) { long long* o = dalloc<long long>(8); mpn<WL>* sink = dalloc<mpn<WL>>(1);
+      for (int rep = 0; rep < 2; rep++) k_bench_wops<WL><<<1, 32, 0, st>>>(a, b2, o, sink);
+      long long ho[8]; CK(cudaMemcpyAsync(ho, o, sizeof(ho), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+      fprintf(stderr, "cycles per op (%d limbs, one warp alone): w_mul %lld  w_addsub %lld  w_rsqrt_c %lld  w_mul_c %lld | one thread: mp_mul %lld  mp_add %lld  mp_rsqrt %lld\n", WL, ho[0], ho[1], ho[2], ho[3], ho[4], ho[5], ho[6]); }
+    return h;
   }
   // kernel-only timing of C = A*B on device-generated operands: out = {split ms, gemm ms per rep (kernel + recombine), kernel-only ms per rep}
   int bench_gemm(int M, int N_, int K, int reps, int path, double* out) override {
@@ -1228,7 +1347,7 @@ template <int NL> struct Solver : SolverBase {
   int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) override {
     std::string w(what); const num* src = nullptr; int64_t n = 0;
     if (j >= 0 && j < (int)cl.size() && !cl[j].owned && (w == "S" || w == "LinvB" || w.size() > 2 || w == "X" || w == "Y" || w == "R" || w == "P" || w == "L")) return -1;
-    if (w == "S") { src = cl[j].S; n = (int64_t)cl[j].P * cl[j].P; } else if (w == "LinvB") { src = cl[j].LinvB; n = (int64_t)cl[j].P * N; }
+    if (w == "S") { src = cl[j].S; n = (int64_t)cl[j].P * cl[j].P; } else if (w == "LinvB") { if (cl[j].big) return -1; src = cl[j].LinvB; n = (int64_t)cl[j].P * N; }
     else if (w == "Q") { src = Q; n = (int64_t)N * N; } else if (w == "d") { src = d; n = Ptot; } else if (w == "p") { src = p; n = N; }
     else if (w == "dx") { src = dx; n = Ptot; } else if (w == "dy") { src = dy; n = N; } else if (w == "x") { src = x; n = Ptot; } else if (w == "y") { src = y; n = N; }
     else { Block& b0 = cl[j].blocks[l]; n = (int64_t)b0.n * b0.n; const num* base = nullptr;

@@ -335,6 +335,56 @@ template <int NL> __global__ void k_split_tc(VecView v, const int32_t* E, int Kp
   for (int t = 0; t < NS; t++) *(uint32_t*)(planes + ((int64_t)t * nvec_pitch + vec) * Kp + 4 * k4) = w[t];
 }
 
+// Split over the PACKED UPPER TRIANGLE of n x n matrices (one matrix per vector): k <-> (a <= b), row by row.  With sym != 0 the
+// entry is M[a][b] + M[b][a] for a != b — so that <A, T> = sum_{a<=b} A[a][b] (T[a][b] + T[b][a] (a != b)) for a symmetric A runs
+// over K = n (n + 1) / 2 instead of n^2 (the dense Schur inner products, src/solver.jl:1100-1103).  E must already allow for the
+// extra bit of the sums (k_exp_add).
+// E[i] += add for the vectors that are not all zero (the symmetrised sums can carry one bit beyond the largest entry; the
+// recombination reads the same exponents the split used)
+__global__ void k_exp_add(int n, int32_t* E, int add) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n && E[i] != I8_EXP_NONE) E[i] += add; }
+template <int NL> __global__ void k_split_tc_tri(const mpn<NL>* base, int64_t mstride, int nvec, int n, int sym, const int32_t* E, int Kp, int64_t nvec_pitch, uint8_t* planes) {
+  constexpr int NS = I8Cfg<NL>::NS;
+  const int K4 = Kp / 4;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)nvec * K4) return;
+  const int k4 = (int)(idx % K4), vec = (int)(idx / K4);
+  const mpn<NL>* M = base + (int64_t)vec * mstride;
+  const int32_t e = E[vec];
+  const int KS = n * (n + 1) / 2, k = 4 * k4;
+  // row a of packed index k: the largest a with a (2n - a + 1) / 2 <= k
+  int a = (int)(((2.0 * n + 1.0) - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * (double)k)) * 0.5);
+  if (a < 0) a = 0; if (a > n - 1) a = n - 1;
+  while (a + 1 < n && (int64_t)(a + 1) * (2 * n - a) / 2 <= k) a++;
+  while (a > 0 && (int64_t)a * (2 * n - a + 1) / 2 > k) a--;
+  int b = a + (k - (int)((int64_t)a * (2 * n - a + 1) / 2));
+  uint32_t w[NS];
+#pragma unroll
+  for (int t = 0; t < NS; t++) w[t] = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    if (k + q < KS) {
+      mpn<NL> v = M[(int64_t)a * n + b];
+      if (sym && a != b) { const mpn<NL> o = M[(int64_t)b * n + a]; mp_add(v, v, o); }
+      int8_t dg[NS]; i8_split<NL>(v, e, dg);
+#pragma unroll
+      for (int t = 0; t < NS; t++) w[t] |= (uint32_t)(uint8_t)dg[t] << (8 * q);
+      if (++b == n) { a++; b = a; }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NS; t++) *(uint32_t*)(planes + ((int64_t)t * nvec_pitch + vec) * Kp + 4 * k4) = w[t];
+}
+// flag[0] |= 1 if some matrix of the batch is not symmetric (bit pattern comparison)
+template <int NL> __global__ void k_check_symmetric(const mpn<NL>* base, int64_t count, int n, int* flag) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count * n * n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t mtx = i / ((int64_t)n * n); const int r = (int)((i / n) % n), c = (int)(i % n);
+    if (r < c) { const mpn<NL> x = base[mtx * n * n + (int64_t)r * n + c], y = base[mtx * n * n + (int64_t)c * n + r];
+      bool same = x.sign == y.sign && (x.sign == 0 || x.exp == y.exp);
+      if (same && x.sign != 0) for (int q = 0; q < NL; q++) same = same && x.l[q] == y.l[q];
+      if (!same) atomicOr(flag, 1); }
+  }
+}
+
 // Same split for vectors whose entries are NOT contiguous (columns of a row-major matrix): consecutive
 // threads take consecutive vectors so the 40-byte reads coalesce, and the digits go through a
 // shared-memory transpose so each plane row receives full 32-byte segments.

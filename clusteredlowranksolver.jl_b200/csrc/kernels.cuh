@@ -334,7 +334,7 @@ template <int NL> __device__ __forceinline__ mpn<NL> shfl_xor_num(const mpn<NL>&
   for (int q = 0; q < NL; q++) r.l[q] = __shfl_xor_sync(0xffffffffu, a.l[q], m);
   r.exp = __shfl_xor_sync(0xffffffffu, a.exp, m); r.sign = __shfl_xor_sync(0xffffffffu, a.sign, m); return r;
 }
-template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(int nb, mpn<NL>* A, int lda, mpn<NL>* Minv, int ldm, int* status, int code, int want_inv) {
+template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(int nb, mpn<NL>* A, int lda, mpn<NL>* Minv, int ldm, int* status, int code, int want_inv, long long* dbg = nullptr) {
   extern __shared__ unsigned char smraw[];
   // beyond 10 limbs four full 32 x 32 arrays do not fit in shared memory: keep the lower triangles only
   constexpr bool PACK = NL > 10; constexpr int SZ = PACK ? 528 : 1024;
@@ -350,21 +350,26 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
   for (int idx = tid; idx < 32 * 32; idx += POTRF_THREADS) { const int i = idx >> 5, j = idx & 31; if (PACK && j > i) continue; mpn<NL> a; mp_zero(a); if (i < nb && j <= i) a = A[(int64_t)i * lda + j]; const int o = PACK ? ix(i, j) : idx; As[o] = a; mp_zero(Ls[o]); mp_zero(Ms[o]); }
   if (tid == 0) bad = 0;
   __syncthreads();
-  if (tid == 0) { mpn<NL> a = As[0]; if (a.sign <= 0) { bad = 1; mp_set_i32(a, 1); } dpiv[0] = a; mpn<NL> r; mp_rsqrt(r, a); rinv[0] = r; }
+  if constexpr (NL == 8 || NL == 16) {
+    if (warp == 23) { wnum a = w_load<NL>(&As[0]); if (a.sign <= 0) { if (lane == 0) bad = 1; mpn<NL> one; mp_set_i32(one, 1); a = w_from<NL>(one); }
+      w_store<NL>(&dpiv[0], a); w_store<NL>(&rinv[0], w_rsqrt_c<NL>(a)); }
+  } else if (tid == 0) { mpn<NL> a = As[0]; if (a.sign <= 0) { bad = 1; mp_set_i32(a, 1); } dpiv[0] = a; mpn<NL> r; mp_rsqrt(r, a); rinv[0] = r; }
   __syncthreads();
   // ---- phase A: factorisation ------------------------------------------------------------------------------------
   // (the scheduler favours the highest warp id on an SM sub-partition, and the pivot chain is the critical path)
+  if (dbg && tid == 0) dbg[0] = clock64();
   for (int c = 0; c < nb; c++) {
+    if (dbg && lane == 0 && (warp == 23 || warp == 0 || warp == 22)) dbg[1 + c * 8 + (warp == 23 ? 0 : (warp == 0 ? 2 : 4))] = clock64();
     if (warp == 23) {
       // pivot chain: d_{c+1} = a_{c+1,c+1} - l_{c+1,c}^2 (columns < c already applied), r_{c+1} = d^-1/2
       if (c + 1 < nb) {
         if constexpr (NL == 8 || NL == 16) {
           // the whole warp works on one number at a time (mpw.cuh): ~4x shorter critical path than one thread
-          wnum l = w_mul<NL>(w_load<NL>(&As[ix(c + 1, c)]), w_load<NL>(&rinv[c]));
-          wnum d = w_sub<NL>(w_load<NL>(&As[ix(c + 1, c + 1)]), w_mul<NL>(l, l));
+          wnum l = w_mul_c<NL>(w_load<NL>(&As[ix(c + 1, c)]), w_load<NL>(&rinv[c]));
+          wnum d = w_addsub_c<NL>(w_load<NL>(&As[ix(c + 1, c + 1)]), w_mul_c<NL>(l, l), -1);
           if (d.sign <= 0) { if (lane == 0) bad = 1; mpn<NL> one; mp_set_i32(one, 1); d = w_from<NL>(one); }
           w_store<NL>(&dpiv[c + 1], d);
-          w_store<NL>(&rinv[c + 1], w_rsqrt<NL>(d));
+          w_store<NL>(&rinv[c + 1], w_rsqrt_c<NL>(d));
         } else if (lane == 0) {
           mpn<NL> l, d; mp_mul(l, As[ix(c + 1, c)], rinv[c]); mp_mul(l, l, l); mp_sub(d, As[ix(c + 1, c + 1)], l);
           if (d.sign <= 0) { bad = 1; mp_set_i32(d, 1); }
@@ -375,7 +380,7 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
       // the diagonal entry (square root with one correction step: nobody's input inside the kernel, so it stays off every critical path)
       if constexpr (NL == 8 || NL == 16) {
         const wnum d = w_load<NL>(&dpiv[c]), y = w_load<NL>(&rinv[c]);
-        wnum sq = w_mul<NL>(d, y); wnum t = w_mul<NL>(w_sub<NL>(d, w_mul<NL>(sq, sq)), y); t.exp -= (t.sign != 0); sq = w_add<NL>(sq, t);
+        wnum sq = w_mul_c<NL>(d, y); wnum t = w_mul_c<NL>(w_addsub_c<NL>(d, w_mul_c<NL>(sq, sq), -1), y); t.exp -= (t.sign != 0); sq = w_addsub_c<NL>(sq, t, 1);
         w_store<NL>(&Ls[ix(c, c)], sq);
         if (lane == 0) Ms[ix(c, c)] = rinv[c];                              // diagonal of the inverse; the substitution kernels use only these
       } else if (lane == 0) { Ms[ix(c, c)] = rinv[c]; mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[ix(c, c)] = sq; }
@@ -391,8 +396,11 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
         mpn<NL> a = As[ix(i, j)], t; mp_mul(t, Ls[ix(i, c)], Ls[ix(j, c)]); mp_sub(a, a, t); As[ix(i, j)] = a;
       }
     }
+    if (dbg && lane == 0 && (warp == 23 || warp == 0 || warp == 22)) dbg[1 + c * 8 + (warp == 23 ? 1 : (warp == 0 ? 3 : 5))] = clock64();
     __syncthreads();                                      // (element (c+1,c+1) lives on in dpiv; its As copy is not read again)
+    if (dbg && tid == 0) dbg[1 + c * 8 + 6] = clock64();
   }
+  if (dbg && tid == 0) dbg[1 + 32 * 8] = clock64();
   // ---- phase B: M = L^-1 by recursive halving ------------------------------------------------------------------------
   if (want_inv) {
     for (int h = 1; h < 32; h <<= 1) {
@@ -415,7 +423,9 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
       __syncthreads();
     }
   }
+  if (dbg && tid == 0) dbg[2 + 32 * 8] = clock64();
   for (int idx = tid; idx < nb * nb; idx += POTRF_THREADS) { const int i = idx / nb, j = idx % nb; mpn<NL> lv, mv; if (j <= i) { lv = Ls[ix(i, j)]; mv = Ms[ix(i, j)]; } else { mp_zero(lv); mp_zero(mv); } A[(int64_t)i * lda + j] = lv; Minv[(int64_t)i * ldm + j] = mv; }
+  if (dbg && tid == 0) dbg[3 + 32 * 8] = clock64();
   if (tid == 0 && bad) atomicCAS(status, 0, code);
 }
 #define POTRF_SMEM(NL) ((4 * ((NL) > 10 ? 528 : 1024) + 64) * sizeof(mpn<NL>))
@@ -442,6 +452,32 @@ template <int NL> __global__ void k_selftest_mpw(int n, const mpn<NL>* a, const 
   }
   mp_sub(ref, x, x); got = w_to<NL>(w_sub<NL>(w_from<NL>(x), w_from<NL>(x))); bad = bad || got.sign != 0 || ref.sign != 0;
   if (bad && lane == 0) atomicAdd(mismatches, 1);
+}
+
+// latency of the building blocks of the pivot chain, one warp alone on an SM: out[i] = cycles per operation of a dependent chain
+// (kernel tuning only: CLRS_WOPS_BENCH=1 with clrs_debug_selftest)
+template <int NL> __global__ void k_bench_wops(const mpn<NL>* a, const mpn<NL>* b, long long* out, mpn<NL>* sink) {
+  const int lane = threadIdx.x & 31; constexpr int REP = 64;
+  mpn<NL> x = a[0], y = b[0]; x.sign = 1; y.sign = 1; x.exp = 0; y.exp = 0;
+  wnum wx = w_from<NL>(x), wy = w_from<NL>(y);
+  long long t0 = clock64();
+  for (int i = 0; i < REP; i++) { wx = w_mul<NL>(wx, wy); wx.exp = 0; }
+  long long t1 = clock64();
+  for (int i = 0; i < REP; i++) { wx = w_addsub<NL>(wx, wy, (i & 1) ? 1 : -1); }
+  long long t2 = clock64();
+  for (int i = 0; i < REP / 8; i++) { wx.sign = 1; wx = w_rsqrt_c<NL>(wx); }
+  long long t3 = clock64();
+  for (int i = 0; i < REP; i++) { wx = w_mul_c<NL>(wx, wy); wx.exp = 0; }
+  long long t4 = clock64();
+  mpn<NL> s = w_to<NL>(wx); s.sign = 1;
+  long long t5 = clock64();
+  for (int i = 0; i < REP; i++) { mp_mul(s, s, y); s.exp = 0; }
+  long long t6 = clock64();
+  for (int i = 0; i < REP; i++) { mpn<NL> t = y; t.sign = (i & 1) ? 1 : -1; mp_add(s, s, t); }
+  long long t7 = clock64();
+  for (int i = 0; i < REP / 8; i++) { s.sign = 1; mp_rsqrt(s, s); }
+  long long t8 = clock64();
+  if (lane == 0) { out[0] = (t1 - t0) / REP; out[1] = (t2 - t1) / REP; out[2] = (t3 - t2) / (REP / 8); out[3] = (t4 - t3) / REP; out[4] = (t6 - t5) / REP; out[5] = (t7 - t6) / REP; out[6] = (t8 - t7) / (REP / 8); sink[0] = s; }
 }
 
 // ---------------------------------------------------------------------------
@@ -507,6 +543,10 @@ template <int NL> __global__ void k_mpn_to_wire(int64_t n, const mpn<NL>* in, in
     for (int k = 0; k < NL; k++) { const int q = k - (NL - nw); if (q >= 0 && q < nw) wl[q] = a.l[k]; }
   }
   }
+}
+// mask[i] = (a[i] != 0): the nonzero structure of the dense constraint matrices, built at upload
+template <int NL> __global__ void k_nonzero_mask(int64_t n, const mpn<NL>* a, uint8_t* mask) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mask[i] = a[i].sign != 0 ? 1 : 0;
 }
 // one thread per (vec, k4): split 4 consecutive entries into NS digits and pack them per slice.
 // kfast != 0: consecutive threads take consecutive k4 (unit-stride vectors), else consecutive vectors.
@@ -821,10 +861,18 @@ __global__ void __launch_bounds__(EIG_THREADS) k_min_eig(const EigTask* tasks, d
       }
       __syncthreads();
       double alpha = block_sum_d(a_part, sh);
-      // full reorthogonalisation (twice)
-      for (int pass = 0; pass < 2; pass++) for (int q = 0; q <= c; q++) {
-        const double* u = V + (int64_t)q * n; double d = 0; for (int i = tid; i < n; i += blockDim.x) d += w[i] * u[i];
-        d = block_sum_d(d, sh); for (int i = tid; i < n; i += blockDim.x) w[i] -= d * u[i]; __syncthreads();
+      // full reorthogonalisation: classical Gram-Schmidt against all previous vectors, twice ("twice is enough"); the c + 1
+      // inner products of a pass are independent, one warp each, so a pass costs two barriers instead of 2 (c + 1) block reductions
+      for (int pass = 0; pass < 2; pass++) {
+        const int nw = blockDim.x >> 5, wid = tid >> 5, ln = tid & 31;
+        for (int q = wid; q <= c; q += nw) {
+          const double* u = V + (int64_t)q * n; double d = 0; for (int i = ln; i < n; i += 32) d += w[i] * u[i];
+          for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+          if (ln == 0) dv[q] = d;                          // (dv is free here: tridiag_min_vec uses it only inside a check)
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) { double s = 0; for (int q = 0; q <= c; q++) s += dv[q] * V[(int64_t)q * n + i]; w[i] -= s; }
+        __syncthreads();
       }
       double bp = 0; for (int i = tid; i < n; i += blockDim.x) bp += w[i] * w[i];
       double beta = sqrt(block_sum_d(bp, sh));

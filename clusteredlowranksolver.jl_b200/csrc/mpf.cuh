@@ -122,8 +122,22 @@ template <int NL> HD void mp_set_i32(mpn<NL>& r, int32_t v) {
   uint32_t m = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v; int z = mp_clz32(m);
   r.l[NL - 1] = m << z; r.exp = 32 - z; r.sign = v < 0 ? -1 : 1;
 }
+// exact power of two as a double, -1022 <= k <= 1023 (the seeds of the Newton iterations scale by these instead of calling ldexp:
+// the library calls dominated the ~2200 cycles the seed of one reciprocal square root cost, measured with k_bench_wops)
+HD double mp_pow2(int k) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((1023 + k) << 20, 0);
+#else
+  return ldexp(1.0, k);
+#endif
+}
 template <int NL> HD void mp_from_double(mpn<NL>& r, double d) {
   mp_zero(r); if (d == 0.0 || !(d == d)) return;
+  uint64_t bits; memcpy(&bits, &d, 8);
+  const int ef = (int)((bits >> 52) & 0x7ff);
+  if (ef != 0 && ef != 0x7ff) {                           // normal number: the 53-bit significand sits at the top of 64 bits
+    const uint64_t mant = ((bits & 0xFFFFFFFFFFFFFull) | (1ull << 52)) << 11;
+    r.l[NL - 1] = (uint32_t)(mant >> 32); r.l[NL - 2] = (uint32_t)mant; r.exp = ef - 1022; r.sign = d < 0 ? -1 : 1; return; }
   int e; double m = frexp(fabs(d), &e);                  // m in [0.5,1)
   uint64_t mant = (uint64_t)ldexp(m, 64);                // exact: 53 significant bits
   r.l[NL - 1] = (uint32_t)(mant >> 32); r.l[NL - 2] = (uint32_t)mant; r.exp = e; r.sign = d < 0 ? -1 : 1;
@@ -223,12 +237,16 @@ template <int NL> HD void mp_submul(mpn<NL>& r, const mpn<NL>& a, const mpn<NL>&
 template <int NL> HD constexpr int mp_newton_steps() { return 32 * NL <= 160 ? 1 : (32 * NL <= 352 ? 2 : (32 * NL <= 704 ? 3 : 4)); }
 // top 96 bits of a mantissa given by its three leading limbs, times 2^sc, as an exact sum hi + lo of two doubles
 HD void mp_mant_dd(uint32_t A, uint32_t B, uint32_t C, int sc, double& hi, double& lo) {
-  hi = ldexp((double)A, sc - 32) + ldexp((double)(B >> 11), sc - 53);      // 32 + 21 = 53 bits: exact
-  lo = ldexp((double)(B & 2047u), sc - 64) + ldexp((double)C, sc - 96);    // 11 + 32 = 43 bits: exact
+  hi = (double)A * mp_pow2(sc - 32) + (double)(B >> 11) * mp_pow2(sc - 53);      // 32 + 21 = 53 bits: exact
+  lo = (double)(B & 2047u) * mp_pow2(sc - 64) + (double)C * mp_pow2(sc - 96);    // 11 + 32 = 43 bits: exact
 }
 // y0 + c = m^(-1/2) (1 + O(2^-95)) for m = mh + ml in [1/4, 1)
 HD void dd_rsqrt_seed(double mh, double ml, double& y0, double& c) {
+#if defined(__CUDA_ARCH__)
+  y0 = rsqrt(mh);                                                          // (any ~52-bit start: the correction below brings y0 + c to ~2^-95)
+#else
   y0 = 1.0 / sqrt(mh);
+#endif
   const double ph = CLRS_DMUL(y0, y0), pl = CLRS_DFMA(y0, y0, -ph);          // y0^2 = ph + pl
   const double th = CLRS_DMUL(mh, ph), tl0 = CLRS_DFMA(mh, ph, -th);         // mh ph = th + tl0
   const double tl = CLRS_DADD(tl0, CLRS_DADD(CLRS_DMUL(mh, pl), CLRS_DMUL(ml, ph)));

@@ -156,3 +156,30 @@ template <int NL> __device__ __forceinline__ wnum w_rsqrt(const wnum& a) {
   y.exp -= (a.exp + odd) / 2;
   return y;
 }
+
+// a double as a warp-distributed number (same value as w_from(mp_from_double(d)) for normal d, without the limb loop)
+template <int NL> __device__ __forceinline__ wnum w_from_double(double d) {
+  wnum r; r.limb = 0; r.exp = 0; r.sign = 0;
+  if (d == 0.0 || !(d == d)) return r;
+  const uint64_t bits = (uint64_t)__double_as_longlong(d); const int ef = (int)((bits >> 52) & 0x7ff);
+  const uint64_t mant = ((bits & 0xFFFFFFFFFFFFFull) | (1ull << 52)) << 11;      // (subnormals and infinities do not occur: seeds of mantissas in [1/4, 1))
+  const int t = threadIdx.x & (NL - 1);
+  r.limb = t == NL - 1 ? (uint32_t)(mant >> 32) : (t == NL - 2 ? (uint32_t)mant : 0u); r.exp = ef - 1022; r.sign = d < 0 ? -1 : 1; return r;
+}
+// ---- out-of-line variants ------------------------------------------------------------------------------------------------
+// A sequential chain of warp-cooperative operations executed ONCE per step (the pivot chain of the diagonal-block Cholesky)
+// is bound by instruction fetch when every operation is inlined: ~2500 straight-line instructions per column, no reuse,
+// 25 cycles per instruction measured (clock64 timeline, profiles/r02_potrf_timeline.txt: 62 k cycles per pivot).  Called
+// as functions the same operations run from ~2 KB of code that stays in the instruction cache.  Same bits as the inline forms.
+template <int NL> __device__ __noinline__ wnum w_mul_c(wnum a, wnum b) { return w_mul<NL>(a, b); }
+template <int NL> __device__ __noinline__ wnum w_addsub_c(wnum a, wnum b, int bsgn) { return w_addsub<NL>(a, b, bsgn); }
+template <int NL> __device__ __noinline__ wnum w_rsqrt_c(wnum a) {
+  wnum m = a; const int odd = a.exp & 1; m.exp = -odd; m.sign = 1;
+  const uint32_t A = __shfl_sync(0xffffffffu, a.limb, NL - 1), B = __shfl_sync(0xffffffffu, a.limb, NL - 2), C = __shfl_sync(0xffffffffu, a.limb, NL - 3);
+  double mh, ml, y0d, cd; mp_mant_dd(A, B, C, -odd, mh, ml); dd_rsqrt_seed(mh, ml, y0d, cd);     // same seed as mp_rsqrt
+  wnum y = w_addsub_c<NL>(w_from_double<NL>(y0d), w_from_double<NL>(cd), 1); const wnum w3 = w_from_double<NL>(3.0);
+#pragma unroll 1
+  for (int it = 0; it < mp_newton_steps<NL>(); it++) { wnum t = w_mul_c<NL>(y, y); t = w_mul_c<NL>(t, m); t = w_addsub_c<NL>(w3, t, -1); y = w_mul_c<NL>(y, t); y.exp -= 1; }
+  y.exp -= (a.exp + odd) / 2;
+  return y;
+}
