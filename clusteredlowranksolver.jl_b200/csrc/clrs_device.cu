@@ -424,7 +424,8 @@ template <int NL> struct Solver : SolverBase {
   // members the helpers use; kernels capture their pointers at enqueue time, so swapping while enqueuing is safe.
   struct Ctx { cudaStream_t st = nullptr; Sliced tA, tB; num* chol_W = nullptr; size_t chol_W_cap = 0; uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0; int32_t* tc_raw = nullptr; size_t tc_raw_cap = 0;
                num* trsm_R = nullptr; size_t trsm_cap = 0; cudaEvent_t ev = nullptr; };
-  Ctx side, side2;                                   // side: Cholesky of Y; side2: R = mu I - XY beside chol(X), and Y's step-length eigenvalue beside X's
+  Ctx side, side2, side3;                            // side: Cholesky of Y; side2: R = mu I - XY beside chol(X), and Y's step-length eigenvalue beside X's; side3: first stage of the dense Schur products
+  cudaEvent_t evS0 = nullptr, evS1 = nullptr; bool stage1_pending = false;
   cudaEvent_t evR0 = nullptr, evR1 = nullptr, evE0 = nullptr, evE1 = nullptr; num *U2 = nullptr, *T1b = nullptr; double* Td2 = nullptr; double* eigV2 = nullptr; EigTask* eigT2 = nullptr;
   cudaEvent_t evY0 = nullptr, evY1 = nullptr; num *LY = nullptr, *MinvY = nullptr;
   void swap_with(Ctx& c) { std::swap(st, c.st); std::swap(tA, c.tA); std::swap(tB, c.tB); std::swap(chol_W, c.chol_W); std::swap(chol_W_cap, c.chol_W_cap);
@@ -644,7 +645,8 @@ template <int NL> struct Solver : SolverBase {
     int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError("no CUDA device: libclrs_b200 has no CPU fallback");
     CK(cudaSetDevice(o.device)); cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, o.device));
     if (pr.major < 10) throw CudaError("an sm_100 device is required");
-    CK(cudaStreamCreate(&st)); CK(cudaStreamCreate(&side.st)); CK(cudaStreamCreate(&side2.st)); for (cudaEvent_t* e : {&evR0, &evR1, &evE0, &evE1}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY1, cudaEventDisableTiming));
+    { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&st, cudaStreamDefault, hi)); }      // the main chain outranks the side streams
+    CK(cudaStreamCreate(&side.st)); CK(cudaStreamCreate(&side2.st)); CK(cudaStreamCreate(&side3.st)); CK(cudaEventCreateWithFlags(&evS0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evS1, cudaEventDisableTiming)); for (cudaEvent_t* e : {&evR0, &evR1, &evE0, &evE1}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&evY1, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming)); for (int k = 1; k < NCTX; k++) { CK(cudaStreamCreate(&pctx[k].st)); CK(cudaEventCreateWithFlags(&pctx[k].ev, cudaEventDisableTiming)); }
     for (auto& e : ev) CK(cudaEventCreate(&e)); for (auto& r : evD) for (auto& e : r) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
@@ -659,6 +661,7 @@ template <int NL> struct Solver : SolverBase {
     cudaSetDevice(opt.device); cudaDeviceSynchronize();
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     owned_sliced.push_back(&tA); owned_sliced.push_back(&tB); owned_sliced.push_back(&side.tA); owned_sliced.push_back(&side.tB); owned_sliced.push_back(&side2.tA); owned_sliced.push_back(&side2.tB);
+    owned_sliced.push_back(&side3.tA); owned_sliced.push_back(&side3.tB); if (side3.tc_bytes) cudaFree(side3.tc_bytes); if (side3.tc_top) cudaFree(side3.tc_top); if (side3.tc_raw) cudaFree(side3.tc_raw); cudaStreamDestroy(side3.st); cudaEventDestroy(evS0); cudaEventDestroy(evS1);
     if (side2.tc_bytes) cudaFree(side2.tc_bytes); if (side2.tc_top) cudaFree(side2.tc_top); if (side2.tc_raw) cudaFree(side2.tc_raw); cudaStreamDestroy(side2.st); for (cudaEvent_t e : {evR0, evR1, evE0, evE1}) if (e) cudaEventDestroy(e);
     if (side.tc_bytes) cudaFree(side.tc_bytes); if (side.tc_top) cudaFree(side.tc_top); if (side.tc_raw) cudaFree(side.tc_raw); cudaEventDestroy(evY0); cudaEventDestroy(evY1); cudaStreamDestroy(side.st);
     for (int k = 1; k < NCTX; k++) { Ctx& c = pctx[k]; owned_sliced.push_back(&c.tA); owned_sliced.push_back(&c.tB); if (c.tc_bytes) cudaFree(c.tc_bytes); if (c.tc_top) cudaFree(c.tc_top); if (c.tc_raw) cudaFree(c.tc_raw);
@@ -973,6 +976,37 @@ template <int NL> struct Solver : SolverBase {
     int64_t np2 = (int64_t)b0.nP * b0.nP;
     nlaunch++, k_schur_lowrank<NL><<<(unsigned)((np2 + 127) / 128), 128, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BX, b0.d_BY, m, c0.S, c0.P);
   }
+  // ---- dense Schur path in two stages (blocks whose A_p are all symmetric, tensor-core shapes) --------------------------------
+  // <A_q, X^-1 A_p Y> = <A_q, (X^-1 W_p)^T> with W_p = A_p Y.  W_p needs only Y, so the first of the two 90000-row products
+  // is issued BEFORE the Cholesky factorisation of X, on a low-priority side stream, and fills the SMs that the single-CTA
+  // panel chain of chol(X) leaves idle (the main stream has the highest priority, so its kernels take the next SM that frees).
+  bool staged(const Block& b0) const { static const int off = getenv("CLRS_SCHUR_STAGED") ? atoi(getenv("CLRS_SCHUR_STAGED")) == 0 : 0; return !off && b0.high_rank && b0.tri && b0.lay == 1 && b0.np > 0; }
+  int dense_chunk(const Block& b0, int nsm = 148) {   // constraints per chunk: two rounds of tiles on nsm SMs (n = 300: 63 on 148 SMs)
+    static const int chunks_off = getenv("CLRS_SCHUR_CHUNKS") ? atoi(getenv("CLRS_SCHUR_CHUNKS")) == 1 : 0;
+    const int n = b0.n, np = b0.np;
+    if (chunks_off || b0.lay != 1 || b0.AallV.lay != 1 || (int64_t)np * n < 32768) return np;
+    int BNt, grp; pick_tiles(n, BNt, grp); const int ntn = (n + BNt - 1) / BNt;
+    return std::max(1, ((2 * nsm / ntn) * 128) / n);
+  }
+  void dense_stage1(Block& b0) {                      // W_p = A_p Y, stored as W[(p,i)][b], and its split by columns (p,b) for stage 2
+    const int n = b0.n, np = b0.np; const int64_t nn = (int64_t)n * n; const int pc = dense_chunk(b0), nchunk = (np + pc - 1) / pc;
+    ensure(b0.T1S, np * n, n, 1);
+    par_for(nchunk, [&](int c) {
+      const int p0 = c * pc, cnt = std::min(pc, np - p0); if (cnt <= 0) return;
+      Sliced Ac = view(b0.AallB, p0 * n, cnt * n), T1c = view(b0.T1S, p0 * n, cnt * n); num* T1p = b0.T1 + (int64_t)p0 * nn;
+      gemm(Ac, 0, b0.YS, 0, cnt * n, n, T1p, n);                                                      // (columns of the symmetric A_p) x (columns of Y)
+      VecView v; v.base = T1p; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = cnt * n; v.K = n; split(T1c, v, false, 1, true); });
+  }
+  void dense_stage2(Block& b0) {                      // T_p^T[(p,b)][a] = sum_i W_p[i][b] X^-1[a][i]; S[p,q] += <A_q, T_p^T> over the packed triangle
+    const int n = b0.n, np = b0.np; const int64_t nn = (int64_t)n * n; const int pc = dense_chunk(b0), nchunk = (np + pc - 1) / pc;
+    ensure(b0.T2V, np, n * (n + 1) / 2, 1);
+    par_for(nchunk, [&](int c) {
+      const int p0 = c * pc, cnt = std::min(pc, np - p0); if (cnt <= 0) return;
+      Sliced T1c = view(b0.T1S, p0 * n, cnt * n); num* T2p = b0.T2 + (int64_t)p0 * nn;
+      gemm(T1c, 0, b0.XiS, 0, cnt * n, n, T2p, n);
+      split_tri(b0.T2V, p0, T2p, cnt, n, true); });
+    gemm(b0.AallV, 0, b0.T2V, 0, np, np, b0.Sd, np, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);          // Sd[q][p], q >= p only
+  }
   void pairings_dense(Block& b0) {                    // T = X^-1 A_p Y, S[p,q] += <A_q, T>   (src/solver.jl:1089-1104)
     const int n = b0.n, np = b0.np; if (np == 0) return; const int64_t nn = (int64_t)n * n;
     // chunk of constraints = a whole number of waves of the product's CTAs on the 148 SMs (n = 300: 2 column tiles x 148 row
@@ -1014,7 +1048,8 @@ template <int NL> struct Solver : SolverBase {
     nlaunch++, k_scatter_upper<NL><<<(unsigned)(((int64_t)np * np + 127) / 128), 128, 0, st>>>(np, b0.d_plist, b0.Sd, c0.S, c0.P);
   }
   void decomposition(int e0) {
-    par_blocks([&](Block* b0) { if (b0->high_rank) pairings_dense(*b0); else pairings_lowrank(*b0); });
+    if (stage1_pending) { CK(cudaStreamWaitEvent(st, evS1, 0)); stage1_pending = false; }
+    par_blocks([&](Block* b0) { if (staged(*b0)) dense_stage2(*b0); else if (b0->high_rank) pairings_dense(*b0); else pairings_lowrank(*b0); });
     par_clusters([&](Clu& c0) { zero(c0.S, (int64_t)c0.P * c0.P);
       for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_add_dense(c0, b0); else schur_add_lowrank(c0, b0); }
       if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); });
@@ -1120,6 +1155,11 @@ template <int NL> struct Solver : SolverBase {
     scalar(0);                                                        // mu, mu_p  (SC_D0 = <X,Y> is kept current)
     // R = mu_p I - X Y
     par_blocks([&](Block* b0) { const int n = b0->n; split_cols(b0->YS, Y + b0->off, n, n, n, b0->lay); });      // Y panels: used by R, the Schur products and the directions
+    { bool any = false; for (Block* b0 : blk) any = any || staged(*b0);                                       // first stage of the dense Schur products: needs only Y
+      if (any && !prof_on) { CK(cudaEventRecord(evS0, st)); swap_with(side3); CK(cudaStreamWaitEvent(st, evS0, 0));
+        for (Block* b0 : blk) if (staged(*b0)) dense_stage1(*b0);
+        CK(cudaEventRecord(evS1, st)); swap_with(side3); stage1_pending = true; }
+      else if (any) for (Block* b0 : blk) if (staged(*b0)) dense_stage1(*b0); }
     CK(cudaEventRecord(evR0, st)); swap_with(side2); CK(cudaStreamWaitEvent(st, evR0, 0));                      // R is first needed by the predictor: beside chol(X) and the Schur assembly
     par_blocks([&](Block* b0) { const int n = b0->n; split_rows(tA, X + b0->off, n, n, n, b0->lay); gemm(tA, 0, b0->YS, 0, n, n, TXY + b0->off, n); });
     nlaunch++, k_residual_R<NL><<<grid_for(tot), 256, 0, st>>>(bt, tot, R, TXY, (const num*)nullptr, sc + SC_MUP);
@@ -1173,7 +1213,12 @@ template <int NL> struct Solver : SolverBase {
     // multi-rank handles launch eagerly: replaying a graph that contains the NCCL collectives of two processes hung on the
     // first replay (2 x B200, NCCL 2.28.9; profiles/README.md), while the eager sharded path is the one validated in round 1
     static const int env_graph_mr = getenv("CLRS_GRAPH_MULTIRANK") ? atoi(getenv("CLRS_GRAPH_MULTIRANK")) : 0;
-    if (!env_graph || graph_off || prof_on || eager_iters < 1 || (nranks > 1 && !env_graph_mr)) { enqueue_iteration(); eager_iters++; return; }
+    // handles with a staged dense Schur path launch eagerly: the main stream's priority over the side stream of the first product
+    // is what lets the panel chain of chol(X) progress beside it, and neither stream nor kernel-node priorities had any effect
+    // inside a replayed graph (measured: 22.3 ms per iteration replayed, 20.4 ms eager; profiles/README.md)
+    static const int staged_eager = getenv("CLRS_STAGED_EAGER") ? atoi(getenv("CLRS_STAGED_EAGER")) : 1;
+    bool any_staged = false; if (staged_eager) for (Block* b0 : blk) any_staged = any_staged || staged(*b0);
+    if (!env_graph || graph_off || prof_on || eager_iters < 1 || (nranks > 1 && !env_graph_mr) || any_staged) { enqueue_iteration(); eager_iters++; return; }
     if (gexec && graph_gen != alloc_gen) drop_graph();
     if (!gexec) {
       const long gen0 = alloc_gen, nl0 = nlaunch; cudaGraph_t g = nullptr;

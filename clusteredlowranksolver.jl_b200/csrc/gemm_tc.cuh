@@ -151,8 +151,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
       uint32_t ca = 0, cb = 0;                                  // running load counters of the two rings
-      const int arow = brow_z * a.a_bvec + m0, brow = brow_z * a.b_bvec + n0;
       const uint32_t abytes = BM * KC, bbytes = (uint32_t)BN * KC;
+      const int arow = brow_z * a.a_bvec + m0, brow = brow_z * a.b_bvec + n0;
       for (int g = g_hi; g >= g_lo; g--) {
         const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
         for (int kc = 0; kc < nkc; kc++) {
@@ -185,16 +185,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // counts are constant.
     static_assert(NA == 4 && NB == 8, "ring phase shifts below assume NA = 4, NB = 8");
     const int koff = warp - 1;
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint64_t descA0 = make_desc(smem_u32(ringA)), descB0 = make_desc(smem_u32(ringB));   // slot s: + s * (SLOT_BYTES >> 4)
     const bool leader = (lane == 0);
     const bool dbgon = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 1;
-    uint32_t ca = 0, cbase = 0; uint32_t epi_parity = 0;
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    uint32_t ca = 0, cbase = 0; uint32_t epi_parity = 0; bool first_group = true;
     for (int g = g_hi; g >= g_lo; g--) {
       const int d0 = g * GROUP, d1 = min(d0 + GROUP - 1, NS - 1), w = d1 - d0;
       const bool carry_in = (g != g_hi);
       if (dbgon && leader) a.dbg[(ngroups - 1 - g) * 8 + 0] = clock64();
-      if (carry_in) { mbar_wait(tmem_empty, epi_parity); epi_parity ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+      // the accumulators are free once the epilogue has drained the previous group
+      if (!first_group) { mbar_wait(tmem_empty, epi_parity); epi_parity ^= 1; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+      first_group = false;
       if (dbgon && leader) a.dbg[(ngroups - 1 - g) * 8 + 1] = clock64();
       const uint32_t tcol = tmem_base + (uint32_t)((w - koff) * BN);         // this warp's accumulator (diagonal d1 - koff)
       for (int kc = 0; kc < nkc; kc++) {
@@ -295,11 +297,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }
       if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 5] = clock64();
-      if (g > 0) {
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(tmem_empty);
-      }
+      // the group is drained (and, for g > 0, the carry is in place): the MMA warps may write the accumulators again
+      if (g > 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tmem_empty);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
