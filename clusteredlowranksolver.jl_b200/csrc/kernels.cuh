@@ -350,57 +350,60 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
   for (int idx = tid; idx < 32 * 32; idx += POTRF_THREADS) { const int i = idx >> 5, j = idx & 31; if (PACK && j > i) continue; mpn<NL> a; mp_zero(a); if (i < nb && j <= i) a = A[(int64_t)i * lda + j]; const int o = PACK ? ix(i, j) : idx; As[o] = a; mp_zero(Ls[o]); mp_zero(Ms[o]); }
   if (tid == 0) bad = 0;
   __syncthreads();
-  if constexpr (NL == 8 || NL == 16) {
-    if (warp == 23) { wnum a = w_load<NL>(&As[0]); if (a.sign <= 0) { if (lane == 0) bad = 1; mpn<NL> one; mp_set_i32(one, 1); a = w_from<NL>(one); }
-      w_store<NL>(&dpiv[0], a); w_store<NL>(&rinv[0], w_rsqrt_c<NL>(a)); }
-  } else if (tid == 0) { mpn<NL> a = As[0]; if (a.sign <= 0) { bad = 1; mp_set_i32(a, 1); } dpiv[0] = a; mpn<NL> r; mp_rsqrt(r, a); rinv[0] = r; }
-  __syncthreads();
-  // ---- phase A: factorisation ------------------------------------------------------------------------------------
-  // (the scheduler favours the highest warp id on an SM sub-partition, and the pivot chain is the critical path)
+  // ---- phase A: division-free elimination, square roots deferred ------------------------------------------------------------
+  // The classical right-looking loop has one reciprocal square root per column on its critical path (~6 k cycles even with
+  // warp-cooperative arithmetic: `k_bench_wops`).  Here the working matrix carries a positive scale instead:
+  //     W^(c+1)_ij = ( W^(c)_cc W^(c)_ij - W^(c)_ic W^(c)_jc ) 2^-e_c ,   pi_(c+1) = pi_c W^(c)_cc 2^-e_c   (e_c = exponent of W^(c)_cc)
+  // so that the true Schur complement is A^(c) = W^(c) / pi_c.  A column step is two multiplications and a subtraction per
+  // element, all elements in parallel, one barrier: no division, no square root, no pivot warp.  The power of two keeps the scale
+  // bounded (pi_c in (2^-c, 1]) and costs nothing.  Afterwards, for all columns at once:
+  //     r_c = (W_cc pi_c)^-1/2 ,   L_ic = W_ic r_c ,   L_cc = W_cc r_c (one correction step) ,   1 / L_cc = r_c pi_c .
+  // The pivot test is unchanged: W^(c)_cc <= 0 exactly when the true pivot is (pi_c > 0).
+  mpn<NL>* pis = Tb;                                      // pi_c, c = 0..32 (Tb is free until phase B)
+  if (tid == 0) { mpn<NL> one; mp_set_i32(one, 1); pis[0] = one; }
   if (dbg && tid == 0) dbg[0] = clock64();
   for (int c = 0; c < nb; c++) {
-    if (dbg && lane == 0 && (warp == 23 || warp == 0 || warp == 22)) dbg[1 + c * 8 + (warp == 23 ? 0 : (warp == 0 ? 2 : 4))] = clock64();
-    if (warp == 23) {
-      // pivot chain: d_{c+1} = a_{c+1,c+1} - l_{c+1,c}^2 (columns < c already applied), r_{c+1} = d^-1/2
-      if (c + 1 < nb) {
-        if constexpr (NL == 8 || NL == 16) {
-          // the whole warp works on one number at a time (mpw.cuh): ~4x shorter critical path than one thread
-          wnum l = w_mul_c<NL>(w_load<NL>(&As[ix(c + 1, c)]), w_load<NL>(&rinv[c]));
-          wnum d = w_addsub_c<NL>(w_load<NL>(&As[ix(c + 1, c + 1)]), w_mul_c<NL>(l, l), -1);
-          if (d.sign <= 0) { if (lane == 0) bad = 1; mpn<NL> one; mp_set_i32(one, 1); d = w_from<NL>(one); }
-          w_store<NL>(&dpiv[c + 1], d);
-          w_store<NL>(&rinv[c + 1], w_rsqrt_c<NL>(d));
-        } else if (lane == 0) {
-          mpn<NL> l, d; mp_mul(l, As[ix(c + 1, c)], rinv[c]); mp_mul(l, l, l); mp_sub(d, As[ix(c + 1, c + 1)], l);
-          if (d.sign <= 0) { bad = 1; mp_set_i32(d, 1); }
-          dpiv[c + 1] = d; mpn<NL> r; mp_rsqrt(r, d); rinv[c + 1] = r;
-        }
-      }
-    } else if (warp == 22) {
-      // the diagonal entry (square root with one correction step: nobody's input inside the kernel, so it stays off every critical path)
-      if constexpr (NL == 8 || NL == 16) {
-        const wnum d = w_load<NL>(&dpiv[c]), y = w_load<NL>(&rinv[c]);
-        wnum sq = w_mul_c<NL>(d, y); wnum t = w_mul_c<NL>(w_addsub_c<NL>(d, w_mul_c<NL>(sq, sq), -1), y); t.exp -= (t.sign != 0); sq = w_addsub_c<NL>(sq, t, 1);
-        w_store<NL>(&Ls[ix(c, c)], sq);
-        if (lane == 0) Ms[ix(c, c)] = rinv[c];                              // diagonal of the inverse; the substitution kernels use only these
-      } else if (lane == 0) { Ms[ix(c, c)] = rinv[c]; mpn<NL> d = dpiv[c], y = rinv[c], sq, t; mp_mul(sq, d, y); mp_mul(t, sq, sq); mp_sub(t, d, t); mp_mul(t, t, y); t.exp -= (t.sign != 0); mp_add(sq, sq, t); Ls[ix(c, c)] = sq; }
-    } else {
-      // column c of the factor, then the trailing update with it (warps 0-21)
-      constexpr int nupd = 704;
-      for (int i = c + 1 + tid; i < nb; i += nupd) { mpn<NL> a; mp_mul(a, As[ix(i, c)], rinv[c]); Ls[ix(i, c)] = a; }
-      asm volatile("bar.sync 1, %0;" ::"r"(nupd) : "memory");
-      const int w = nb - c - 1;
-      for (int idx = tid + 1; idx < w * (w + 1) / 2; idx += nupd) {              // lower triangle only; idx 0 = (c+1,c+1) belongs to the pivot chain
-        int ii = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((ii + 1) * (ii + 2) / 2 <= idx) ii++; while (ii * (ii + 1) / 2 > idx) ii--;
-        const int i = c + 1 + ii, j = c + 1 + (idx - ii * (ii + 1) / 2);
-        mpn<NL> a = As[ix(i, j)], t; mp_mul(t, Ls[ix(i, c)], Ls[ix(j, c)]); mp_sub(a, a, t); As[ix(i, j)] = a;
-      }
+    if (dbg && lane == 0 && warp == 0) dbg[1 + c * 8 + 2] = clock64();
+    mpn<NL> d = As[ix(c, c)];
+    if (d.sign <= 0) { if (tid == 0) bad = 1; mp_set_i32(d, 1); }             // (every thread takes the same branch)
+    const int32_t e = d.exp;
+    if (tid == POTRF_THREADS - 1) { dpiv[c] = d; mpn<NL> m = d; m.exp = 0; mpn<NL> p; mp_mul(p, pis[c], m); pis[c + 1] = p; }
+    const int w = nb - c - 1;
+    for (int idx = tid; idx < w * (w + 1) / 2; idx += POTRF_THREADS - 32) {     // lower triangle of the trailing block (the last warp keeps the scale)
+      if (tid >= POTRF_THREADS - 32) break;
+      int ii = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((ii + 1) * (ii + 2) / 2 <= idx) ii++; while (ii * (ii + 1) / 2 > idx) ii--;
+      const int i = c + 1 + ii, j = c + 1 + (idx - ii * (ii + 1) / 2);
+      mpn<NL> x, t; mp_mul(x, d, As[ix(i, j)]); mp_mul(t, As[ix(i, c)], As[ix(j, c)]); mp_sub(x, x, t);
+      if (x.sign != 0) x.exp -= e;
+      As[ix(i, j)] = x;
     }
-    if (dbg && lane == 0 && (warp == 23 || warp == 0 || warp == 22)) dbg[1 + c * 8 + (warp == 23 ? 1 : (warp == 0 ? 3 : 5))] = clock64();
-    __syncthreads();                                      // (element (c+1,c+1) lives on in dpiv; its As copy is not read again)
+    if (dbg && lane == 0 && warp == 0) dbg[1 + c * 8 + 3] = clock64();
+    __syncthreads();
     if (dbg && tid == 0) dbg[1 + c * 8 + 6] = clock64();
   }
   if (dbg && tid == 0) dbg[1 + 32 * 8] = clock64();
+  // all columns at once: r_c, the diagonal of the factor and of its inverse (one warp per column, or one thread without warp-cooperative arithmetic)
+  for (int c = warp; c < nb; c += POTRF_THREADS / 32) {
+    if constexpr (NL == 8 || NL == 16) {
+      const wnum dd = w_load<NL>(&dpiv[c]), pc = w_load<NL>(&pis[c]);
+      const wnum r = w_rsqrt_c<NL>(w_mul_c<NL>(dd, pc));
+      wnum sq = w_mul_c<NL>(dd, r);                                            // sqrt(W_cc / pi_c), then s += (W_cc - s^2 pi_c) r / 2
+      wnum t = w_mul_c<NL>(w_addsub_c<NL>(dd, w_mul_c<NL>(w_mul_c<NL>(sq, sq), pc), -1), r); t.exp -= (t.sign != 0); sq = w_addsub_c<NL>(sq, t, 1);
+      w_store<NL>(&rinv[c], r); w_store<NL>(&Ls[ix(c, c)], sq); w_store<NL>(&Ms[ix(c, c)], w_mul_c<NL>(r, pc));
+    } else if (lane == 0) {
+      mpn<NL> dd = dpiv[c], pc = pis[c], r, sq, t; mp_mul(t, dd, pc); mp_rsqrt(r, t);
+      mp_mul(sq, dd, r); mp_mul(t, sq, sq); mp_mul(t, t, pc); mp_sub(t, dd, t); mp_mul(t, t, r); t.exp -= (t.sign != 0); mp_add(sq, sq, t);
+      rinv[c] = r; Ls[ix(c, c)] = sq; mp_mul(t, r, pc); Ms[ix(c, c)] = t;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nb * (nb - 1) / 2; idx += POTRF_THREADS) {          // L_ic = W_ic r_c below the diagonal
+    int i = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f); while ((i + 1) * (i + 2) / 2 <= idx) i++; while (i * (i + 1) / 2 > idx) i--;
+    const int cc = idx - i * (i + 1) / 2; i += 1;                                // strict lower triangle: row i >= 1, column cc < i
+    mpn<NL> x; mp_mul(x, As[ix(i, cc)], rinv[cc]); Ls[ix(i, cc)] = x;
+  }
+  __syncthreads();
+  if (dbg && tid == 0) dbg[2 + 32 * 8] = clock64();
   // ---- phase B: M = L^-1 by recursive halving ------------------------------------------------------------------------
   if (want_inv) {
     for (int h = 1; h < 32; h <<= 1) {
@@ -423,7 +426,7 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
       __syncthreads();
     }
   }
-  if (dbg && tid == 0) dbg[2 + 32 * 8] = clock64();
+  if (dbg && tid == 0) dbg[4 + 32 * 8] = clock64();
   for (int idx = tid; idx < nb * nb; idx += POTRF_THREADS) { const int i = idx / nb, j = idx % nb; mpn<NL> lv, mv; if (j <= i) { lv = Ls[ix(i, j)]; mv = Ms[ix(i, j)]; } else { mp_zero(lv); mp_zero(mv); } A[(int64_t)i * lda + j] = lv; Minv[(int64_t)i * ldm + j] = mv; }
   if (dbg && tid == 0) dbg[3 + 32 * 8] = clock64();
   if (tid == 0 && bad) atomicCAS(status, 0, code);

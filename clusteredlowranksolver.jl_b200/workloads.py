@@ -237,6 +237,48 @@ def lovasz_theta_cycle(n, prec=256):
                             clusters=[cl], name=f"theta(C_{n})")
 
 
+def povm_two_states(prec=256):
+    """Optimal discrimination of the two pure qubit states of example_POVM (examples/jump.jl:41-58, test/moi_tests.jl:9-10):
+    maximize (1/2) sum_i Re <rho_i, E_i> s.t. E_1 + E_2 = I, E_i Hermitian PSD; optimum 1/2 + sqrt(2)/4.
+    JuMP's HermitianPSDCone reaches the solver as real symmetric PSD blocks Z_i = [[A_i, -B_i], [B_i, A_i]] (E_i = A_i + i B_i)
+    with equality constraints for the block structure, i.e. a dense-path SDP with TWO blocks in ONE cluster that share the
+    coupling constraints: 16 constraints, two 4 x 4 dense blocks, no free variables."""
+    with mpmath.workprec(prec + 64):
+        def sym(entries):                       # symmetric 4 x 4 matrix with the given (a, b, value) in both triangles
+            M = [[mpf(0)] * 4 for _ in range(4)]
+            for a, b, v in entries:
+                M[a][b] += mpf(v) / (1 if a == b else 2)
+                if a != b:
+                    M[b][a] += mpf(v) / 2
+            return M
+        # <sym([(a,b,v)]), Z> = v Z[a][b] for a symmetric Z
+        structure = [[(0, 0, 1), (2, 2, -1)], [(1, 1, 1), (3, 3, -1)], [(0, 1, 1), (2, 3, -1)],      # upper-left block = lower-right block
+                     [(2, 0, 1)], [(3, 1, 1)], [(3, 0, 1), (2, 1, 1)]]                             # lower-left block antisymmetric
+        coupling = [([(0, 0, 1)], 1), ([(1, 1, 1)], 1), ([(0, 1, 1)], 0), ([(3, 0, 1)], 0)]          # sum_i A_i = I, sum_i B_i = 0
+        # rho_1 = 1/2 [1,-1][1,-1]^T ; rho_2 = 1/2 [1,-i][1,-i]^* = 1/2 [[1, i], [-i, 1]]: R + iS with S = 1/2 [[0, 1], [-1, 0]]
+        R = [[[mpf(1) / 2, -mpf(1) / 2], [-mpf(1) / 2, mpf(1) / 2]], [[mpf(1) / 2, 0], [0, mpf(1) / 2]]]
+        S = [[[0, 0], [0, 0]], [[0, mpf(1) / 2], [-mpf(1) / 2, 0]]]
+        blocks = []
+        P = 2 * len(structure) + len(coupling)
+        for i in range(2):
+            Zrho = [[mpf(0)] * 4 for _ in range(4)]
+            for a in range(2):
+                for b in range(2):
+                    Zrho[a][b] = Zrho[2 + a][2 + b] = mpf(R[i][a][b])
+                    Zrho[2 + a][b] = mpf(S[i][a][b])
+                    Zrho[a][2 + b] = -mpf(S[i][a][b])
+            C = [[v / 4 for v in row] for row in Zrho]             # (1/N) (1/2) <Z(rho_i), Z_i>, N = 2
+            blk = PSDBlock(m=1, delta=4, high_rank=True, C=_w(C, prec), name=("E", i + 1))
+            for k, ent in enumerate(structure):
+                blk.dense[len(structure) * i + k] = _w(sym(ent), prec)
+            for k, (ent, _) in enumerate(coupling):
+                blk.dense[2 * len(structure) + k] = _w(sym(ent), prec)
+            blocks.append(blk)
+        c = [mpf(0)] * (2 * len(structure)) + [mpf(rhs) for _, rhs in coupling]
+        cl = Cluster(B=wire.wire_zeros((P, 0), prec), c=_w(c, prec), blocks=blocks)
+        return ClusteredSDP(prec=prec, maximize=True, constant=_w(0, prec), b=wire.wire_zeros((0,), prec), clusters=[cl], name="povm_two_states")
+
+
 # ---------------------------------------------------------------------------
 # config 1: univariate polynomial minimisation (examples/PolyOpt.jl:7-30)
 # ---------------------------------------------------------------------------

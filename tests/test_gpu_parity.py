@@ -516,3 +516,38 @@ def test_two_radii_sphere_packing_d15_prec300_reference_test_on_device():
     with mpmath.workprec(200):
         assert r.status == "Optimal" and 0 < r.p_obj - mpmath.pi ** 4 / 384 < mpmath.mpf(10) ** -4
         assert abs(r.p_obj - mpmath.pi ** 4 / 384 - mpmath.mpf("7.0919e-5")) < mpmath.mpf(10) ** -8
+
+
+@pytest.mark.gpu
+def test_three_point_bound_d14_first_two_iterations_match_the_oracle():
+    """BASELINE config 4 at its largest survey shape (d2 = d3 = 14: P = 894, 61 blocks up to n = 225).  A full oracle solve of it
+    takes hours on the CPUs of the build container (~9 minutes per iteration), so the golden holds the first two iterations:
+    the printed row of each and the objectives of the iterate after them.  The step lengths carry the Float64 eigenvalue, so the
+    comparison is to 1e-7, not to the last bit."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "threepoint_4_14_14_first2.json")
+    if not os.path.exists(path):
+        pytest.skip("golden not generated (tests/golden/make_golden.py threepoint_4_14_14_first2)")
+    import json
+    g = json.load(open(path))
+    sdp = workloads.three_point_bound(4, Fraction(1, 6), 14, 14)
+    assert sdp.describe() == g["describe"]
+    r = solvesdp(sdp, lib="device", duality_gap_threshold=1e-30, maxiterations=2, omega_p=10 ** 3, omega_d=10 ** 3)
+    assert r.iterations == g["iterations"] == 2 and r.error_code == 2
+    for hd, hg in zip(r.history, g["history"]):
+        for k in ("mu", "d_obj", "p_obj", "gap", "err_P", "err_p", "err_d", "alpha_d", "alpha_p", "beta_c", "d_obj_new", "p_obj_new", "gap_new"):
+            assert abs(hd[k] - hg[k]) <= 1e-7 * max(abs(hg[k]), 1e-300), (k, hd[k], hg[k])
+    with mpmath.workprec(300):
+        assert abs(r.d_obj - mpmath.mpf(g["d_obj"])) <= mpmath.mpf(10) ** -7 * abs(mpmath.mpf(g["d_obj"]))
+        assert abs(r.p_obj - mpmath.mpf(g["p_obj"])) <= mpmath.mpf(10) ** -7 * abs(mpmath.mpf(g["p_obj"]))
+
+
+@pytest.mark.gpu
+def test_povm_two_states_on_device():
+    """test/moi_tests.jl:9-10 on the device: 1/2 + sqrt(2)/4 to 1e-30, same iteration count as the oracle (two dense blocks sharing constraints)."""
+    sdp = workloads.povm_two_states()
+    dev = solvesdp(sdp, lib="device", duality_gap_threshold=1e-30)
+    ref = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-30)
+    with mpmath.workprec(300):
+        target = mpmath.mpf(1) / 2 + mpmath.sqrt(2) / 4
+        assert dev.status == "Optimal" and abs(dev.p_obj - target) < mpmath.mpf(10) ** -30 and abs(dev.d_obj - target) < mpmath.mpf(10) ** -30
+        assert abs(dev.iterations - ref.iterations) <= 1 and abs(dev.p_obj - ref.p_obj) < mpmath.mpf(10) ** -25

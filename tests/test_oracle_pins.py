@@ -141,3 +141,12 @@ def test_lovasz_theta_of_the_five_cycle_is_sqrt5():          # test/moi_tests.jl
         assert abs(r.p_obj - mpmath.sqrt(5)) < mpmath.mpf(10) ** -26
         r = solve(workloads.lovasz_theta_cycle(7))
         assert abs(r.p_obj - 7 * mpmath.cos(mpmath.pi / 7) / (1 + mpmath.cos(mpmath.pi / 7))) < mpmath.mpf(10) ** -26
+
+
+def test_povm_two_states_is_half_plus_quarter_sqrt2():       # test/moi_tests.jl:9-10 (example_POVM, atol 1e-30): two dense blocks in one cluster
+    sdp = workloads.povm_two_states()
+    assert sdp.num_constraints == 16 and [b.n for b in sdp.clusters[0].blocks] == [4, 4]
+    r = solve(sdp)
+    with mpmath.workprec(300):
+        target = mpmath.mpf(1) / 2 + mpmath.sqrt(2) / 4
+        assert abs(r.p_obj - target) < mpmath.mpf(10) ** -30 and abs(r.d_obj - target) < mpmath.mpf(10) ** -30
