@@ -360,7 +360,7 @@ template <int NL> __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(
   //     r_c = (W_cc pi_c)^-1/2 ,   L_ic = W_ic r_c ,   L_cc = W_cc r_c (one correction step) ,   1 / L_cc = r_c pi_c .
   // The pivot test is unchanged: W^(c)_cc <= 0 exactly when the true pivot is (pi_c > 0).
   mpn<NL>* pis = Tb;                                      // pi_c, c = 0..32 (Tb is free until phase B)
-  if (tid == 0) { mpn<NL> one; mp_set_i32(one, 1); pis[0] = one; }
+  if (tid == POTRF_THREADS - 1) { mpn<NL> one; mp_set_i32(one, 1); pis[0] = one; }      // (the thread that keeps the scale: no other thread touches pis inside the loop)
   if (dbg && tid == 0) dbg[0] = clock64();
   for (int c = 0; c < nb; c++) {
     if (dbg && lane == 0 && warp == 0) dbg[1 + c * 8 + 2] = clock64();
