@@ -465,6 +465,24 @@ def main():
                     S2.close()
                 except Exception as e:      # a side table must never take the headline down
                     table[name] = {"error": str(e)}
+            # opt-in fast path (SURVEY.md §8(f)2,4; NOT the graded dense path): the same MAX-CUT SDP read from SDPA-sparse text,
+            # uploaded as triplets, Schur complement from the nonzero entries of the A_p (X^-1 o Y)
+            if kind == "maxcut":
+                try:
+                    from clrs_b200 import sdpa, workloads as wl
+                    t0 = time.perf_counter()
+                    s2 = sdpa.sdpa_sparse_to_sdp(sdpa.maxcut_sdpa_text(wl.laplacian_random(args.n, 0.5, 0)), name=f"maxcut(n={args.n}) from SDPA-sparse text")
+                    S2 = Solver(s2, lib="device", device=local_rank, duality_gap_threshold=GAP, sparse_schur=True)
+                    torch.cuda.synchronize()
+                    setup_s = time.perf_counter() - t0
+                    _, dms, _, nl, _, _, info = measure(S2, 4, 3, torch.cuda.synchronize, None, e2e=False)
+                    table["maxcut_sparse_schur"] = {"workload": s2.describe(), "config_index": 1, "value": 4 / (dms / 1e3), "ms_per_step": dms / 4,
+                                                    "gpu_launches_per_step": nl / 4, "setup_seconds": setup_s,
+                                                    "phase_ms": dict(zip(PHASES, [round(v, 4) for v in info.phase_ms])),
+                                                    "note": "clrs_options.sparse_schur = 1 + clrs_add_sparse_term: opt-in shortcut, same optimum as the dense path (tests/test_gpu_sparse.py); the headline above is the dense GEMM path"}
+                    S2.close()
+                except Exception as e:
+                    table["maxcut_sparse_schur"] = {"error": str(e)}
             out["configs"] = table
         # ---- time to duality gap 1e-30 (the second half of BASELINE.json's metric): a full solve from the default start ----
         if kind == "maxcut" and not args.no_time_to_gap:

@@ -44,7 +44,7 @@ class Options(C.Structure):
                 ("step_length_threshold", C.c_double),
                 ("need_dual_feasible", C.c_int32), ("need_primal_feasible", C.c_int32),
                 ("safe_step", C.c_int32), ("correctoronly", C.c_int32),
-                ("device", C.c_int32), ("gemm_path", C.c_int32)]
+                ("device", C.c_int32), ("gemm_path", C.c_int32), ("sparse_schur", C.c_int32)]
 
 
 class IterInfo(C.Structure):
@@ -106,9 +106,11 @@ class Solver:
     """One solver handle (device or oracle) holding one uploaded SDP."""
 
     def __init__(self, sdp: ClusteredSDP, lib: str = "device", device: int = 0, gemm_path: int = 0,
-                 matmul_prec: int = 0, oracle_skip_zeros: bool = False, comm=None, **kwargs):
+                 matmul_prec: int = 0, oracle_skip_zeros: bool = False, comm=None, sparse_schur: bool = False, **kwargs):
         """comm = (rank, nranks, unique_id_bytes): shard the clusters of the SDP over `nranks` handles
-        (one per GPU / process); every rank uploads the same SDP and calls iterate() in lock step."""
+        (one per GPU / process); every rank uploads the same SDP and calls iterate() in lock step.
+        sparse_schur: let dense blocks with sparse constraint matrices form S from the nonzero entries (clrs_options.sparse_schur;
+        off by default: the reference's dense path exploits no sparsity, src/solver.jl:1088)."""
         self.kind = lib
         self.lib = load_library(lib)
         self.pre = _BACKENDS[lib][1]
@@ -134,6 +136,7 @@ class Solver:
             setattr(o, k, int(v))
         o.device = device
         o.gemm_path = gemm_path
+        o.sparse_schur = int(bool(sparse_schur))
         self.h = C.c_void_p()
         self._call("create", C.byref(o), C.byref(self.h), check_handle=False)
         # full-precision overrides: the reference converts these with Arb(v, prec=prec) (src/solver.jl:138-139)
@@ -191,6 +194,11 @@ class Solver:
                            C.c_int32(int(blk.high_rank)), P(blk.C))
                 for p, A in blk.dense.items():
                     self._call("add_dense_term", self.h, C.c_int32(j), C.c_int32(l), C.c_int32(p), P(A))
+                for p, (rows, cols, vals, mirror) in blk.sparse.items():
+                    r32, c32 = np.ascontiguousarray(rows, dtype=np.int32), np.ascontiguousarray(cols, dtype=np.int32)
+                    keep.extend([r32, c32])
+                    self._call("add_sparse_term", self.h, C.c_int32(j), C.c_int32(l), C.c_int32(p), C.c_int32(len(r32)),
+                               r32.ctypes.data_as(C.c_void_p), c32.ctypes.data_as(C.c_void_p), P(vals), C.c_int32(int(mirror)))
                 for t in blk.lowrank:
                     self._call("add_lowrank_term", self.h, C.c_int32(j), C.c_int32(l), C.c_int32(t.r), C.c_int32(t.s),
                                C.c_int32(t.p), C.c_int32(int(t.lam.shape[0])), P(t.lam), P(t.vs), P(t.ws))

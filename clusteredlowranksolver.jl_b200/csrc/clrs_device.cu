@@ -216,6 +216,7 @@ struct SolverBase {
   virtual int add_cluster(int j, int P, const void* B, const void* c) = 0;
   virtual int add_block(int j, int l, int m, int delta, int high_rank, const void* C) = 0;
   virtual int add_dense_term(int j, int l, int p, const void* A) = 0;
+  virtual int add_sparse_term(int j, int l, int p, int nnz, const int32_t* rows, const int32_t* cols, const void* vals, int mirror) = 0;
   virtual int add_lowrank_term(int j, int l, int r, int s, int p, int rank, const void* lam, const void* vs, const void* ws) = 0;
   virtual int finalize() = 0;
   virtual int set_state(const void* x, const void* X, const void* y, const void* Y) = 0;
@@ -611,7 +612,7 @@ template <int NL> struct Solver : SolverBase {
     std::vector<num> hC;
     // dense
     std::vector<int> dense_p; size_t Aall_cap = 0;
-    int np = 0; int32_t* d_plist = nullptr; num* Aall = nullptr; int32_t* nz_start = nullptr; int32_t* nz_idx = nullptr; int32_t* nzT_start = nullptr; int32_t* nzT_p = nullptr; int64_t nnz = 0; Sliced AallB, AallV; num* T1 = nullptr; num* T2 = nullptr; num* Sd = nullptr; Sliced T1S, T2V; bool tri = false;   /* tri: Schur inner products over the packed upper triangle (all A_p symmetric) */
+    int np = 0; int32_t* d_plist = nullptr; num* Aall = nullptr; int32_t* nz_start = nullptr; int32_t* nz_idx = nullptr; int32_t* nzT_start = nullptr; int32_t* nzT_p = nullptr; int64_t nnz = 0; Sliced AallB, AallV; num* T1 = nullptr; num* T2 = nullptr; num* Sd = nullptr; Sliced T1S, T2V; bool sparse = false;   /* sparse: S from the nonzero lists of the A_p (k_schur_sparse), no products */ bool tri = false;   /* tri: Schur inner products over the packed upper triangle (all A_p symmetric) */
     // low rank
     std::vector<HTerm> lr;
     int nP = 0; int32_t* lr_plist = nullptr; int32_t* lr_tstart = nullptr; LRTermDev* lr_terms = nullptr; num* lr_lam = nullptr;
@@ -693,18 +694,39 @@ template <int NL> struct Solver : SolverBase {
     b0.hC.resize((size_t)b0.n * b0.n); for (size_t i = 0; i < b0.hC.size(); i++) w2m(b0.hC[i], (const char*)C + i * wire_size());
     return 0;
   }
-  int add_dense_term(int j, int l, int p_, const void* A) override {
-    if (j < 0 || j >= (int)cl.size() || l < 0 || l >= (int)cl[j].blocks.size()) { err = "clrs_add_dense_term: no such block"; return CLRS_ERR_ARG; }
-    if (p_ < 0 || p_ >= cl[j].P) { err = "clrs_add_dense_term: constraint row out of range"; return CLRS_ERR_ARG; }
-    Block& b0 = cl[j].blocks[l]; if (!b0.high_rank) { err = "dense term on a low-rank block"; return CLRS_ERR_ARG; }
-    // the matrix goes to the device as raw wire bytes and is converted there (27e6 numbers for the BASELINE workload: a host
-    // loop over them cost more than the whole upload); the buffer of the block grows geometrically
+  // next n x n slot of the block's dense constraint buffer (grown geometrically, at most P_j slots)
+  num* dense_slot(int j, Block& b0) {
     const size_t nn = (size_t)b0.n * b0.n, have = b0.dense_p.size();
     if (have + 1 > b0.Aall_cap) { const size_t cap = std::max<size_t>(8, std::min<size_t>(2 * b0.Aall_cap, (size_t)cl[j].P)); const size_t ncap = std::max(cap, have + 1);
       num* nb_ = nullptr; CK(cudaMalloc((void**)&nb_, ncap * nn * sizeof(num))); allocs.push_back(nb_);
       if (b0.Aall) { CK(cudaMemcpyAsync(nb_, b0.Aall, have * nn * sizeof(num), cudaMemcpyDeviceToDevice, st)); CK(cudaStreamSynchronize(st)); release(b0.Aall); }
       b0.Aall = nb_; b0.Aall_cap = ncap; }
-    wire_to_device(b0.Aall + have * nn, A, nn);
+    return b0.Aall + have * nn;
+  }
+  int add_dense_term(int j, int l, int p_, const void* A) override {
+    if (j < 0 || j >= (int)cl.size() || l < 0 || l >= (int)cl[j].blocks.size()) { err = "clrs_add_dense_term: no such block"; return CLRS_ERR_ARG; }
+    if (p_ < 0 || p_ >= cl[j].P) { err = "clrs_add_dense_term: constraint row out of range"; return CLRS_ERR_ARG; }
+    Block& b0 = cl[j].blocks[l]; if (!b0.high_rank) { err = "dense term on a low-rank block"; return CLRS_ERR_ARG; }
+    // the matrix goes to the device as raw wire bytes and is converted there (27e6 numbers for the BASELINE workload: a host
+    // loop over them cost more than the whole upload)
+    wire_to_device(dense_slot(j, b0), A, (size_t)b0.n * b0.n);
+    b0.dense_p.push_back(p_);
+    return 0;
+  }
+  // the same constraint matrix given by its nonzero entries (SDPA-sparse input, src/SDPAtoCLRS.jl:3-31): only the triplets cross
+  // PCIe (MAX-CUT n = 300: 300 numbers instead of 27e6), the dense slot is zeroed and filled on the device
+  int add_sparse_term(int j, int l, int p_, int nnz, const int32_t* rows, const int32_t* cols, const void* vals, int mirror) override {
+    if (j < 0 || j >= (int)cl.size() || l < 0 || l >= (int)cl[j].blocks.size()) { err = "clrs_add_sparse_term: no such block"; return CLRS_ERR_ARG; }
+    if (p_ < 0 || p_ >= cl[j].P || nnz < 0) { err = "clrs_add_sparse_term: constraint row out of range"; return CLRS_ERR_ARG; }
+    Block& b0 = cl[j].blocks[l]; if (!b0.high_rank) { err = "sparse term on a low-rank block"; return CLRS_ERR_ARG; }
+    for (int t = 0; t < nnz; t++) if (rows[t] < 0 || rows[t] >= b0.n || cols[t] < 0 || cols[t] >= b0.n) { err = "clrs_add_sparse_term: entry out of range"; return CLRS_ERR_ARG; }
+    num* slot = dense_slot(j, b0); const size_t nn = (size_t)b0.n * b0.n;
+    CK(cudaMemsetAsync(slot, 0, nn * sizeof(num), st));                  // all-zero bytes are the number 0 (sign = 0)
+    if (nnz > 0) { int32_t* drc = nullptr; num* dv = nullptr; CK(cudaMalloc((void**)&drc, 2 * (size_t)nnz * sizeof(int32_t))); CK(cudaMalloc((void**)&dv, (size_t)nnz * sizeof(num)));
+      CK(cudaMemcpyAsync(drc, rows, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(drc + nnz, cols, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      wire_to_device(dv, vals, (size_t)nnz);
+      nlaunch++, k_scatter_triplets<NL><<<(nnz + 127) / 128, 128, 0, st>>>(nnz, drc, drc + nnz, dv, b0.n, mirror, slot);
+      CK(cudaStreamSynchronize(st)); CK(cudaFree(drc)); CK(cudaFree(dv)); }
     b0.dense_p.push_back(p_);
     return 0;
   }
@@ -801,7 +823,15 @@ template <int NL> struct Solver : SolverBase {
         for (int i = 0; i < b0.np; i++) for (int32_t q = st_[i]; q < st_[i + 1]; q++) tp[fill[idx[q]]++] = i;       // ascending p per position
         b0.nnz = (int64_t)idx.size(); b0.nz_start = upload(st_); b0.nz_idx = upload(idx); b0.nzT_start = upload(tcount); b0.nzT_p = upload(tp); }
       if (!b0.Aall) b0.Aall = dalloc<num>(1);
-      b0.T1 = dalloc<num>((size_t)b0.np * n * n); b0.T2 = dalloc<num>((size_t)b0.np * n * n); b0.Sd = dalloc<num>((size_t)b0.np * b0.np);
+      b0.Sd = dalloc<num>((size_t)b0.np * b0.np);
+      { // opt-in sparsity shortcut: 3 multiplications per pair of nonzero entries on the CUDA cores against the two
+        // n^3 products per constraint + the inner products on the tensor cores (roughly 4 x the multi-precision multiply rate)
+        static const int sp_env = getenv("CLRS_SPARSE_SCHUR") ? atoi(getenv("CLRS_SPARSE_SCHUR")) : -1;
+        const bool want = sp_env >= 0 ? sp_env != 0 : opt.sparse_schur != 0;
+        const double dense_macs = 2.0 * b0.np * (double)n * n * n + 0.5 * (double)b0.np * b0.np * n * n, sparse_macs = 1.5 * (double)b0.nnz * (double)b0.nnz;
+        b0.sparse = want && b0.np > 0 && 4.0 * sparse_macs < dense_macs; }
+      if (b0.sparse) return 0;
+      b0.T1 = dalloc<num>((size_t)b0.np * n * n); b0.T2 = dalloc<num>((size_t)b0.np * n * n);
       own(b0.AallB); own(b0.AallV); own(b0.T1S); own(b0.T2V);
       if (b0.np > 0) {
         VecView v; v.base = b0.Aall; v.bstride = (int64_t)n * n; v.vper = n; v.sv = 1; v.sk = n; v.nvec = b0.np * n; v.K = n; split(b0.AallB, v, false, b0.lay);   // columns of every A_p
@@ -980,7 +1010,7 @@ template <int NL> struct Solver : SolverBase {
   // <A_q, X^-1 A_p Y> = <A_q, (X^-1 W_p)^T> with W_p = A_p Y.  W_p needs only Y, so the first of the two 90000-row products
   // is issued BEFORE the Cholesky factorisation of X, on a low-priority side stream, and fills the SMs that the single-CTA
   // panel chain of chol(X) leaves idle (the main stream has the highest priority, so its kernels take the next SM that frees).
-  bool staged(const Block& b0) const { static const int off = getenv("CLRS_SCHUR_STAGED") ? atoi(getenv("CLRS_SCHUR_STAGED")) == 0 : 0; return !off && b0.high_rank && b0.tri && b0.lay == 1 && b0.np > 0; }
+  bool staged(const Block& b0) const { static const int off = getenv("CLRS_SCHUR_STAGED") ? atoi(getenv("CLRS_SCHUR_STAGED")) == 0 : 0; return !off && b0.high_rank && !b0.sparse && b0.tri && b0.lay == 1 && b0.np > 0; }
   int dense_chunk(const Block& b0, int nsm = 148) {   // constraints per chunk: two rounds of tiles on nsm SMs (n = 300: 63 on 148 SMs)
     static const int chunks_off = getenv("CLRS_SCHUR_CHUNKS") ? atoi(getenv("CLRS_SCHUR_CHUNKS")) == 1 : 0;
     const int n = b0.n, np = b0.np;
@@ -1043,13 +1073,17 @@ template <int NL> struct Solver : SolverBase {
     // S[p,q] += sum_ab T2_p[ab] A_q[ab]
     gemm(b0.AallV, 0, b0.T2V, 0, np, np, b0.Sd, np, 0, nullptr, 0, 1, 0, 0, 0, 0, 1);          // Sd[q][p], q >= p only
   }
+  void schur_sparse(Block& b0) {                     // Sd[q][p], q >= p, from the nonzero entries of the A_p (k_schur_sparse)
+    const int np = b0.np; if (np == 0) return;
+    nlaunch++, k_schur_sparse<NL><<<(unsigned)(((int64_t)np * np * 32 + 255) / 256), 256, 0, st>>>(np, b0.n, b0.nz_start, b0.nz_idx, b0.Aall, Xi + b0.off, Y + b0.off, b0.Sd);
+  }
   void schur_add_dense(Clu& c0, Block& b0) {
     const int np = b0.np; if (np == 0) return;
     nlaunch++, k_scatter_upper<NL><<<(unsigned)(((int64_t)np * np + 127) / 128), 128, 0, st>>>(np, b0.d_plist, b0.Sd, c0.S, c0.P);
   }
   void decomposition(int e0) {
     if (stage1_pending) { CK(cudaStreamWaitEvent(st, evS1, 0)); stage1_pending = false; }
-    par_blocks([&](Block* b0) { if (staged(*b0)) dense_stage2(*b0); else if (b0->high_rank) pairings_dense(*b0); else pairings_lowrank(*b0); });
+    par_blocks([&](Block* b0) { if (b0->sparse) schur_sparse(*b0); else if (staged(*b0)) dense_stage2(*b0); else if (b0->high_rank) pairings_dense(*b0); else pairings_lowrank(*b0); });
     par_clusters([&](Clu& c0) { zero(c0.S, (int64_t)c0.P * c0.P);
       for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_add_dense(c0, b0); else schur_add_lowrank(c0, b0); }
       if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); });
@@ -1391,6 +1425,7 @@ template <int NL> struct Solver : SolverBase {
   }
   int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) override {
     std::string w(what); const num* src = nullptr; int64_t n = 0;
+    if (w == "sparse?") return (j >= 0 && j < (int)cl.size() && l >= 0 && l < (int)cl[j].blocks.size() && cl[j].blocks[l].sparse) ? 1 : 0;   // which Schur path the block takes (tests)
     if (j >= 0 && j < (int)cl.size() && !cl[j].owned && (w == "S" || w == "LinvB" || w.size() > 2 || w == "X" || w == "Y" || w == "R" || w == "P" || w == "L")) return -1;
     if (w == "S") { src = cl[j].S; n = (int64_t)cl[j].P * cl[j].P; } else if (w == "LinvB") { if (cl[j].big) return -1; src = cl[j].LinvB; n = (int64_t)cl[j].P * N; }
     else if (w == "Q") { src = Q; n = (int64_t)N * N; } else if (w == "d") { src = d; n = Ptot; } else if (w == "p") { src = p; n = N; }
@@ -1429,6 +1464,7 @@ int clrs_set_free(clrs_handle* h, int32_t N, const void* b, const void* c, int32
 int clrs_add_cluster(clrs_handle* h, int32_t j, int32_t P, const void* B, const void* c) { GUARD(h, return h->s->add_cluster(j, P, B, c);) }
 int clrs_add_block(clrs_handle* h, int32_t j, int32_t l, int32_t m, int32_t delta, int32_t hr, const void* C) { GUARD(h, return h->s->add_block(j, l, m, delta, hr, C);) }
 int clrs_add_dense_term(clrs_handle* h, int32_t j, int32_t l, int32_t p, const void* A) { GUARD(h, return h->s->add_dense_term(j, l, p, A);) }
+int clrs_add_sparse_term(clrs_handle* h, int32_t j, int32_t l, int32_t p, int32_t nnz, const int32_t* rows, const int32_t* cols, const void* vals, int32_t mirror) { GUARD(h, return h->s->add_sparse_term(j, l, p, nnz, rows, cols, vals, mirror);) }
 int clrs_add_lowrank_term(clrs_handle* h, int32_t j, int32_t l, int32_t r, int32_t s, int32_t p, int32_t rank, const void* lam, const void* vs, const void* ws) { GUARD(h, return h->s->add_lowrank_term(j, l, r, s, p, rank, lam, vs, ws);) }
 int clrs_finalize(clrs_handle* h) { GUARD(h, return h->s->finalize();) }
 int clrs_set_state(clrs_handle* h, const void* x, const void* X, const void* y, const void* Y) { GUARD(h, return h->s->set_state(x, X, y, Y);) }

