@@ -81,7 +81,8 @@ def config(n, n_gpus, kind="maxcut", sdp=None):
     if kind != "maxcut":
         return {"workload": f"{sdp.describe() if sdp is not None else kind} (BASELINE.json configs[{CONFIG_INDEX[kind]}])",
                 "step": "one predictor-corrector IPM iteration", "l2": "L2 flushed by the iteration's own temporaries only; latency-bound small blocks",
-                "parallelism": ("clusters sharded over ranks (LPT on P^3 + sum n^3), NCCL on the free-variable coupling (Q, u, p) and scalars" if kind.startswith("sphere") else "replicas only") if n_gpus > 1 else "single GPU"}
+                "parallelism": ("clusters sharded over ranks (LPT on P^3 + sum n^3), NCCL on the free-variable coupling (Q, u, p) and scalars" if kind.startswith("sphere") else
+                                "one cluster: its PSD blocks sharded over ranks (LPT on n^3), S_j and <A_*,.> all-reduced, factor and solves replicated" if kind.startswith("threepoint") else "replicas only") if n_gpus > 1 else "single GPU"}
     return {"workload": f"GW MAX-CUT relaxation, G({n},0.5) numpy default_rng(0), dense constraint path "
                         f"(BASELINE.json configs[1]), prec=256, J=1 P={n} one dense block {n}x{n}, N=0",
             "step": "one predictor-corrector IPM iteration", "l2": "working set (~7 GB of slices/temporaries) exceeds the 126 MB L2",
@@ -330,7 +331,7 @@ def main():
         its, threads, desc = cpu_arm(args.n, max(1, args.steps), max(0, min(args.warmup, 1)), kind=kind)
         sdp = workload(args.n, kind) if kind != "maxcut" else None
         print(file=real_stdout, flush=True, *[json.dumps({"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "strong" if (kind.startswith("sphere") and n_gpus > 1) else "weak", "vs_baseline": None,
+                          "warmup": args.warmup, "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "strong" if ((kind.startswith("sphere") or kind.startswith("threepoint")) and n_gpus > 1) else "weak", "vs_baseline": None,
                           "dtype": "mpfr (cpu)", "data": "synthetic", "config": config(args.n, args.gpus, kind, sdp),
                           "cpu_baseline": {"value": its, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc, "host_cpus": os.cpu_count()},
                           "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
@@ -350,7 +351,7 @@ def main():
     import clrs_b200
     from clrs_b200 import Solver
     sdp = workload(args.n, kind)
-    sharded = world > 1 and kind in ("sphere", "sphere2", "sphere8")
+    sharded = world > 1 and kind in ("sphere", "sphere2", "sphere8", "threepoint", "threepoint14")      # clusters / blocks of a split cluster over the ranks
     comm = None
     if sharded:                 # one communicator over the ranks; the id travels through torch.distributed
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")

@@ -282,7 +282,11 @@ class Solver:
         """Bytes of (x, X, y, Y) this handle reads in set_state / writes in get_state: the clusters it owns plus y."""
         n = self.sdp.N
         for j, cl in enumerate(self.sdp.clusters):
-            if self.kind == "device" and self.nranks > 1 and self.cluster_owner(j) != self.rank:
+            if self.kind == "device" and self.nranks > 1:
+                mine = [b for l, b in enumerate(cl.blocks) if self.block_owner(j, l) == self.rank]
+                if not mine and self.cluster_owner(j) != self.rank:
+                    continue
+                n += cl.P + 2 * sum(b.n * b.n for b in mine)
                 continue
             n += cl.P + 2 * sum(b.n * b.n for b in cl.blocks)
         return n * self.dtype.itemsize
@@ -290,6 +294,11 @@ class Solver:
     def cluster_owner(self, j: int) -> int:
         fn = self._fn("cluster_owner"); fn.restype = C.c_int
         return int(fn(self.h, C.c_int32(j)))
+
+    def block_owner(self, j: int, l: int) -> int:
+        """Rank that holds block l of cluster j (differs from cluster_owner(j) only inside a split cluster)."""
+        fn = self._fn("block_owner"); fn.restype = C.c_int
+        return int(fn(self.h, C.c_int32(j), C.c_int32(l)))
 
     # -- measurement hooks (device library only) ------------------------------
     def profile(self, enable: bool):

@@ -235,6 +235,7 @@ struct SolverBase {
   virtual int comm_init(int rank, int nranks, const void* uid) = 0;
   virtual int selftest() = 0;
   virtual int owner_of(int j) = 0;
+  virtual int block_owner_of(int j, int l) = 0;
   size_t wire_size() const { return 16 + 8 * (size_t)((prec + 63) / 64); }
 };
 
@@ -373,6 +374,7 @@ template <int NL> struct Solver : SolverBase {
     // column tiles (N = 641) the three-diagonal groups lose to wave quantisation: wide tiles only for one or two of them
     if (force == 4 || bnB <= 128 || (force != 3 && (ntB > 2 || cost(bnA) <= cost(bnB) * 1.02))) { BN = bnA; group = 4; } else { BN = bnB; group = 3; }
   }
+  static int tc_epi() { static const int v = getenv("CLRS_TC_EPI") ? atoi(getenv("CLRS_TC_EPI")) : 0; return v; }   // epilogue variant of tc::k_gemm_tc (gemm_tc.cuh)
   void gemm_tc(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode, const num* D, int ldd,
                int batch, int64_t a_bvec, int64_t b_bvec, int64_t c_bs, int64_t d_bs, int lower_only, int trans = 0) {
     if (a0 != 0 || b0 != 0) throw CudaError("gemm_tc: panel offsets are not supported");
@@ -388,7 +390,7 @@ template <int NL> struct Solver : SolverBase {
     if (nch > 1 && batch != 1) throw CudaError("gemm_tc: split-K with a batch is not supported");
     int kch = ((A.Kp + nch - 1) / nch + 127) & ~127; nch = (A.Kp + kch - 1) / kch;
     tc::Args a; a.M = M; a.N = N; a.Kp = A.Kp; a.k0 = 0; a.BN = BN; a.group = group; a.dsplit = 0; a.oraw = nullptr; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch;
-    a.lower_only = lower_only; a.Kp_total = A.Kp; a.dbg = nullptr;
+    a.lower_only = lower_only; a.Kp_total = A.Kp; a.dbg = nullptr; a.epi = tc_epi();
     // under-parallelised products (a few tiles on 148 SMs): one CTA per (tile, K range, diagonal group), raw int32 sums
     // accumulated with red.add, carries resolved in k_tc_recombine_raw
     static const int dsplit_off = getenv("CLRS_TC_DSPLIT") ? atoi(getenv("CLRS_TC_DSPLIT")) == 0 : 0;
@@ -476,6 +478,7 @@ template <int NL> struct Solver : SolverBase {
     rank = rank_; nranks = nranks_; gflags = dalloc<int>((size_t)nranks * FL_COUNT); return CLRS_OK;
   }
   int owner_of(int j) override { return (j >= 0 && j < (int)cl.size()) ? cl[j].owner : -1; }
+  int block_owner_of(int j, int l) override { return (j >= 0 && j < (int)cl.size() && l >= 0 && l < (int)cl[j].blocks.size()) ? cl[j].blocks[l].brank : -1; }
   long long* lane_buf = nullptr; int32_t* lane_E = nullptr; size_t lane_cap = 0;
   void allreduce(num* v, int64_t n, int op) {      // op 0 sum, 1 max-abs, 2 min
     if (nranks == 1 || n == 0) return;
@@ -608,6 +611,7 @@ template <int NL> struct Solver : SolverBase {
   struct HTerm { int r, s, p, k; num lam; std::vector<num> v, w; int colV = -1, rowW = -1; };
   struct Block {
     int j = 0, l = 0, m = 1, delta = 1, n = 1; bool high_rank = false; int64_t off = 0;   // offset in the flat block storage (owned blocks)
+    bool mine = true; int brank = 0;                                                      // split clusters: the rank that holds this block
     int64_t goff = 0;                                                                      // offset in the global (all ranks) block order
     std::vector<num> hC;
     // dense
@@ -624,7 +628,7 @@ template <int NL> struct Solver : SolverBase {
     // per-iteration cached panels (layout `lay`: 1 = tensor-core panels for large blocks)
     Sliced YS, XiS, MS, MSY; int lay = 0;
   };
-  struct Clu { int owner = 0; bool owned = true; int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; unsigned* ready = nullptr; int off = 0;
+  struct Clu { int owner = 0; bool owned = true; bool split = false, lead = true;   /* split: the BLOCKS of this cluster are spread over the ranks; S_j, x_j, B_j, the factor and the solves are replicated, `lead` (= the owner) alone adds the cluster-level terms to cross-rank sums */ int P = 0; std::vector<num> hB, hc; std::vector<Block> blocks; num *B = nullptr, *S = nullptr, *Minv = nullptr, *LinvB = nullptr, *t = nullptr; unsigned* ready = nullptr; int off = 0;
                bool big = false; num *Bc = nullptr, *Gc = nullptr, *Qs = nullptr; };   /* big: L^-1 B and its Q contribution are split by COLUMNS over all ranks: Bc = this rank's columns of B (P x ncr), Gc = all column chunks of L^-1 B ([rank][P][ncr]), Qs = this rank's N x ncr slab of G^T G */
   std::vector<Clu> cl; std::vector<Block*> blk;   // blk: all blocks in (j,l) order
   int N = 0, Ptot = 0, Ksum = 0, maximize = 1; std::vector<num> hb; num hconst;
@@ -633,7 +637,7 @@ template <int NL> struct Solver : SolverBase {
   // device state
   num *X = nullptr, *Y = nullptr, *Cm = nullptr, *L = nullptr, *Minv = nullptr, *Xi = nullptr, *R = nullptr, *P = nullptr, *dX = nullptr, *dY = nullptr, *T1 = nullptr, *TXY = nullptr, *U = nullptr;
   num* tmpU = nullptr; num* LinvBall = nullptr; int Pown = 0; unsigned* q_ready = nullptr; int ncr = 0;   /* ncr: columns of B per rank for big clusters */
-  num *x = nullptr, *y = nullptr, *c = nullptr, *b = nullptr, *d = nullptr, *p = nullptr, *dx = nullptr, *dy = nullptr, *tr = nullptr, *Q = nullptr, *QMinv = nullptr, *tmpN = nullptr;
+  num *x = nullptr, *y = nullptr, *c = nullptr, *cobj = nullptr, *b = nullptr, *d = nullptr, *p = nullptr, *dx = nullptr, *dy = nullptr, *tr = nullptr, *Q = nullptr, *QMinv = nullptr, *tmpN = nullptr;
   num* sc = nullptr; int* flags = nullptr; double* dinfo = nullptr; double* Td = nullptr; double* lamX = nullptr; double* lamY = nullptr; double* eigV = nullptr; EigTask* eigT = nullptr;
   int64_t* d_boff = nullptr; int32_t* d_bn = nullptr; BlockTab bt;
   num hopt[10]; bool hopt_set[10] = {false};
@@ -752,10 +756,27 @@ template <int NL> struct Solver : SolverBase {
   // ---- finalize: build tables (precompute_matrices_bilinear_pairings, src/solver.jl:985-1059), allocate, initialise ----
   int finalize() override {
     Ptot = 0; Ksum = 0; tot = 0; gtot = 0; blk.clear();
-    { std::vector<double> wgt; for (auto& c0 : cl) { double w = (double)c0.P * c0.P * c0.P; for (auto& b0 : c0.blocks) { double n3 = (double)b0.n * b0.n * b0.n; w += n3 * (b0.high_rank ? 2.0 * b0.dense_p.size() + 15 : 15); } wgt.push_back(w); }
-      std::vector<int> owner; partition_clusters(wgt, nranks, owner); for (size_t j = 0; j < cl.size(); j++) { cl[j].owner = owner[j]; cl[j].owned = owner[j] == rank; } }
+    { // work items of the partition: whole clusters (weights P^3 + sum n^3, src/threadinginfo.jl:88,97) — except that a cluster that alone
+      // outweighs a rank's fair share and has several blocks is SPLIT: its blocks become items of their own (§8(e)(i): config 4 is one
+      // cluster of 49-61 blocks), while its Schur complement, factor and solves are replicated on every rank
+      static const int split_env = getenv("CLRS_SPLIT_BLOCKS") ? atoi(getenv("CLRS_SPLIT_BLOCKS")) : -1;      // 0 never, 1 every multi-block cluster, default by weight
+      static const int bigp0 = getenv("CLRS_BIG_CLUSTER") ? atoi(getenv("CLRS_BIG_CLUSTER")) : 512;
+      auto bw = [](const Block& b0) { const double n3 = (double)b0.n * b0.n * b0.n; return n3 * (b0.high_rank ? 2.0 * b0.dense_p.size() + 15 : 15); };
+      std::vector<double> cw; double total = 0; for (auto& c0 : cl) { double w = (double)c0.P * c0.P * c0.P; for (auto& b0 : c0.blocks) w += bw(b0); cw.push_back(w); total += w; }
+      std::vector<double> wgt; std::vector<std::pair<int, int>> item;                    // (cluster, block or -1)
+      for (size_t j = 0; j < cl.size(); j++) { Clu& c0 = cl[j];
+        const bool bigc = nranks > 1 && N > 0 && bigp0 > 0 && c0.P >= bigp0;            // column-split clusters keep their blocks together
+        c0.split = nranks > 1 && !bigc && c0.blocks.size() >= 2 && split_env != 0 && (split_env == 1 || cw[j] > 1.25 * total / nranks);
+        if (!c0.split) { wgt.push_back(cw[j]); item.push_back({(int)j, -1}); continue; }
+        for (size_t l = 0; l < c0.blocks.size(); l++) { wgt.push_back(bw(c0.blocks[l])); item.push_back({(int)j, (int)l}); } }
+      std::vector<int> owner; partition_clusters(wgt, nranks, owner);
+      for (auto& c0 : cl) { c0.owner = -1; }
+      for (size_t i = 0; i < item.size(); i++) { Clu& c0 = cl[item[i].first];
+        if (item[i].second < 0) { c0.owner = owner[i]; c0.owned = owner[i] == rank; c0.lead = c0.owned; for (auto& b0 : c0.blocks) { b0.brank = owner[i]; b0.mine = c0.owned; } }
+        else { Block& b0 = c0.blocks[item[i].second]; b0.brank = owner[i]; b0.mine = owner[i] == rank; if (c0.owner < 0) c0.owner = owner[i]; c0.owned = true; c0.lead = c0.owner == rank; } }
+      for (auto& c0 : cl) if (c0.owner < 0) { c0.owner = 0; c0.owned = rank == 0; c0.lead = c0.owned; } }
     for (auto& c0 : cl) { c0.off = Ptot; Ptot += c0.P;
-      for (auto& b0 : c0.blocks) { Ksum += b0.n; b0.goff = gtot; gtot += (int64_t)b0.n * b0.n; if (c0.owned) { b0.off = tot; tot += (int64_t)b0.n * b0.n; blk.push_back(&b0); } } }
+      for (auto& b0 : c0.blocks) { Ksum += b0.n; b0.goff = gtot; gtot += (int64_t)b0.n * b0.n; if (c0.owned && b0.mine) { b0.off = tot; tot += (int64_t)b0.n * b0.n; blk.push_back(&b0); } } }
     std::vector<int64_t> boff; std::vector<int32_t> bn; for (Block* b0 : blk) { boff.push_back(b0->off); bn.push_back(b0->n); } boff.push_back(tot);
     d_boff = upload(boff); d_bn = upload(bn); bt.off = d_boff; bt.n = d_bn; bt.nblocks = (int)blk.size();
     num** flat[] = {&X, &Y, &Cm, &L, &Minv, &Xi, &R, &P, &dX, &dY, &T1, &TXY, &U, &LY, &MinvY};
@@ -763,7 +784,9 @@ template <int NL> struct Solver : SolverBase {
     { std::vector<num> hC(tot); for (Block* b0 : blk) std::copy(b0->hC.begin(), b0->hC.end(), hC.begin() + b0->off); CK(cudaMemcpyAsync(Cm, hC.data(), tot * sizeof(num), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
     x = dalloc<num>(Ptot); d = dalloc<num>(Ptot); dx = dalloc<num>(Ptot); tr = dalloc<num>(Ptot);
     y = dalloc<num>(N); p = dalloc<num>(N); dy = dalloc<num>(N); tmpN = dalloc<num>(N); Q = dalloc<num>((size_t)N * N); QMinv = dalloc<num>((size_t)N * N);
-    { std::vector<num> hc; num z; mp_zero(z); for (auto& c0 : cl) { if (c0.owned) hc.insert(hc.end(), c0.hc.begin(), c0.hc.end()); else hc.insert(hc.end(), c0.P, z); } c = upload(hc); b = upload(hb); }   // c of clusters owned elsewhere reads as 0
+    { std::vector<num> hc, hco; num z; mp_zero(z); for (auto& c0 : cl) { if (c0.owned) hc.insert(hc.end(), c0.hc.begin(), c0.hc.end()); else hc.insert(hc.end(), c0.P, z);
+        if (c0.owned && c0.lead) hco.insert(hco.end(), c0.hc.begin(), c0.hc.end()); else hco.insert(hco.end(), c0.P, z); }
+      c = upload(hc); cobj = upload(hco); b = upload(hb); }   // c of clusters owned elsewhere reads as 0; cobj: <c,x> is summed over the ranks, a split cluster counts once
     tmpU = dalloc<num>(N); q_ready = dalloc<unsigned>((size_t)(N + 31) / 32 + 1);
     Td = dalloc<double>(tot); lamX = dalloc<double>(blk.size()); lamY = dalloc<double>(blk.size());
     { std::vector<EigTask> et; size_t vtot = 0; for (Block* b0 : blk) vtot += (size_t)b0->n * (std::min(b0->n, EIG_MMAX) + 1); eigV = dalloc<double>(vtot); size_t o = 0;
@@ -777,9 +800,10 @@ template <int NL> struct Solver : SolverBase {
     static const int bigp = getenv("CLRS_BIG_CLUSTER") ? atoi(getenv("CLRS_BIG_CLUSTER")) : 512;
     ncr = nranks > 1 ? (N + nranks - 1) / nranks : N;
     for (auto& c0 : cl) c0.big = nranks > 1 && N > 0 && bigp > 0 && c0.P >= bigp;
-    Pown = 0; for (auto& c0 : cl) if (c0.owned && !c0.big) Pown += c0.P;
+    Pown = 0; for (auto& c0 : cl) if (c0.owned && c0.lead && !c0.big) Pown += c0.P;
     LinvBall = dalloc<num>((size_t)Pown * N);
-    { int64_t o = 0; for (auto& c0 : cl) if (c0.owned && !c0.big) { c0.LinvB = LinvBall + o * N; o += c0.P; } }
+    { int64_t o = 0; for (auto& c0 : cl) if (c0.owned && c0.lead && !c0.big) { c0.LinvB = LinvBall + o * N; o += c0.P; } }
+    for (auto& c0 : cl) if (c0.owned && !c0.lead && !c0.big) c0.LinvB = dalloc<num>((size_t)c0.P * N);
     for (auto& c0 : cl) {
       if (c0.big) {                                                    // on every rank: the factor, this rank's columns of B, all chunks of G, the Q slab
         std::vector<num> hBc((size_t)c0.P * ncr); num z; mp_zero(z);
@@ -789,7 +813,7 @@ template <int NL> struct Solver : SolverBase {
       }
       if (!c0.owned) { for (auto& b0 : c0.blocks) if (b0.Aall) { release(b0.Aall); b0.Aall = nullptr; } continue; }   // uploaded before the partition was known
       c0.B = upload(c0.hB); c0.S = dalloc<num>((size_t)c0.P * c0.P); c0.Minv = dalloc<num>((size_t)c0.P * c0.P); c0.t = dalloc<num>(c0.P); c0.ready = dalloc<unsigned>((size_t)(c0.P + 31) / 32 + 1);
-      for (auto& b0 : c0.blocks) if (int rc = finalize_block(c0, b0)) return rc;
+      for (auto& b0 : c0.blocks) { if (!b0.mine) { if (b0.Aall) { release(b0.Aall); b0.Aall = nullptr; } continue; } if (int rc = finalize_block(c0, b0)) return rc; }
     }
     // scalars
     { std::vector<num> h(SC_COUNT); for (auto& v : h) mp_zero(v);
@@ -923,20 +947,24 @@ template <int NL> struct Solver : SolverBase {
       if (b0.high_rank || b0.nP == 0) return;
       for (int r = 0; r < m; r++) for (int s = 0; s <= r; s++) { if (b0.rs[r * m + s].cnt == 0) continue;
         split_rows(tA, Zb + (int64_t)r * dl * n + (int64_t)s * dl, n, dl, dl); gemm(tA, 0, b0.Vs[r], 0, dl, b0.u_r[r], b0.ZV[r * m + s], b0.u_r[r]); } });
-    par_clusters([&](Clu& c0) { for (auto& b0 : c0.blocks) {                                        // blocks of one cluster add into the same rows: in order
+    par_clusters([&](Clu& c0) { for (auto& b0 : c0.blocks) { if (!b0.mine) continue;               // blocks of one cluster add into the same rows: in order
       const num* Zb = Z + b0.off; const int n = b0.n, m = b0.m, dl = b0.delta; num* oj = out + c0.off;
       if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)n * n, b0.nz_start, b0.nz_idx, Zb, oj); continue; }
       if (b0.nP == 0) continue;
       nlaunch++, k_trace_vectors<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_W, b0.d_ZV, m, dl, oj);
     } });
+    sum_split_rows(out);
   }
   // out[p] = <A_p, Y> from the stored pairings (src/solver.jl:1368-1407)
   void trace_pairings(num* out) {
     zero(out, Ptot);
-    par_clusters([&](Clu& c0) { for (auto& b0 : c0.blocks) { num* oj = out + c0.off;
+    par_clusters([&](Clu& c0) { for (auto& b0 : c0.blocks) { if (!b0.mine) continue; num* oj = out + c0.off;
       if (b0.high_rank) { if (b0.np) nlaunch++, k_trace_dense<NL><<<b0.np, 128, 128 * sizeof(num), st>>>(b0.np, b0.d_plist, b0.Aall, (int64_t)b0.n * b0.n, b0.nz_start, b0.nz_idx, Y + b0.off, oj); continue; }
       if (b0.nP) nlaunch++, k_trace_pairings<NL><<<(b0.nP + 63) / 64, 64, 0, st>>>(b0.nP, b0.lr_plist, b0.lr_tstart, b0.lr_terms, b0.lr_lam, b0.d_BY, b0.m, oj); } });
+    sum_split_rows(out);
   }
+  // rows of a split cluster hold this rank's blocks only: summed over the ranks (main stream, cluster order: the same order on every rank)
+  void sum_split_rows(num* out) { if (nranks > 1) for (auto& c0 : cl) if (c0.split && c0.P) allreduce(out + c0.off, c0.P, 0); }
   // P, d, p  (compute_residuals!, src/solver.jl:863-918); `tr` must hold <A_*, Y>
   void residuals() {
     weighted_A(P, x);
@@ -946,13 +974,13 @@ template <int NL> struct Solver : SolverBase {
     if (N > 0) for (auto& c0 : cl) if (c0.owned && c0.P) nlaunch++, k_gemv_n<NL><<<(c0.P * 32 + 255) / 256, 256, 0, st>>>(c0.P, N, c0.B, N, y, d + c0.off, -1, 1);
     // p = +-b - sum_j B_j^T x_j   (partial sums over the owned clusters, combined over the ranks)
     if (N > 0) { zero(p, N);
-      for (auto& c0 : cl) if (c0.owned && c0.P) nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1);
+      for (auto& c0 : cl) if (c0.owned && c0.lead && c0.P) nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.B, N, x + c0.off, p, -1, 1);
       allreduce(p, N, 0);
       addsub(p, p, 1, b, maximize ? 1 : -1, N); }
   }
   void errors() { reduce(P, nullptr, tot, sc + SC_ERRP, 0); allreduce(sc + SC_ERRP, 1, 1); reduce(p, nullptr, N, sc + SC_ERRp, 0); reduce(d, nullptr, Ptot, sc + SC_ERRd, 0); allreduce(sc + SC_ERRd, 1, 1); }
   void objectives() {
-    reduce(c, x, Ptot, sc + SC_CX, 0); reduce(Cm, Y, tot, sc + SC_CY, 0); allreduce(sc + SC_CX, 2, 0);   // SC_CX, SC_CY are adjacent
+    reduce(cobj, x, Ptot, sc + SC_CX, 0); reduce(Cm, Y, tot, sc + SC_CY, 0); allreduce(sc + SC_CX, 2, 0);   // SC_CX, SC_CY are adjacent
     reduce(b, y, N, sc + SC_BY, 0);
     scalar(4);
   }
@@ -1085,8 +1113,9 @@ template <int NL> struct Solver : SolverBase {
     if (stage1_pending) { CK(cudaStreamWaitEvent(st, evS1, 0)); stage1_pending = false; }
     par_blocks([&](Block* b0) { if (b0->sparse) schur_sparse(*b0); else if (staged(*b0)) dense_stage2(*b0); else if (b0->high_rank) pairings_dense(*b0); else pairings_lowrank(*b0); });
     par_clusters([&](Clu& c0) { zero(c0.S, (int64_t)c0.P * c0.P);
-      for (auto& b0 : c0.blocks) { if (b0.high_rank) schur_add_dense(c0, b0); else schur_add_lowrank(c0, b0); }
+      for (auto& b0 : c0.blocks) { if (!b0.mine) continue; if (b0.high_rank) schur_add_dense(c0, b0); else schur_add_lowrank(c0, b0); }
       if (c0.P) nlaunch++, k_mirror<NL><<<grid_for((int64_t)c0.P * c0.P), 256, 0, st>>>(c0.P, c0.S, c0.P, 1); });
+    if (nranks > 1) for (auto& c0 : cl) if (c0.split && c0.P) allreduce(c0.S, (int64_t)c0.P * c0.P, 0);   // S_j = sum over the ranks' blocks; every rank factors the same matrix
     rec(ev[e0]);
     par_clusters([&](Clu& c0) { chol(c0.S, c0.P, c0.P, c0.Minv, c0.P, CLRS_ERR_CHOL_S, false); });
     rec(ev[e0 + 1]);
@@ -1132,7 +1161,7 @@ template <int NL> struct Solver : SolverBase {
     // block elimination  (:1527-1582)
     if (N > 0) zero(tmpU, N);
     par_clusters([&](Clu& c0) { if (c0.P) { copy(c0.t, dx + c0.off, c0.P); trsv(c0.S, c0.P, c0.P, c0.Minv, c0.P, c0.t, false, c0.ready); } });                 // t_j = L_j^-1 rhs_j
-    if (N > 0) for (auto& c0 : cl) { if (!c0.owned || c0.P == 0) continue;
+    if (N > 0) for (auto& c0 : cl) { if (!c0.owned || !c0.lead || c0.P == 0) continue;
       if (c0.big) { for (int s = 0; s < nranks; s++) { const int ncs = std::min(ncr, N - s * ncr); if (ncs > 0) nlaunch++, k_gemv_t<NL><<<(ncs + 31) / 32, 256, 0, st>>>(c0.P, ncs, c0.Gc + (size_t)s * c0.P * ncr, ncr, c0.t, tmpU + s * ncr, 1, 1); } continue; }
       nlaunch++, k_gemv_t<NL><<<(N + 31) / 32, 256, 0, st>>>(c0.P, N, c0.LinvB, N, c0.t, tmpU, 1, 1); }                                        // u += LinvB_j^T t_j
     if (N > 0) { allreduce(tmpU, N, 0); addsub(dy, p, 1, tmpU, -1, N);                                                                       // dy = p - sum_j u_j
@@ -1408,7 +1437,7 @@ template <int NL> struct Solver : SolverBase {
     if (lay == 1) {      // the product kernel alone, one K range (no recombination)
       int BN, group; pick_tiles(N_, BN, group);
       CUtensorMap mA = make_map(sa, tc::BM), mB = make_map(sb, BN);
-      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(((1 << 17) / NS / 128) * 128, sa.Kp); a.k0 = 0; a.BN = BN; a.group = group; a.dsplit = 0; a.oraw = nullptr; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp; a.dbg = nullptr;
+      tc::Args a; a.M = M; a.N = N_; a.Kp = std::min(((1 << 17) / NS / 128) * 128, sa.Kp); a.k0 = 0; a.BN = BN; a.group = group; a.dsplit = 0; a.oraw = nullptr; a.a_bvec = 0; a.b_bvec = 0; a.NS = NS; a.Npitch = (N_ + 15) & ~15; a.batch = 1; a.obytes = tc_bytes; a.otop = tc_top; a.lower_only = 0; a.kz_stride = 0; a.Kp_total = a.Kp; a.dbg = nullptr; a.epi = tc_epi();
       if ((size_t)M * a.Npitch > tc_cap) throw CudaError("bench_gemm: byte planes smaller than one product");
       dim3 grid((N_ + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, 1);
       CK(cudaEventRecord(e1, st));
@@ -1430,7 +1459,7 @@ template <int NL> struct Solver : SolverBase {
     if (w == "S") { src = cl[j].S; n = (int64_t)cl[j].P * cl[j].P; } else if (w == "LinvB") { if (cl[j].big) return -1; src = cl[j].LinvB; n = (int64_t)cl[j].P * N; }
     else if (w == "Q") { src = Q; n = (int64_t)N * N; } else if (w == "d") { src = d; n = Ptot; } else if (w == "p") { src = p; n = N; }
     else if (w == "dx") { src = dx; n = Ptot; } else if (w == "dy") { src = dy; n = N; } else if (w == "x") { src = x; n = Ptot; } else if (w == "y") { src = y; n = N; }
-    else { Block& b0 = cl[j].blocks[l]; n = (int64_t)b0.n * b0.n; const num* base = nullptr;
+    else { Block& b0 = cl[j].blocks[l]; if (!b0.mine) return -1; n = (int64_t)b0.n * b0.n; const num* base = nullptr;
       if (w == "Xinv") base = Xi; else if (w == "R") base = R; else if (w == "P") base = P; else if (w == "dX") base = dX; else if (w == "dY") base = dY; else if (w == "X") base = X; else if (w == "Y") base = Y; else if (w == "L") base = L;
       if (!base) return -1; src = base + b0.off; }
     if (n > cap) return -n; if (n) download_wire(out, src, n); return n;
@@ -1475,6 +1504,7 @@ int clrs_get_objectives(clrs_handle* h, void* d, void* p, void* g) { GUARD(h, re
 int clrs_comm_init(clrs_handle* h, int32_t rank, int32_t nranks, const void* uid) { GUARD(h, return h->s->comm_init(rank, nranks, uid);) }
 int clrs_comm_unique_id(void* out128) { std::string e; memset(out128, 0, 128); if (!g_nccl.load(e)) return CLRS_ERR_CUDA; return g_nccl.GetUniqueId(out128) == 0 ? CLRS_OK : CLRS_ERR_CUDA; }
 int clrs_cluster_owner(clrs_handle* h, int32_t j) { return h->s->owner_of(j); }
+int clrs_block_owner(clrs_handle* h, int32_t j, int32_t l) { return h->s->block_owner_of(j, l); }
 int clrs_debug_selftest(clrs_handle* h) { try { return h->s->selftest(); } catch (const std::exception& e) { h->err = e.what(); return -1; } }
 int clrs_partition_clusters(int32_t J, const double* weight, int32_t nranks, int32_t* owner) {
   if (J < 0 || nranks < 1) return CLRS_ERR_ARG; std::vector<double> w(weight, weight + J); std::vector<int> o; partition_clusters(w, nranks, o); for (int j = 0; j < J; j++) owner[j] = o[j]; return CLRS_OK;

@@ -105,6 +105,7 @@ struct Args {
   int kz_stride;           // > 0: blockIdx.z selects the K range [z*kz_stride, ...) instead of a batch entry (split-K, partial results per z)
   int Kp_total;
   long long* dbg;          // optional timeline of CTA (0,0,0): clock64 stamps (kernel tuning only)
+  int epi;                 // epilogue variant: 0 = one TMEM load + wait per accumulator and column chunk; 1 = the loads of all accumulators of a chunk in flight together, one wait (CLRS_TC_EPI)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -255,46 +256,75 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(tmem_full, full_parity); full_parity ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 4] = clock64();
-      uint32_t va[4][16], vb[4][16];
-      auto issue = [&](uint32_t (&v)[4][16], int c0) {
-#pragma unroll
-        for (int acc = 0; acc < 4; acc++) if (acc <= w) tmem_ld16(tlane + (uint32_t)(acc * BN + c0), v[acc]);
-      };
-      auto landed = [&](uint32_t (&v)[4][16]) {       // the loads have completed; tie the registers to this point so no use is scheduled above the wait
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int acc = 0; acc < 4; acc++) reg_fence16(v[acc]);
-      };
       if (a.dsplit) {
         // raw sums of this group and K range: added into the int32 planes (exact, so the order of the CTAs does not matter)
         for (int c0 = 0; c0 < bn; c0 += 16) {
           const bool store_ok = (m < a.M) && (n0 + c0 < a.Npitch);
-          issue(va, c0); landed(va);
+          for (int acc = w; acc >= 0; acc--) {
+            uint32_t v[16];
+            tmem_ld16(tlane + (uint32_t)(acc * BN + c0), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (store_ok) {
+              int32_t* dst = a.oraw + ((size_t)(d0 + acc) * a.M + m) * a.Npitch + n0 + c0;
 #pragma unroll
-          for (int acc = 3; acc >= 0; acc--) {
-            if (acc > w || !store_ok) continue;
-            int32_t* dst = a.oraw + ((size_t)(d0 + acc) * a.M + m) * a.Npitch + n0 + c0;
-#pragma unroll
-            for (int q = 0; q < 16; q++) if ((int32_t)va[acc][q] != 0) atomicAdd(dst + q, (int32_t)va[acc][q]);
+              for (int q = 0; q < 16; q++) if ((int32_t)v[q] != 0) atomicAdd(dst + q, (int32_t)v[q]);
+            }
           }
         }
         continue;
       }
-      // Column chunks of 16, software-pipelined: the TMEM loads of ALL accumulators of the next chunk are in flight while this chunk's
-      // carry chain runs, and one tcgen05.wait::ld covers a whole chunk (before: one load + one wait per accumulator and chunk, i.e.
-      // 30-32 exposed TMEM round trips per group = the 6.4-8 k cycles of epilogue per group in profiles/README.md)
-      auto process = [&](uint32_t (&v)[4][16], int c0) {
+      if (a.epi == 1) {
+        // all accumulators of a 16-column chunk are loaded together and one tcgen05.wait::ld covers them (8-10 exposed TMEM round trips
+        // per group instead of 30-32).  A double-buffered version of this loop (next chunk's loads in flight during the carry chain)
+        // needed 168 registers with spills in this one-body kernel and slowed the MMA-issuing warps: 0.98 -> 1.16 ms per launch.
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+          uint32_t v[4][16];
+#pragma unroll
+          for (int acc = 0; acc < 4; acc++) if (acc <= w) tmem_ld16(tlane + (uint32_t)(acc * BN + c0), v[acc]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int acc = 0; acc < 4; acc++) reg_fence16(v[acc]);
+          int32_t carry[16];
+#pragma unroll
+          for (int q = 0; q < 16; q++) carry[q] = 0;
+          const bool store_ok = (m < a.M) && (n0 + c0 < a.Npitch);
+#pragma unroll
+          for (int acc = 3; acc >= 0; acc--) {
+            if (acc > w) continue;
+            uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+              const int32_t t = (int32_t)v[acc][q] + carry[q];
+              packed[q >> 2] |= (uint32_t)(t & 255) << (8 * (q & 3));
+              carry[q] = t >> 8;
+            }
+            if (store_ok) *(uint4*)(a.obytes + (size_t)(d0 + acc) * plane + rowoff + n0 + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+          if (g > 0) {
+            uint32_t cv[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) cv[q] = (uint32_t)carry[q];
+            tmem_st16(tlane + (uint32_t)((GROUP - 1) * BN + c0), cv);
+          } else if (store_ok) {
+            int4* dst = (int4*)(a.otop + rowoff + n0 + c0);
+            dst[0] = make_int4(carry[0], carry[1], carry[2], carry[3]); dst[1] = make_int4(carry[4], carry[5], carry[6], carry[7]);
+            dst[2] = make_int4(carry[8], carry[9], carry[10], carry[11]); dst[3] = make_int4(carry[12], carry[13], carry[14], carry[15]);
+          }
+        }
+      } else
+      for (int c0 = 0; c0 < bn; c0 += 16) {
         int32_t carry[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) carry[q] = 0;
         const bool store_ok = (m < a.M) && (n0 + c0 < a.Npitch);
-#pragma unroll
-        for (int acc = 3; acc >= 0; acc--) {
-          if (acc > w) continue;
+        for (int acc = w; acc >= 0; acc--) {
+          uint32_t v[16];
+          tmem_ld16(tlane + (uint32_t)(acc * BN + c0), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           uint32_t packed[4] = {0, 0, 0, 0};
 #pragma unroll
           for (int q = 0; q < 16; q++) {
-            const int32_t t = (int32_t)v[acc][q] + carry[q];
+            const int32_t t = (int32_t)v[q] + carry[q];
             packed[q >> 2] |= (uint32_t)(t & 255) << (8 * (q & 3));
             carry[q] = t >> 8;
           }
@@ -309,18 +339,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           int4* dst = (int4*)(a.otop + rowoff + n0 + c0);
           dst[0] = make_int4(carry[0], carry[1], carry[2], carry[3]); dst[1] = make_int4(carry[4], carry[5], carry[6], carry[7]);
           dst[2] = make_int4(carry[8], carry[9], carry[10], carry[11]); dst[3] = make_int4(carry[12], carry[13], carry[14], carry[15]);
-        }
-      };
-      issue(va, 0);
-      for (int c0 = 0; c0 < bn; c0 += 32) {          // bn is a multiple of 16 and warp-uniform
-        landed(va);
-        const bool second = c0 + 16 < bn;
-        if (second) issue(vb, c0 + 16);
-        process(va, c0);
-        if (second) {
-          landed(vb);
-          if (c0 + 32 < bn) issue(va, c0 + 32);
-          process(vb, c0 + 16);
         }
       }
       if (dbge) a.dbg[(ngroups - 1 - g) * 8 + 5] = clock64();

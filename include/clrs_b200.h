@@ -196,6 +196,11 @@ int clrs_comm_init(clrs_handle* h, int32_t rank, int32_t nranks, const void* ncc
 int clrs_comm_unique_id(void* out128);
 /* rank that owns cluster j after clrs_finalize (LPT on P_j^3 + sum n^3, src/threadinginfo.jl:88,97) */
 int clrs_cluster_owner(clrs_handle* h, int32_t j);
+/* A cluster that alone outweighs a rank's fair share and has several PSD blocks is SPLIT (the three-point bound
+ * is one cluster of 49-61 blocks): its blocks are spread over the ranks (same LPT, weights n^3), each rank adds its blocks' part of
+ * S_j and of <A_*, .>, the parts are summed with one all-reduce, and S_j, its factor and the solves are replicated.  Returns the
+ * rank that holds block l of cluster j (= clrs_cluster_owner(j) for a cluster that is not split). */
+int clrs_block_owner(clrs_handle* h, int32_t j, int32_t l);
 /* the partitioner itself (host only, no GPU needed): owner[j] for J clusters of the given weights */
 int clrs_partition_clusters(int32_t J, const double* weight, int32_t nranks, int32_t* owner);
 

@@ -23,13 +23,25 @@ def shared_uid():
 ok = True
 cases = [("sphere_packing(8,7,2 radii): 7 clusters, 50 free variables", lambda: workloads.sphere_packing(8, 7, [Fraction(1, 2), Fraction(1, 2)]), 1e-20),
          ("polyopt d=20: one cluster (rank 1 owns nothing)", lambda: workloads.polyopt_random(20, 0), 1e-30),
-         ("sphere_packing(8,9,3 radii): 11 clusters", lambda: workloads.sphere_packing(8, 9, [Fraction(1, 2), Fraction(1, 2), Fraction(3, 4)]), 1e-15)]
+         ("sphere_packing(8,9,3 radii): 11 clusters", lambda: workloads.sphere_packing(8, 9, [Fraction(1, 2), Fraction(1, 2), Fraction(3, 4)]), 1e-15),
+         # single clusters with many blocks: the BLOCKS are spread over the ranks, S_j is all-reduced
+         ("three_point_bound(4,1/6,4,4): one cluster, 28 blocks, split by blocks", lambda: workloads.three_point_bound(4, Fraction(1, 6), 4, 4), 1e-30),
+         ("delsarte(8,8): one cluster with a free variable, 19 blocks, split by blocks", lambda: workloads.delsarte(8, 8, Fraction(1, 2)), 1e-30),
+         ("theta(C_9) + maxcut: dense single block (not split)", lambda: workloads.lovasz_theta_cycle(9), 1e-30)]
+if os.environ.get("CLRS_MULTI_CASES"):
+    keep = [int(t) for t in os.environ["CLRS_MULTI_CASES"].split(",")]
+    cases = [c for i, c in enumerate(cases) if i in keep]
 for name, make, gap in cases:
     sdp = make()
     uid = shared_uid()
     t0 = time.time()
-    multi = solvesdp(sdp, lib="device", device=local, duality_gap_threshold=gap, comm=(rank, world, uid))
+    multi = solvesdp(sdp, lib="device", device=local, duality_gap_threshold=gap, comm=(rank, world, uid), keep_solver=True)
     tm = time.time() - t0
+    owners = sorted({multi.solver.block_owner(j, l) for j, c in enumerate(sdp.clusters) for l in range(len(c.blocks))})
+    multi.solver.close()
+    if "split by blocks" in name and len(owners) < min(world, 2):
+        ok = False
+        print(f"[FAIL] {name}: blocks were not spread over the ranks (owners {owners})", flush=True)
     dist.barrier()
     if rank == 0:
         single = solvesdp(sdp, lib="device", device=local, duality_gap_threshold=gap)
