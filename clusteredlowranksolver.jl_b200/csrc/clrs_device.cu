@@ -374,7 +374,14 @@ template <int NL> struct Solver : SolverBase {
     // column tiles (N = 641) the three-diagonal groups lose to wave quantisation: wide tiles only for one or two of them
     if (force == 4 || bnB <= 128 || (force != 3 && (ntB > 2 || cost(bnA) <= cost(bnB) * 1.02))) { BN = bnA; group = 4; } else { BN = bnB; group = 3; }
   }
-  static int tc_epi() { static const int v = getenv("CLRS_TC_EPI") ? atoi(getenv("CLRS_TC_EPI")) : 0; return v; }   // epilogue variant of tc::k_gemm_tc (gemm_tc.cuh)
+  // matmul_prec (src/solver.jl:93,125): the products of the bilinear pairings and the T Y product of the dense path may be formed at a lower
+  // precision.  Here that means FEWER SLICE-PAIR DIAGONALS: only the ns_cur most significant diagonals D_s, s < ns_cur, are produced
+  // (8 bits each; 22 guard + 2 headroom bits as at full precision), i.e. ns (ns + 1) / 2 instead of 630 int8 products per MAC at 256 bit.
+  // Tensor-core path only; the CUDA-core kernel keeps all diagonals (at least as accurate as asked).
+  int ns_cur = NS;
+  int ns_matmul() const { if (opt.matmul_prec <= 0 || opt.matmul_prec >= prec) return NS; return std::max(4, std::min(NS, (opt.matmul_prec + 24 + 7) / 8)); }
+  struct NsScope { Solver& s; NsScope(Solver& s_) : s(s_) { s.ns_cur = s.ns_matmul(); } ~NsScope() { s.ns_cur = NS; } };
+  static int tc_epi() { static const int v = getenv("CLRS_TC_EPI") ? atoi(getenv("CLRS_TC_EPI")) : 1; return v; }   // epilogue variant of tc::k_gemm_tc (gemm_tc.cuh)
   void gemm_tc(const Sliced& A, int a0, const Sliced& B, int b0, int M, int N, num* C, int ldc, int mode, const num* D, int ldd,
                int batch, int64_t a_bvec, int64_t b_bvec, int64_t c_bs, int64_t d_bs, int lower_only, int trans = 0) {
     if (a0 != 0 || b0 != 0) throw CudaError("gemm_tc: panel offsets are not supported");
@@ -389,12 +396,12 @@ template <int NL> struct Solver : SolverBase {
     if (batch == 1 && tiles < 148 && A.Kp >= 256) { const int waves = (tiles * nch + 147) / 148; nch = std::max(nch, std::min(waves * 148 / tiles, A.Kp >= 2048 ? A.Kp / 512 : (A.Kp + 127) / 128)); }
     if (nch > 1 && batch != 1) throw CudaError("gemm_tc: split-K with a batch is not supported");
     int kch = ((A.Kp + nch - 1) / nch + 127) & ~127; nch = (A.Kp + kch - 1) / kch;
-    tc::Args a; a.M = M; a.N = N; a.Kp = A.Kp; a.k0 = 0; a.BN = BN; a.group = group; a.dsplit = 0; a.oraw = nullptr; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = NS; a.Npitch = Npitch;
+    tc::Args a; a.M = M; a.N = N; a.Kp = A.Kp; a.k0 = 0; a.BN = BN; a.group = group; a.dsplit = 0; a.oraw = nullptr; a.a_bvec = (int)a_bvec; a.b_bvec = (int)b_bvec; a.NS = ns_cur; a.Npitch = Npitch;
     a.lower_only = lower_only; a.Kp_total = A.Kp; a.dbg = nullptr; a.epi = tc_epi();
     // under-parallelised products (a few tiles on 148 SMs): one CTA per (tile, K range, diagonal group), raw int32 sums
     // accumulated with red.add, carries resolved in k_tc_recombine_raw
     static const int dsplit_off = getenv("CLRS_TC_DSPLIT") ? atoi(getenv("CLRS_TC_DSPLIT")) == 0 : 0;
-    const int ngroups = (NS + group - 1) / group;
+    const int ngroups = (ns_cur + group - 1) / group;
     if (!dsplit_off && batch == 1 && tiles * nch < 74 && (int64_t)M * Npitch <= (1 << 19) && A.Kp <= KMAX) {
       const int nkc = (A.Kp + 127) / 128; int nzk = std::max(1, std::min(nkc, (296 + tiles * ngroups - 1) / (tiles * ngroups)));
       kch = ((nkc + nzk - 1) / nzk) * 128; nzk = (A.Kp + kch - 1) / kch;
@@ -414,7 +421,7 @@ template <int NL> struct Solver : SolverBase {
     dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, a.batch);
     nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
     const int64_t tot_ = (int64_t)batch * M * N;
-    nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1, trans);
+    nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1, trans, ns_cur);
   }
   // ---- optional per-launch GEMM profile (bench.py roofline) ------------------------------------
   bool prof_on = false; cudaEvent_t pe0 = nullptr, pe1 = nullptr; double prof_ms[3] = {0, 0, 0}, prof_flops[3] = {0, 0, 0}; long prof_n[3] = {0, 0, 0};   // 0: CUDA-core path, 1: tcgen05 small outputs, 2: tcgen05 outputs >= 1e6 numbers
@@ -1019,6 +1026,7 @@ template <int NL> struct Solver : SolverBase {
   void pairings_lowrank(Block& b0) {
     const int n = b0.n, m = b0.m, dl = b0.delta;
     if (b0.nP == 0) return;
+    NsScope mp(*this);                                                                                // pairings at matmul_prec (:1125-1143)
     for (int pass = 0; pass < 2; pass++) {
       const num* Src = (pass == 0 ? Y : Xi) + b0.off; auto& Bout = pass == 0 ? b0.BY : b0.BX;
       for (int r = 0; r < m; r++) { if (b0.u_r[r] == 0) continue;
@@ -1052,7 +1060,7 @@ template <int NL> struct Solver : SolverBase {
     par_for(nchunk, [&](int c) {
       const int p0 = c * pc, cnt = std::min(pc, np - p0); if (cnt <= 0) return;
       Sliced Ac = view(b0.AallB, p0 * n, cnt * n), T1c = view(b0.T1S, p0 * n, cnt * n); num* T1p = b0.T1 + (int64_t)p0 * nn;
-      gemm(Ac, 0, b0.YS, 0, cnt * n, n, T1p, n);                                                      // (columns of the symmetric A_p) x (columns of Y)
+      { NsScope mp(*this); gemm(Ac, 0, b0.YS, 0, cnt * n, n, T1p, n); }                                // (columns of the symmetric A_p) x (columns of Y): the T Y product, at matmul_prec (:1097)
       VecView v; v.base = T1p; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = cnt * n; v.K = n; split(T1c, v, false, 1, true); });
   }
   void dense_stage2(Block& b0) {                      // T_p^T[(p,b)][a] = sum_i W_p[i][b] X^-1[a][i]; S[p,q] += <A_q, T_p^T> over the packed triangle
@@ -1085,7 +1093,7 @@ template <int NL> struct Solver : SolverBase {
         num* T1p = b0.T1 + (int64_t)p0 * nn; num* T2p = b0.T2 + (int64_t)p0 * nn;
         gemm(Ac, 0, b0.XiS, 0, cnt * n, n, T1p, n);
         { VecView v; v.base = T1p; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = cnt * n; v.K = n; split(T1c, v, false, 1, true); }
-        gemm(T1c, 0, b0.YS, 0, cnt * n, n, T2p, n);
+        { NsScope mp(*this); gemm(T1c, 0, b0.YS, 0, cnt * n, n, T2p, n); }
         if (b0.tri) split_tri(b0.T2V, p0, T2p, cnt, n, true);
         else { VecView v; v.base = T2p; v.bstride = 0; v.vper = cnt; v.sv = nn; v.sk = 1; v.nvec = cnt; v.K = n * n; split(T2c, v, true, 1, true); }
       });
@@ -1094,7 +1102,7 @@ template <int NL> struct Solver : SolverBase {
     gemm(b0.AallB, 0, b0.XiS, 0, np * n, n, b0.T1, n);
     // T2[(p,i)][b] = sum_j T1_p[i][j] Y[j][b]
     { VecView v; v.base = b0.T1; v.bstride = nn; v.vper = n; v.sv = 1; v.sk = n; v.nvec = np * n; v.K = n; split(b0.T1S, v, false, b0.lay); }
-    gemm(b0.T1S, 0, b0.YS, 0, np * n, n, b0.T2, n);
+    { NsScope mp(*this); gemm(b0.T1S, 0, b0.YS, 0, np * n, n, b0.T2, n); }
     if (b0.tri) { ensure(b0.T2V, np, n * (n + 1) / 2, 1); split_tri(b0.T2V, 0, b0.T2, np, n, true); }
     else { VecView v; v.base = b0.T2; v.bstride = 0; v.vper = np; v.sv = nn; v.sk = 1; v.nvec = np; v.K = n * n; split(b0.T2V, v, true, b0.AallV.lay); }
     }

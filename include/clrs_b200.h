@@ -88,7 +88,8 @@ enum {
  * src/solver.jl:138-139). */
 typedef struct clrs_options {
   int32_t prec;                      /* bits; 256 default (precision(BigFloat)); <= 512 in this build (8, 10 or 16 limbs) */
-  int32_t matmul_prec;               /* bits for pairings/S GEMMs (solver.jl:125); 0 = prec.  This build computes the pairings at prec whatever the value (at least as accurate as asked) */
+  int32_t matmul_prec;               /* bits for the products of the bilinear pairings and the T Y product of the dense path (solver.jl:93,125,1097,1125-1143); 0 = prec.
+                                        Lower values produce fewer slice-pair diagonals on the tensor cores (ceil((matmul_prec + 24) / 8) of the 35 at 256 bit) */
   double  beta_infeasible;           /* 3//10 */
   double  beta_feasible;             /* 1//10 */
   double  gamma;                     /* 9//10 */
