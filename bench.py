@@ -48,7 +48,11 @@ SNAP_ITER = 3               # the snapshot is the iterate after this many iterat
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from `ncu --set full` captures of this
 # build (profiles/): keyed by (workload, class).  None = not captured for this build.
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # tc::k_gemm_tc grid (2,148,1) on one 63-constraint chunk (18900 x 300 x 300): 651.5 MB read + 176.3 MB written
+    # (profiles/r02_tc_kernel_ncu_full.txt; algorithmic: 212 MB of left-operand planes in, 224 MB of byte planes + carry plane out)
+    ("maxcut", "tc_large"): 827.7e6,
+}
 
 
 def workload(n, kind="maxcut"):
@@ -447,6 +451,32 @@ def main():
             v1 = K / (dms1 / 1e3)
             out["strong_scaling"] = {"value_1gpu": v1, "ms_per_step_1gpu": dms1 / K, "speedup": value / v1, "n_gpus": world,
                                      "note": "same SDP, same build, unsharded handle on rank 0's GPU while the other ranks wait"}
+        dist.barrier()
+
+    # ---- second sharded workload in the same run: BASELINE configs[3] (three-point bound, ONE cluster) sharded by PSD blocks ----
+    if sharded and args.workload is None and not args.no_configs:
+        try:
+            sdp2 = workload(300, "threepoint")
+            uid2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid2 = torch.tensor(list(clrs_b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(uid2, 0)
+            S2 = Solver(sdp2, lib="device", device=local_rank, comm=(rank, world, bytes(uid2.cpu().tolist())), duality_gap_threshold=GAP)
+            owners = sorted({S2.block_owner(0, l) for l in range(len(sdp2.clusters[0].blocks))})
+            _, dms2, _, _, _, _, info2 = measure(S2, 4, 3, sync, None, e2e=False)
+            S2.close()
+            dms2 = allmax(dms2)
+            entry = {"workload": sdp2.describe(), "config_index": 3, "value": 4 / (dms2 / 1e3), "ms_per_step": dms2 / 4, "n_gpus": world, "scaling": "strong",
+                     "ranks_holding_blocks": owners, "parallelism": config(300, world, "threepoint", sdp2)["parallelism"],
+                     "phase_ms": dict(zip(clrs_b200.PHASES, [round(v, 4) for v in info2.phase_ms]))}
+            if rank == 0:
+                S3 = Solver(sdp2, lib="device", device=local_rank, duality_gap_threshold=GAP)
+                _, dms3, _, _, _, _, _ = measure(S3, 4, 3, torch.cuda.synchronize, None, e2e=False)
+                S3.close()
+                entry["value_1gpu"] = 4 / (dms3 / 1e3); entry["ms_per_step_1gpu"] = dms3 / 4; entry["speedup"] = (dms3 / 4) / (dms2 / 4)
+            out["sharded_configs"] = {"threepoint": entry}
+        except Exception as e:          # a side table must never take the headline down
+            out["sharded_configs"] = {"threepoint": {"error": str(e)}}
         dist.barrier()
 
     if rank == 0 and world == 1:

@@ -8,7 +8,7 @@ Julia shim, plus generators for the BASELINE.json workloads.
 from . import wire
 from .sdp import ClusteredSDP, Cluster, PSDBlock, LowRankTerm
 from .api import (Solver, SolverFailure, solvesdp, IterInfo, Options, load_library, PHASES, DEVICE_LIB, register_backend,
-                  nccl_unique_id, partition_clusters)
+                  nccl_unique_id, partition_clusters, plan_shards)
 
 __all__ = ["wire", "ClusteredSDP", "Cluster", "PSDBlock", "LowRankTerm", "Solver", "SolverFailure", "solvesdp",
-           "IterInfo", "Options", "load_library", "PHASES", "DEVICE_LIB", "register_backend", "nccl_unique_id", "partition_clusters"]
+           "IterInfo", "Options", "load_library", "PHASES", "DEVICE_LIB", "register_backend", "nccl_unique_id", "partition_clusters", "plan_shards"]

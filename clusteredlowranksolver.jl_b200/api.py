@@ -453,3 +453,23 @@ def partition_clusters(weights, nranks: int):
     if fn(C.c_int32(len(weights)), w, C.c_int32(nranks), out) != 0:
         raise ValueError("clrs_partition_clusters failed")
     return list(out)
+
+
+def plan_shards(sdp: ClusteredSDP, nranks: int, split_mode: int = -1, big_cluster: int = 512):
+    """The library's shard plan for `sdp` on `nranks` ranks (host only): (cluster_owner, split, block_owner[j][l]).
+    Same weights as clrs_finalize: P_j^3 per cluster, 15 n^3 per block ((2 #A_p + 15) n^3 for a dense block)."""
+    lib = load_library("device")
+    J = len(sdp.clusters)
+    nb = [len(c.blocks) for c in sdp.clusters]
+    bw = [float(b.n) ** 3 * (2.0 * (len(b.dense) + len(b.sparse)) + 15 if b.high_rank else 15) for c in sdp.clusters for b in c.blocks]
+    p3 = (C.c_double * J)(*[float(c.P) ** 3 for c in sdp.clusters])
+    big = (C.c_int32 * J)(*[int(nranks > 1 and sdp.N > 0 and big_cluster > 0 and c.P >= big_cluster) for c in sdp.clusters])
+    own, spl, bown = (C.c_int32 * J)(), (C.c_int32 * J)(), (C.c_int32 * max(1, len(bw)))()
+    fn = lib.clrs_plan_shards
+    fn.restype = C.c_int
+    if fn(C.c_int32(J), p3, (C.c_int32 * J)(*nb), (C.c_double * max(1, len(bw)))(*bw), big, C.c_int32(nranks), C.c_int32(split_mode), own, spl, bown) != 0:
+        raise ValueError("clrs_plan_shards failed")
+    out, o = [], 0
+    for n in nb:
+        out.append(list(bown[o:o + n])); o += n
+    return list(own), [bool(v) for v in spl], out

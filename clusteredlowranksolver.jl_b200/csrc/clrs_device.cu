@@ -55,6 +55,29 @@ static void partition_clusters(const std::vector<double>& w, int R, std::vector<
   for (int j : order) { int best = 0; for (int r = 1; r < R; r++) if (load[r] < load[best]) best = r; owner[j] = best; load[best] += w[j]; }
 }
 
+// The whole plan of a sharded solve (host only, deterministic on every rank).  Work items are whole clusters (weight cw[j] = P_j^3 +
+// the block weights) — except that a cluster that alone outweighs a rank's fair share by 25 % and has several blocks is SPLIT: its
+// blocks become items of their own (the three-point bound is ONE cluster of 49-61 blocks), while its Schur
+// complement, factor and solves are replicated.  Clusters that take the column-split path (`bigc`, §8(e)(ii)) keep their blocks together.
+// split_mode: 0 never, 1 every multi-block cluster, -1 by weight.
+struct ShardPlan { std::vector<int> cluster_owner, split; std::vector<std::vector<int>> block_owner; };
+static ShardPlan plan_shards(const std::vector<double>& p3, const std::vector<std::vector<double>>& bw, const std::vector<int>& bigc, int R, int split_mode) {
+  const size_t J = p3.size(); ShardPlan pl; pl.cluster_owner.assign(J, -1); pl.split.assign(J, 0); pl.block_owner.resize(J);
+  std::vector<double> cw(J); double total = 0; for (size_t j = 0; j < J; j++) { cw[j] = p3[j]; for (double w : bw[j]) cw[j] += w; total += cw[j]; }
+  std::vector<double> wgt; std::vector<std::pair<int, int>> item;                    // (cluster, block or -1)
+  for (size_t j = 0; j < J; j++) {
+    pl.split[j] = R > 1 && !bigc[j] && bw[j].size() >= 2 && split_mode != 0 && (split_mode == 1 || cw[j] > 1.25 * total / R);
+    pl.block_owner[j].assign(bw[j].size(), -1);
+    if (!pl.split[j]) { wgt.push_back(cw[j]); item.push_back({(int)j, -1}); continue; }
+    for (size_t l = 0; l < bw[j].size(); l++) { wgt.push_back(bw[j][l]); item.push_back({(int)j, (int)l}); } }
+  std::vector<int> owner; partition_clusters(wgt, R, owner);
+  for (size_t i = 0; i < item.size(); i++) { const int j = item[i].first, l = item[i].second;
+    if (l < 0) { pl.cluster_owner[j] = owner[i]; for (auto& o : pl.block_owner[j]) o = owner[i]; }
+    else { pl.block_owner[j][l] = owner[i]; if (pl.cluster_owner[j] < 0) pl.cluster_owner[j] = owner[i]; } }      // the lead of a split cluster: the rank of its first block
+  for (size_t j = 0; j < J; j++) if (pl.cluster_owner[j] < 0) pl.cluster_owner[j] = 0;
+  return pl;
+}
+
 // scalar slots in device memory
 enum { SC_MU, SC_MUP, SC_MUC, SC_BETA, SC_BETAC, SC_ALPHAD, SC_ALPHAP, SC_D0, SC_D1, SC_D2, SC_D3, SC_DOBJ, SC_POBJ, SC_GAP,
        SC_ERRP, SC_ERRp, SC_ERRd, SC_CX, SC_CY, SC_BY, SC_K, SC_ONE, SC_BETA_INF, SC_BETA_FEAS, SC_GAMMA, SC_OMEGA_P, SC_OMEGA_D,
@@ -763,25 +786,16 @@ template <int NL> struct Solver : SolverBase {
   // ---- finalize: build tables (precompute_matrices_bilinear_pairings, src/solver.jl:985-1059), allocate, initialise ----
   int finalize() override {
     Ptot = 0; Ksum = 0; tot = 0; gtot = 0; blk.clear();
-    { // work items of the partition: whole clusters (weights P^3 + sum n^3, src/threadinginfo.jl:88,97) — except that a cluster that alone
-      // outweighs a rank's fair share and has several blocks is SPLIT: its blocks become items of their own (§8(e)(i): config 4 is one
-      // cluster of 49-61 blocks), while its Schur complement, factor and solves are replicated on every rank
+    { // clusters (and the blocks of split clusters) -> ranks: plan_shards above; weights P^3 + sum n^3 (src/threadinginfo.jl:88,97)
       static const int split_env = getenv("CLRS_SPLIT_BLOCKS") ? atoi(getenv("CLRS_SPLIT_BLOCKS")) : -1;      // 0 never, 1 every multi-block cluster, default by weight
       static const int bigp0 = getenv("CLRS_BIG_CLUSTER") ? atoi(getenv("CLRS_BIG_CLUSTER")) : 512;
-      auto bw = [](const Block& b0) { const double n3 = (double)b0.n * b0.n * b0.n; return n3 * (b0.high_rank ? 2.0 * b0.dense_p.size() + 15 : 15); };
-      std::vector<double> cw; double total = 0; for (auto& c0 : cl) { double w = (double)c0.P * c0.P * c0.P; for (auto& b0 : c0.blocks) w += bw(b0); cw.push_back(w); total += w; }
-      std::vector<double> wgt; std::vector<std::pair<int, int>> item;                    // (cluster, block or -1)
-      for (size_t j = 0; j < cl.size(); j++) { Clu& c0 = cl[j];
-        const bool bigc = nranks > 1 && N > 0 && bigp0 > 0 && c0.P >= bigp0;            // column-split clusters keep their blocks together
-        c0.split = nranks > 1 && !bigc && c0.blocks.size() >= 2 && split_env != 0 && (split_env == 1 || cw[j] > 1.25 * total / nranks);
-        if (!c0.split) { wgt.push_back(cw[j]); item.push_back({(int)j, -1}); continue; }
-        for (size_t l = 0; l < c0.blocks.size(); l++) { wgt.push_back(bw(c0.blocks[l])); item.push_back({(int)j, (int)l}); } }
-      std::vector<int> owner; partition_clusters(wgt, nranks, owner);
-      for (auto& c0 : cl) { c0.owner = -1; }
-      for (size_t i = 0; i < item.size(); i++) { Clu& c0 = cl[item[i].first];
-        if (item[i].second < 0) { c0.owner = owner[i]; c0.owned = owner[i] == rank; c0.lead = c0.owned; for (auto& b0 : c0.blocks) { b0.brank = owner[i]; b0.mine = c0.owned; } }
-        else { Block& b0 = c0.blocks[item[i].second]; b0.brank = owner[i]; b0.mine = owner[i] == rank; if (c0.owner < 0) c0.owner = owner[i]; c0.owned = true; c0.lead = c0.owner == rank; } }
-      for (auto& c0 : cl) if (c0.owner < 0) { c0.owner = 0; c0.owned = rank == 0; c0.lead = c0.owned; } }
+      auto bwf = [](const Block& b0) { const double n3 = (double)b0.n * b0.n * b0.n; return n3 * (b0.high_rank ? 2.0 * b0.dense_p.size() + 15 : 15); };
+      std::vector<double> p3; std::vector<std::vector<double>> bw; std::vector<int> bigc;
+      for (auto& c0 : cl) { p3.push_back((double)c0.P * c0.P * c0.P); bw.emplace_back(); for (auto& b0 : c0.blocks) bw.back().push_back(bwf(b0));
+        bigc.push_back(nranks > 1 && N > 0 && bigp0 > 0 && c0.P >= bigp0); }                                   // column-split clusters keep their blocks together
+      const ShardPlan pl = plan_shards(p3, bw, bigc, nranks, split_env);
+      for (size_t j = 0; j < cl.size(); j++) { Clu& c0 = cl[j]; c0.split = pl.split[j] != 0; c0.owner = pl.cluster_owner[j]; c0.lead = c0.owner == rank; c0.owned = c0.split || c0.lead;
+        for (size_t l = 0; l < c0.blocks.size(); l++) { c0.blocks[l].brank = pl.block_owner[j][l]; c0.blocks[l].mine = pl.block_owner[j][l] == rank; } } }
     for (auto& c0 : cl) { c0.off = Ptot; Ptot += c0.P;
       for (auto& b0 : c0.blocks) { Ksum += b0.n; b0.goff = gtot; gtot += (int64_t)b0.n * b0.n; if (c0.owned && b0.mine) { b0.off = tot; tot += (int64_t)b0.n * b0.n; blk.push_back(&b0); } } }
     std::vector<int64_t> boff; std::vector<int32_t> bn; for (Block* b0 : blk) { boff.push_back(b0->off); bn.push_back(b0->n); } boff.push_back(tot);
@@ -1516,6 +1530,15 @@ int clrs_block_owner(clrs_handle* h, int32_t j, int32_t l) { return h->s->block_
 int clrs_debug_selftest(clrs_handle* h) { try { return h->s->selftest(); } catch (const std::exception& e) { h->err = e.what(); return -1; } }
 int clrs_partition_clusters(int32_t J, const double* weight, int32_t nranks, int32_t* owner) {
   if (J < 0 || nranks < 1) return CLRS_ERR_ARG; std::vector<double> w(weight, weight + J); std::vector<int> o; partition_clusters(w, nranks, o); for (int j = 0; j < J; j++) owner[j] = o[j]; return CLRS_OK;
+}
+int clrs_plan_shards(int32_t J, const double* p3, const int32_t* nblocks, const double* block_weight, const int32_t* column_split, int32_t nranks, int32_t split_mode,
+                     int32_t* cluster_owner, int32_t* split, int32_t* block_owner) {
+  if (J < 0 || nranks < 1) return CLRS_ERR_ARG;
+  std::vector<double> p(p3, p3 + J); std::vector<std::vector<double>> bw(J); std::vector<int> big(J, 0); size_t o = 0;
+  for (int j = 0; j < J; j++) { bw[j].assign(block_weight + o, block_weight + o + nblocks[j]); o += nblocks[j]; if (column_split) big[j] = column_split[j]; }
+  const ShardPlan pl = plan_shards(p, bw, big, nranks, split_mode); o = 0;
+  for (int j = 0; j < J; j++) { cluster_owner[j] = pl.cluster_owner[j]; split[j] = pl.split[j]; for (int l = 0; l < nblocks[j]; l++) block_owner[o++] = pl.block_owner[j][l]; }
+  return CLRS_OK;
 }
 int clrs_mp_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, const void* A, const void* B, void* C, int32_t path, double* ms) { GUARD(h, return h->s->mp_gemm(M, N, K, A, B, C, path, ms);) }
 int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L) { GUARD(h, return h->s->mp_cholesky(n, A, L);) }

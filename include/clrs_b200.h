@@ -204,6 +204,12 @@ int clrs_cluster_owner(clrs_handle* h, int32_t j);
 int clrs_block_owner(clrs_handle* h, int32_t j, int32_t l);
 /* the partitioner itself (host only, no GPU needed): owner[j] for J clusters of the given weights */
 int clrs_partition_clusters(int32_t J, const double* weight, int32_t nranks, int32_t* owner);
+/* the whole plan of a sharded solve (host only): p3[j] = P_j^3, nblocks[j] blocks with weights block_weight[] (concatenated;
+ * 15 n^3, or (2 * #A_p + 15) n^3 for a dense block), column_split[j] != 0 for clusters on the column-split path (may be NULL);
+ * split_mode -1 by weight (a cluster heavier than 1.25 x the fair share with >= 2 blocks), 0 never, 1 always.
+ * Out: cluster_owner[J] (the lead of a split cluster), split[J], block_owner[] (concatenated like block_weight). */
+int clrs_plan_shards(int32_t J, const double* p3, const int32_t* nblocks, const double* block_weight, const int32_t* column_split,
+                     int32_t nranks, int32_t split_mode, int32_t* cluster_owner, int32_t* split, int32_t* block_owner);
 
 /* ---- standalone kernels of the path (parity tests / microbenchmarks) ---- */
 /* C = A * B (M x K times K x N) in multi-limb arithmetic on the device,

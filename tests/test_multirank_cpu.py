@@ -142,3 +142,26 @@ def test_two_ranks_sum_multi_limb_numbers_through_int64_lanes():
             # one 32-bit guard lane below the aligned 256-bit mantissas, then the sum is truncated to 256 bits
             assert abs(got[i] - exact) <= big * mpmath.mpf(2) ** -280 + abs(exact) * mpmath.mpf(2) ** -255, i
         assert got[5] == 0 and got[6] == 3 + 3 * mpmath.mpf(2) ** 40
+
+
+def test_shard_plan_splits_single_heavy_clusters_by_blocks():
+    """config 4 is ONE cluster -> its blocks are spread over the ranks; §8(e)(ii)/(iii): sphere packing keeps whole
+    clusters (the big SOS2 cluster takes the column-split path), single-block SDPs are never split."""
+    sys.path.insert(0, ROOT)
+    import clrs_b200
+    from clrs_b200 import workloads, plan_shards
+    tp = workloads.three_point_bound(4, Fraction(1, 6), 4, 4)
+    own, split, bown = plan_shards(tp, 4)
+    assert split == [True] and sorted(set(bown[0])) == [0, 1, 2, 3] and own[0] == bown[0][0]
+    w = [float(b.n) ** 3 * (2.0 * len(b.dense) + 15 if b.high_rank else 15) for b in tp.clusters[0].blocks]      # the library's block weights
+    load = [sum(wi for wi, o in zip(w, bown[0]) if o == r) for r in range(4)]
+    assert max(load) <= sum(w) / 4 + max(w)                              # greedy LPT: no rank exceeds the fair share by more than one item
+    assert plan_shards(tp, 1)[1] == [False] and plan_shards(tp, 4, split_mode=0)[1] == [False]
+    sp = workloads.sphere_packing(8, 5, [Fraction(1, 2), Fraction(1, 2), Fraction(3, 4)])
+    own, split, bown = plan_shards(sp, 2, big_cluster=20)
+    assert not any(s and c.P >= 20 for s, c in zip(split, sp.clusters))  # column-split clusters keep their blocks together
+    for j, c in enumerate(sp.clusters):
+        if not split[j]:
+            assert all(o == own[j] for o in bown[j])
+    assert plan_shards(workloads.maxcut(workloads.laplacian_cycle(5)), 8)[1] == [False]
+    assert plan_shards(tp, 4) == plan_shards(tp, 4)                      # deterministic
