@@ -456,15 +456,13 @@ template <int NL> struct Solver : SolverBase {
   // for the step length only needs the iterate, so it runs beside the Schur assembly.  swap_ctx() exchanges the
   // members the helpers use; kernels capture their pointers at enqueue time, so swapping while enqueuing is safe.
   struct Ctx { cudaStream_t st = nullptr; Sliced tA, tB; num* chol_W = nullptr; size_t chol_W_cap = 0; uint8_t* tc_bytes = nullptr; int32_t* tc_top = nullptr; size_t tc_cap = 0; int32_t* tc_raw = nullptr; size_t tc_raw_cap = 0;
-               num* trsm_R = nullptr; size_t trsm_cap = 0; cudaEvent_t ev = nullptr;
-               cudaStream_t la_st = nullptr; cudaEvent_t la_evD = nullptr, la_evP = nullptr; };   /* look-ahead stream of Solver::chol (next diagonal block factored beside the trailing update) */
+               num* trsm_R = nullptr; size_t trsm_cap = 0; cudaEvent_t ev = nullptr; };
   Ctx side, side2, side3;                            // side: Cholesky of Y; side2: R = mu I - XY beside chol(X), and Y's step-length eigenvalue beside X's; side3: first stage of the dense Schur products
   cudaEvent_t evS0 = nullptr, evS1 = nullptr; bool stage1_pending = false;
   cudaEvent_t evR0 = nullptr, evR1 = nullptr, evE0 = nullptr, evE1 = nullptr; num *U2 = nullptr, *T1b = nullptr; double* Td2 = nullptr; double* eigV2 = nullptr; EigTask* eigT2 = nullptr;
   cudaEvent_t evY0 = nullptr, evY1 = nullptr; num *LY = nullptr, *MinvY = nullptr;
   void swap_with(Ctx& c) { std::swap(st, c.st); std::swap(tA, c.tA); std::swap(tB, c.tB); std::swap(chol_W, c.chol_W); std::swap(chol_W_cap, c.chol_W_cap);
-    std::swap(tc_bytes, c.tc_bytes); std::swap(tc_top, c.tc_top); std::swap(tc_cap, c.tc_cap); std::swap(tc_raw, c.tc_raw); std::swap(tc_raw_cap, c.tc_raw_cap); std::swap(trsm_R, c.trsm_R); std::swap(trsm_cap, c.trsm_cap);
-    std::swap(la_st, c.la_st); std::swap(la_evD, c.la_evD); std::swap(la_evP, c.la_evP); }
+    std::swap(tc_bytes, c.tc_bytes); std::swap(tc_top, c.tc_top); std::swap(tc_cap, c.tc_cap); std::swap(tc_raw, c.tc_raw); std::swap(tc_raw_cap, c.tc_raw_cap); std::swap(trsm_R, c.trsm_R); std::swap(trsm_cap, c.trsm_cap); }
   void swap_ctx() { swap_with(side); }
   // Independent items (PSD blocks, clusters) are enqueued round-robin on NCTX execution contexts, so that the many small
   // kernels of a many-block problem (one diagonal-block Cholesky CTA, 16-CTA GEMMs) overlap instead of queueing on one
@@ -554,7 +552,6 @@ template <int NL> struct Solver : SolverBase {
   // ---- blocked Cholesky with explicit factor inverse -----------------------------------
   // A (n x n, lower part read) -> L in place (strict upper zeroed); Minv = L^-1 (lower triangular, full n x n buffer)
   num* chol_W = nullptr; size_t chol_W_cap = 0;
-  cudaStream_t la_st = nullptr; cudaEvent_t la_evD = nullptr, la_evP = nullptr;      // look-ahead stream + events of the current execution context
   // full_inverse: also assemble L^-1 below the diagonal blocks (X and Y blocks: products with L^-1 and X^-1 follow);
   // otherwise only the inverses of the 32 x 32 diagonal blocks are formed and solves go by block substitution.
   // Two-level blocking: 128-column outer panels, 32-column steps inside a panel.  A step factors its 32 x 32 diagonal block
@@ -567,56 +564,31 @@ template <int NL> struct Solver : SolverBase {
     if (ldm == n) zero(Minv, (int64_t)n * n); else for (int r = 0; r < n; r++) zero(Minv + (int64_t)r * ldm, n);
     static const int pnl_env = getenv("CLRS_CHOL_PANEL") ? std::max(32, atoi(getenv("CLRS_CHOL_PANEL")) / 32 * 32) : 0;
     const int pnl = pnl_env ? pnl_env : (n >= 448 ? PNL : 32);        // measured: n = 640 gains (L^-1 B 7.8 -> 4.4 ms at 16 limbs), n <= 400 does not
-    // Look-ahead (CLRS_CHOL_LOOKAHEAD=0 disables it): the single-CTA factorisation of the NEXT diagonal block is the one piece of a step
-    // that cannot use the machine, so it is taken off the main chain.  A step first solves only the 32 rows of the next block (T1) and
-    // applies only the update of that diagonal block D (U1); then D is factored on the context's look-ahead stream while the main stream
-    // solves the remaining rows (T2) and applies the rest of the update (U2, which never touches D).  The arithmetic of every entry is
-    // the same as in the plain right-looking order (same products, same K ranges), so the factor is bit-identical.
-    static const int la_env = getenv("CLRS_CHOL_LOOKAHEAD") ? atoi(getenv("CLRS_CHOL_LOOKAHEAD")) : 1;
-    auto potrf = [&](int k0, int nb, cudaStream_t s_) { nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), s_>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code, full_inverse ? 1 : 0, k0 == 0 ? potrf_dbg : nullptr); };
-    auto solve_rows = [&](int k0, int nb, int r0, int cnt) {            // rows [r0, r0 + cnt) of block column k0: L = A inv(L11)^T
-      if (cnt <= 0) return; num* Ar = A + (int64_t)r0 * lda + k0;
-      if (full_inverse) { split_rows(tA, Ar, lda, cnt, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb); gemm(tA, 0, tB, 0, cnt, nb, Ar, lda); }
-      else nlaunch++, k_trsm32<NL><<<(cnt + 7) / 8, 256, 0, st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, Ar, lda, 1, cnt, Ar, lda, 1); };
-    // C -= (vectors [a0, a0 + M) of P) (vectors [b0, b0 + N) of P)^T for a panel P split by rows (either layout)
-    auto rank_update = [&](const Sliced& Pn, int a0, int M, int b0, int N, num* C, int lower) {
-      if (M <= 0 || N <= 0) return;
-      if (Pn.lay == 1) { Sliced l = view(Pn, a0, M), r = view(Pn, b0, N); gemm(l, 0, r, 0, M, N, C, lda, 1, C, lda, 1, 0, 0, 0, 0, lower); }
-      else gemm(Pn, a0, Pn, b0, M, N, C, lda, 1, C, lda, 1, 0, 0, 0, 0, lower); };
-    bool pending = false;                                               // the diagonal block of this step was factored on the look-ahead stream
+    // (Measured and not kept, round 2: a look-ahead variant that factored the next diagonal block on a second stream beside the rest of the
+    //  trailing update — bit-identical factor, tools/gpu_chol_check.py — did not shorten the chain: the 32-step substitution of k_trsm32 has the
+    //  same ~100 us latency for 32 rows as for 600, so splitting it into "next block" + "rest" put it on the critical path twice:
+    //  chol S of the P = 640 cluster 8.5 -> 9.1 ms, profiles/README.md.  What would shorten the chain is a panel kernel that factors the
+    //  diagonal block together with the 32 rows below it and applies the update of the next diagonal block itself.)
     for (int K0 = 0; K0 < n; K0 += pnl) {
-      const int KE = std::min(n, K0 + pnl), kw = KE - K0;
-      bool carved = false;                                              // the first diagonal block after this panel already has the panel's update
+      const int KE = std::min(n, K0 + pnl);
       for (int k0 = K0; k0 < KE; k0 += 32) {
-        const int nb = std::min(32, KE - k0), rem = n - k0 - nb, r1 = k0 + nb, nbn = std::min(32, rem);
-        if (pending) { CK(cudaStreamWaitEvent(st, la_evP, 0)); pending = false; } else potrf(k0, nb, st);
+        const int nb = std::min(32, KE - k0), rem = n - k0 - nb;
+        nlaunch++, k_potrf_diag<NL><<<1, POTRF_THREADS, POTRF_SMEM(NL), st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, flags + FL_STATUS, code, full_inverse ? 1 : 0, k0 == 0 ? potrf_dbg : nullptr);
         if (rem <= 0) continue;
-        const bool last = r1 >= KE;                                     // the next diagonal block opens the next panel: its update spans the whole panel (K = kw)
-        const bool la = la_env && !prof_on && rem > nbn;                // something to overlap with
-        if (!la) {
-          solve_rows(k0, nb, r1, rem);
-          const int pc = KE - r1;                                       // columns of this panel still to be factored
-          if (pc > 0) { split_rows(tA, A + (int64_t)r1 * lda + k0, lda, rem, nb); rank_update(tA, 0, rem, 0, pc, A + (int64_t)r1 * lda + r1, 0); }   // (the strict upper part of A is never read)
-          continue;
-        }
-        solve_rows(k0, nb, r1, nbn);                                                                                            // T1
-        { num* D = A + (int64_t)r1 * lda + r1; const int kc = last ? K0 : k0, kk = last ? kw : nb;                              // U1
-          split_rows(tB, A + (int64_t)r1 * lda + kc, lda, nbn, kk); rank_update(tB, 0, nbn, 0, nbn, D, 0); }
-        CK(cudaEventRecord(la_evD, st)); CK(cudaStreamWaitEvent(la_st, la_evD, 0)); potrf(r1, nbn, la_st); CK(cudaEventRecord(la_evP, la_st)); pending = true;
-        if (last) carved = true;
-        solve_rows(k0, nb, r1 + nbn, rem - nbn);                                                                                // T2
-        if (!last) { const int pc = KE - r1;                                                                                    // U2 inside the panel: rows below the next block
-          split_rows(tA, A + (int64_t)r1 * lda + k0, lda, rem, nb); rank_update(tA, nbn, rem - nbn, 0, pc, A + (int64_t)(r1 + nbn) * lda + r1, 0); }
+        num* A21 = A + (int64_t)(k0 + nb) * lda + k0;
+        if (full_inverse) { split_rows(tA, A21, lda, rem, nb); split_rows(tB, Minv + (int64_t)k0 * ldm + k0, ldm, nb, nb);
+          gemm(tA, 0, tB, 0, rem, nb, A21, lda); }                    // L21 = A21 * inv(L11)^T
+        else nlaunch++, k_trsm32<NL><<<(rem + 7) / 8, 256, 0, st>>>(nb, A + (int64_t)k0 * lda + k0, lda, Minv + (int64_t)k0 * ldm + k0, ldm, A21, lda, 1, rem, A21, lda, 1);   // rows of L21 by substitution
+        const int pc = KE - k0 - nb;                                  // columns of this panel still to be factored
+        if (pc > 0) { num* Ap = A + (int64_t)(k0 + nb) * lda + k0 + nb;
+          split_rows(tA, A21, lda, rem, nb);
+          gemm(tA, 0, tA, 0, rem, pc, Ap, lda, 1, Ap, lda); }           // A[k0+nb:, k0+nb:KE] -= L21 L21[0:pc]^T  (the strict upper part of A is never read)
       }
       const int remO = n - KE;
-      if (remO > 0) { num* Lp = A + (int64_t)KE * lda + K0; num* A22 = A + (int64_t)KE * lda + KE;      // A22 -= L21 L21^T (lower), K = panel width
+      if (remO > 0) { const int kw = KE - K0; num* Lp = A + (int64_t)KE * lda + K0; num* A22 = A + (int64_t)KE * lda + KE;
         split_rows(tA, Lp, lda, remO, kw, use_tc(remO, remO, kw) ? 1 : 0);
-        if (!carved) rank_update(tA, 0, remO, 0, remO, A22, 1);
-        else { const int nbn = std::min(32, remO), below = remO - nbn;                                  // the next diagonal block is done (and being factored): the rows below it
-          rank_update(tA, nbn, below, 0, nbn, A22 + (int64_t)nbn * lda, 0);
-          rank_update(tA, nbn, below, nbn, below, A22 + (int64_t)nbn * lda + nbn, 1); } }
+        gemm(tA, 0, tA, 0, remO, remO, A22, lda, 1, A22, lda, 1, 0, 0, 0, 0, 1); }   // A22 -= L21 L21^T (lower), K = panel width
     }
-    if (pending) { CK(cudaStreamWaitEvent(st, la_evP, 0)); pending = false; }
     nlaunch++, k_zero_upper<NL><<<grid_for((int64_t)n * n), 256, 0, st>>>(n, A, lda);
     // rows of the inverse below the diagonal blocks: M[i,0:k0] = -inv(L_ii) * (L[i,0:k0] * M[0:k0,0:k0])
     if (full_inverse && n > 32) {
@@ -720,8 +692,6 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaFuncSetAttribute(k_potrf_diag<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM(NL)));
     CK(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     CK(cudaEventCreate(&pe0)); CK(cudaEventCreate(&pe1));
-    { auto mk = [&](cudaStream_t& s_, cudaEvent_t& a_, cudaEvent_t& b_) { CK(cudaStreamCreate(&s_)); CK(cudaEventCreateWithFlags(&a_, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b_, cudaEventDisableTiming)); };
-      mk(la_st, la_evD, la_evP); for (Ctx* c : {&side, &side2, &side3}) mk(c->la_st, c->la_evD, c->la_evP); for (int k = 1; k < NCTX; k++) mk(pctx[k].la_st, pctx[k].la_evD, pctx[k].la_evP); }
     mp_zero(hconst);
     double dv[10] = {o.beta_infeasible, o.beta_feasible, o.gamma, o.omega_p, o.omega_d, o.duality_gap_threshold, o.dual_error_threshold, o.primal_error_threshold, o.max_complementary_gap, o.step_length_threshold};
     for (int i = 0; i < 10; i++) mp_from_double(hopt[i], dv[i]);
@@ -741,8 +711,6 @@ template <int NL> struct Solver : SolverBase {
     if (tc_bytes) cudaFree(tc_bytes); if (tc_top) cudaFree(tc_top); if (tc_raw) cudaFree(tc_raw); if (pe0) cudaEventDestroy(pe0); if (pe1) cudaEventDestroy(pe1);
     for (void* p : allocs) cudaFree(p);
     if (wstage) cudaFree(wstage); if (gbuf) cudaFree(gbuf); if (lane_buf) cudaFree(lane_buf); if (lane_E) cudaFree(lane_E);
-    { auto rm = [&](cudaStream_t s_, cudaEvent_t a_, cudaEvent_t b_) { if (a_) cudaEventDestroy(a_); if (b_) cudaEventDestroy(b_); if (s_) cudaStreamDestroy(s_); };
-      rm(la_st, la_evD, la_evP); for (Ctx* c : {&side, &side2, &side3}) rm(c->la_st, c->la_evD, c->la_evP); for (int k = 1; k < NCTX; k++) rm(pctx[k].la_st, pctx[k].la_evD, pctx[k].la_evP); }
     drop_graph(); for (auto& e : ev) cudaEventDestroy(e); for (auto& r : evD) for (auto& e : r) cudaEventDestroy(e);
     cudaStreamDestroy(st);
   }
