@@ -49,9 +49,9 @@ SNAP_ITER = 3               # the snapshot is the iterate after this many iterat
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from `ncu --set full` captures of this
 # build (profiles/): keyed by (workload, class).  None = not captured for this build.
 NCU_TRAFFIC = {
-    # tc::k_gemm_tc grid (2,148,1) on one 63-constraint chunk (18900 x 300 x 300): 651.5 MB read + 176.3 MB written
-    # (profiles/r02_tc_kernel_ncu_full.txt; algorithmic: 212 MB of left-operand planes in, 224 MB of byte planes + carry plane out)
-    ("maxcut", "tc_large"): 827.7e6,
+    # tc::k_gemm_tc grid (2,148,1) on one 63-constraint chunk (18900 x 300 x 300): 668.8 MB read + 176.2 MB written per launch
+    # (profiles/r02_tc_kernel_ncu_full.txt, final build; algorithmic: 212 MB of left-operand planes in, 224 MB of byte planes + carry plane out)
+    ("maxcut", "tc_large"): 845.0e6,
 }
 
 

@@ -444,7 +444,8 @@ template <int NL> struct Solver : SolverBase {
     dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, a.batch);
     nlaunch++, tc::k_gemm_tc<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(mA, mB, a);
     const int64_t tot_ = (int64_t)batch * M * N;
-    nlaunch++, k_tc_recombine<NL><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1, trans, ns_cur);
+    if (ns_cur < NS) nlaunch++, k_tc_recombine<NL, true><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1, trans, ns_cur);
+    else nlaunch++, k_tc_recombine<NL, false><<<(unsigned)((tot_ + 127) / 128), 128, 0, st>>>(M, N, Npitch, a.batch, tc_bytes, tc_top, A.E, a_bvec, B.E, b_bvec, C, ldc, c_bs, D, ldd, d_bs, mode, lower_only, nch > 1 ? nch : 1, trans, NS);
   }
   // ---- optional per-launch GEMM profile (bench.py roofline) ------------------------------------
   bool prof_on = false; cudaEvent_t pe0 = nullptr, pe1 = nullptr; double prof_ms[3] = {0, 0, 0}, prof_flops[3] = {0, 0, 0}; long prof_n[3] = {0, 0, 0};   // 0: CUDA-core path, 1: tcgen05 small outputs, 2: tcgen05 outputs >= 1e6 numbers

@@ -470,7 +470,7 @@ template <int NL> __global__ void __launch_bounds__(256) k_split_tc_t(VecView v,
 }
 
 // byte planes + top -> multi-limb C (op with D), one thread per output
-template <int NL> __global__ void k_tc_recombine(int M, int N, int Npitch, int batch, const uint8_t* obytes, const int32_t* otop,
+template <int NL, bool PARTIAL = false> __global__ void k_tc_recombine(int M, int N, int Npitch, int batch, const uint8_t* obytes, const int32_t* otop,
                                                  const int32_t* EA, int64_t a_bvec, const int32_t* EB, int64_t b_bvec,
                                                  mpn<NL>* C, int ldc, int64_t c_bs, const mpn<NL>* D, int ldd, int64_t d_bs, int mode, int lower_only, int nsum, int trans, int ns_used = I8Cfg<NL>::NS) {
   constexpr int NS = I8Cfg<NL>::NS;
@@ -490,8 +490,10 @@ template <int NL> __global__ void k_tc_recombine(int M, int N, int Npitch, int b
   for (int z = 0; z < (nsum > 1 ? nsum : 1); z++) {
     const size_t off = ((size_t)(nsum > 1 ? z : bz) * M + m) * Npitch + n;
     uint32_t dg[NS];
+    // PARTIAL (matmul_prec): diagonals beyond ns_used were not produced.  A separate instantiation: predicating the 35 byte loads of the
+    // full-precision kernel doubled its time (114 -> 228 us per 5.7e6 outputs)
 #pragma unroll
-    for (int s = 0; s < NS; s++) dg[s] = s < ns_used ? obytes[(size_t)s * plane + off] : 0u;      // diagonals beyond ns_used were not produced (matmul_prec)
+    for (int s = 0; s < NS; s++) { if constexpr (PARTIAL) dg[s] = s < ns_used ? obytes[(size_t)s * plane + off] : 0u; else dg[s] = obytes[(size_t)s * plane + off]; }
     const int64_t top = (int64_t)otop[off] * 256 + (int64_t)dg[0];
     mpn<NL> t;
     if (ea == I8_EXP_NONE || eb == I8_EXP_NONE) mp_zero(t); else i8_recombine<NL>(t, top, dg, ea + eb);

@@ -94,3 +94,19 @@ def test_matmul_prec_produces_fewer_diagonals_and_still_converges():
     with mpmath.workprec(400):
         p = mpmath.mpf(g["p_obj"])
         assert abs(res.p_obj - p) <= mpmath.mpf(10) ** -13 * abs(p)
+
+
+def test_sparse_term_arguments_are_validated():
+    """Out-of-range entries and repeated positions are refused (the scatter kernel writes without ordering)."""
+    from clrs_b200 import PSDBlock, Cluster, ClusteredSDP
+    one = wire.to_wire(1, PREC)
+
+    def make(rows, cols, mirror):
+        blk = PSDBlock(m=1, delta=3, high_rank=True, C=wire.wire_eye_scaled(3, 1, PREC))
+        blk.sparse[0] = (np.array(rows, dtype=np.int32), np.array(cols, dtype=np.int32), wire.to_wire([1] * len(rows), PREC), mirror)
+        return ClusteredSDP(prec=PREC, maximize=True, constant=wire.to_wire(0, PREC), b=wire.wire_zeros((0,), PREC),
+                            clusters=[Cluster(B=wire.wire_zeros((1, 0), PREC), c=wire.to_wire([1], PREC), blocks=[blk])])
+    for rows, cols, mirror in (([0, 0], [1, 1], False), ([0, 1], [1, 0], True), ([3], [0], False), ([0], [-1], False)):
+        with pytest.raises(RuntimeError):
+            Solver(make(rows, cols, mirror), lib="device")
+    Solver(make([0, 1], [1, 0], False), lib="device").close()           # both triangles listed explicitly: fine without mirroring
