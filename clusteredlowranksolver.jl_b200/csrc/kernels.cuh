@@ -253,6 +253,9 @@ template <int NL> __global__ void __launch_bounds__(1024) k_trsv_block(int nb, c
 // waits for CTAs that were dispatched before it.  The diagonal triangle is staged while waiting; an update
 // r_b -= L[b, k] x_k is done as soon as x_k is published (st.release / ld.acquire on a per-block flag).  Same arithmetic in
 // the same order as k_trsv_block + k_trsv_update: the results are bit-identical.  `ready` (one word per block) must be zero.
+// (Measured and not kept, round 2: publishing the rows of the in-block substitution through per-row shared-memory flags instead of one CTA
+//  barrier per column — bit-identical, all tests green — changed nothing: `solve` 1.65 -> 1.70 ms on config 2, 12.7 -> 13.1 ms on sphere packing
+//  (4,31).  The chain is the 32 dependent w_mul + w_sub pairs themselves, not the barrier between them.)
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 template <int NL> __device__ __forceinline__ mpn<NL> ld_cg_num(const mpn<NL>* p) {
@@ -263,7 +266,7 @@ template <int NL> __device__ __forceinline__ mpn<NL> ld_cg_num(const mpn<NL>* p)
 }
 template <int NL> __global__ void __launch_bounds__(1024) k_trsv_fused(int n, const mpn<NL>* L, int ldl, const mpn<NL>* Minv, int ldm, mpn<NL>* x, int transposed, unsigned* ready) {
   static_assert(sizeof(mpn<NL>) == 4 * (NL + 2), "mpn layout: NL limbs, exponent, sign");
-  __shared__ mpn<NL> Ls[528]; __shared__ mpn<NL> rinv[32]; __shared__ mpn<NL> rs[32]; __shared__ mpn<NL> xk[32]; __shared__ volatile int done[32];
+  __shared__ mpn<NL> Ls[528]; __shared__ mpn<NL> rinv[32]; __shared__ mpn<NL> rs[32]; __shared__ mpn<NL> xk[32];
   const int nblk = (n + 31) / 32;
   const int b = transposed ? nblk - 1 - (int)blockIdx.x : (int)blockIdx.x;
   const int k0 = b * 32, nb = min(32, n - k0);
@@ -282,30 +285,20 @@ template <int NL> __global__ void __launch_bounds__(1024) k_trsv_fused(int n, co
     if (w < nb) { mpn<NL> v = xk[lane]; mpn<NL> acc; mp_zero(acc); if (lane < knb) mp_mul(acc, a, v); warp_reduce_add(acc);
       if (lane == 0) { mpn<NL> r = rs[w]; mp_sub(r, r, acc); rs[w] = r; } }
   }
-  if (threadIdx.x < 32) done[threadIdx.x] = 0;
   __syncthreads();
   if constexpr (NL == 8 || NL == 16) {
-    // Row w is owned by warp w and stays in its registers; a row is published (rs[w], then done[w]) once all earlier columns have been
-    // subtracted, and a warp waits only for the column it needs next.  Same operations in the same order as the barrier-per-column form of
-    // k_trsv_block (bit-identical), without 32 CTA-wide barriers and the shared-memory round trip of the row on the critical path
-    // (ncu, profiles/r02_trsv_ncu.txt: the barrier was the first stall reason, 27-38 warps stalled per issue).
-    if (w < nb) {
-      wnum r = w_mul<NL>(w_load<NL>(&rs[w]), w_load<NL>(&rinv[w]));
-      const int ncols = transposed ? nb - 1 - w : w;
-      for (int s = 0; s < ncols; s++) {
-        const int c = transposed ? nb - 1 - s : s;
-        // only the row right behind column c is on the critical path and polls tightly; the others back off so that their polling does not take
-        // issue slots from the warp that is producing the column
-        { const int dist = transposed ? c - w : w - c; while (done[c] == 0) { if (dist > 1) __nanosleep(100); } }
-        __threadfence_block();
-        const wnum l = w_load<NL>(transposed ? &Ls[c * (c + 1) / 2 + w] : &Ls[w * (w + 1) / 2 + c]);
-        r = w_sub<NL>(r, w_mul<NL>(l, w_load<NL>(&rs[c])));
-      }
-      __syncwarp(); w_store<NL>(&rs[w], r);
-      __threadfence_block(); __syncwarp();
-      if (lane == 0) done[w] = 1;
-    }
+    if (w < nb) { const wnum r = w_mul<NL>(w_load<NL>(&rs[w]), w_load<NL>(&rinv[w])); __syncwarp(); w_store<NL>(&rs[w], r); }
     __syncthreads();
+    for (int s = 0; s < nb; s++) {
+      const int c = transposed ? nb - 1 - s : s;
+      const bool upd = transposed ? (w < c) : (w > c && w < nb);
+      if (upd) {
+        const wnum l = w_load<NL>(transposed ? &Ls[c * (c + 1) / 2 + w] : &Ls[w * (w + 1) / 2 + c]);
+        const wnum r = w_sub<NL>(w_load<NL>(&rs[w]), w_mul<NL>(l, w_load<NL>(&rs[c])));
+        __syncwarp(); w_store<NL>(&rs[w], r);
+      }
+      __syncthreads();
+    }
   } else {
     if (w == 0) { mpn<NL> r = rs[lane]; warp_trisolve32<NL>(nb, Ls, rinv, r, transposed); rs[lane] = r; }
     __syncthreads();
