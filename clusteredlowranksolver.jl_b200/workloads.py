@@ -487,6 +487,57 @@ def sphere_packing(n, d, r, prec=256):
                             name=f"sphere_packing(n={n},d={d},Nr={Nr})")
 
 
+def cohnelkies(n, d, r=1, prec=256):
+    """The Cohn-Elkies linear-programming bound for sphere packings in R^n as an SDP (examples/SpherePacking.jl:117-185;
+    test/runtests_solver.jl:19-20: cohnelkies(8, 15, prec=256) = pi^4/384 to 1e-4).
+
+    Free variables a_1..a_{2d+1} (a_0 = 1 is the constant of the first constraint):
+      con1 at the rescaled Laguerre points x:   <SOS21, b b^T> + x <SOS22, b b^T> - sum_k a_k x^k = 1
+      con2 at the points x + r^2:               b_0(x)^2 SOS31 + (x - r^2) <SOS32, b b^T> + sum_k a_k k!/pi^k L_k(pi x) = -L_0(pi x) = -1
+      minimise   vol(B(r/2)) (L_0(0) + sum_k a_k k!/pi^k L_k(0))
+    Two clusters coupled by the free variables; SOS31 is given as a 1 x 1 matrix (the dense path), the others as rank-1 terms;
+    the basis is re-orthogonalised on the shifted samples for the second constraint, as the example does."""
+    with mpmath.workprec(prec + 64):
+        r = mpf(r.numerator) / r.denominator if isinstance(r, Fraction) else mpf(r)
+        deg = 2 * d + 1
+        ns = deg + 1
+        alpha = mpf(n) / 2 - 1
+        N = deg
+        vol = mpmath.sqrt(mpmath.pi) ** n / mpmath.gamma(mpf(n) / 2 + 1) * (r / 2) ** n
+        polys = laguerre_coefficients(deg, alpha, 2 * mpmath.pi)
+        maxc = [max(pl) for pl in polys]
+        evalb = lambda xs: [[mpmath.polyval(list(reversed(polys[k])), x) / maxc[k] for k in range(deg + 1)] for x in xs]
+        fact = [mpmath.factorial(k) / mpmath.pi ** k for k in range(deg + 1)]
+        # constraint 1
+        x1 = sample_points_rescaled_laguerre(deg)
+        V1, x1 = approximatefekete(evalb(x1), x1)
+        b21 = PSDBlock(m=1, delta=d + 1, high_rank=False, C=wire.wire_zeros((d + 1, d + 1), prec), name="SOS21")
+        b22 = PSDBlock(m=1, delta=d + 1, high_rank=False, C=wire.wire_zeros((d + 1, d + 1), prec), name="SOS22")
+        B1 = []
+        for p, x in enumerate(x1):
+            vec = [V1[p, k] for k in range(d + 1)]
+            b21.lowrank.append(_rank1(0, 0, p, 1, vec, prec))
+            b22.lowrank.append(_rank1(0, 0, p, x, vec, prec))
+            B1.append([-x ** k for k in range(1, deg + 1)])
+        c1 = Cluster(B=_w(B1, prec), c=_w([1] * ns, prec), blocks=[b21, b22])
+        # constraint 2
+        x2 = [x + r ** 2 for x in sample_points_rescaled_laguerre(deg)]
+        V2, x2 = approximatefekete(evalb(x2), x2)
+        b31 = PSDBlock(m=1, delta=1, high_rank=True, C=wire.wire_zeros((1, 1), prec), name="SOS31")
+        b32 = PSDBlock(m=1, delta=d + 1, high_rank=False, C=wire.wire_zeros((d + 1, d + 1), prec), name="SOS32")
+        B2 = []
+        for p, x in enumerate(x2):
+            b31.dense[p] = _w([[V2[p, 0] ** 2]], prec)
+            b32.lowrank.append(_rank1(0, 0, p, x - r ** 2, [V2[p, k] for k in range(d + 1)], prec))
+            Lv = laguerre_values(deg, alpha, mpmath.pi * x)
+            B2.append([fact[k] * Lv[k] for k in range(1, deg + 1)])
+        c2 = Cluster(B=_w(B2, prec), c=_w([-1] * ns, prec), blocks=[b31, b32])
+        L0 = laguerre_values(deg, alpha, mpf(0))
+        bvec = [vol * fact[k] * L0[k] for k in range(1, deg + 1)]
+        return ClusteredSDP(prec=prec, maximize=False, constant=_w(vol * L0[0], prec), b=_w(bvec, prec), clusters=[c1, c2],
+                            name=f"cohnelkies(n={n},d={d})")
+
+
 # ---------------------------------------------------------------------------
 # config 4: three-point bound for spherical codes (examples/ThreePointBound.jl:45-169)
 # ---------------------------------------------------------------------------

@@ -519,6 +519,17 @@ def test_two_radii_sphere_packing_d15_prec300_reference_test_on_device():
 
 
 @pytest.mark.gpu
+def test_cohn_elkies_8_15_reference_test_on_device():
+    """test/runtests_solver.jl:19-20 on the device: cohnelkies(8, 15, prec=256) = pi^4/384 to 1e-4, and the oracle's value and iteration count."""
+    sdp = workloads.cohnelkies(8, 15)
+    r = solvesdp(sdp, lib="device")
+    o = solvesdp(sdp, lib="oracle")
+    with mpmath.workprec(200):
+        assert r.status == o.status == "Optimal" and 0 < r.p_obj - mpmath.pi ** 4 / 384 < mpmath.mpf(10) ** -4
+        assert abs(r.p_obj - o.p_obj) < mpmath.mpf(10) ** -14 and abs(r.iterations - o.iterations) <= 1
+
+
+@pytest.mark.gpu
 def test_three_point_bound_d14_first_two_iterations_match_the_oracle():
     """BASELINE config 4 at its largest survey shape (d2 = d3 = 14: P = 894, 61 blocks up to n = 225).  A full oracle solve of it
     takes hours on the CPUs of the build container (~9 minutes per iteration), so the golden holds the first two iterations:

@@ -66,6 +66,16 @@ def test_two_radii_sphere_packing_near_cohn_elkies():      # test/runtests_solve
         assert target - mpmath.mpf(10) ** -12 < r.p_obj < target + mpmath.mpf(4) / 1000
 
 
+def test_cohn_elkies_8_15_as_in_the_reference_test():
+    """test/runtests_solver.jl:19-20: cohnelkies(8, 15, prec=256) is pi^4/384 to 1e-4 (default gap 1e-15); one dense 1 x 1 block,
+    three rank-1 SOS blocks, two clusters coupled by 31 free variables."""
+    r = solve(workloads.cohnelkies(8, 15), gap=1e-15)
+    with mpmath.workprec(200):
+        target = mpmath.pi ** 4 / 384
+        assert 0 < r.p_obj - target < mpmath.mpf(10) ** -4
+        assert abs(r.p_obj - target - mpmath.mpf("7.0919e-5")) < mpmath.mpf(10) ** -8     # the same degree-15 bound as the two-radii SDP below
+
+
 def test_two_radii_sphere_packing_d15_prec300_as_in_the_reference_test():
     """test/runtests_solver.jl:21-22: Nsphere_packing(8, 15, [1//2, 1//2], 2, prec=300) is pi^4/384 to 1e-4 (default gap 1e-15)."""
     r = solve(workloads.sphere_packing(8, 15, [Fraction(1, 2), Fraction(1, 2)], prec=300), gap=1e-15)
