@@ -59,3 +59,26 @@ def test_product_package_cannot_reach_the_oracle_without_registration():
             "except RuntimeError as e:\n    print('refused')\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
     assert out.stdout.strip() == "refused", (out.stdout, out.stderr[-500:])
+
+
+def test_ctypes_structs_have_the_layout_the_c_compiler_gives_the_header(tmp_path):
+    """sizeof / offsetof of clrs_options and clrs_iter_info as gcc sees include/clrs_b200.h, against the ctypes mirrors in api.py
+    (the Julia structs in INTEGRATION.md list the same fields in the same order)."""
+    import subprocess
+    from clrs_b200 import IterInfo
+    fields_o = [n for n, _ in Options._fields_]
+    fields_i = [n for n, _ in IterInfo._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "clrs_b200.h")}"', 'int main(void) {',
+           '  printf("%zu %zu\\n", sizeof(clrs_options), sizeof(clrs_iter_info));']
+    src += [f'  printf("%zu\\n", offsetof(clrs_options, {n}));' for n in fields_o]
+    src += [f'  printf("%zu\\n", offsetof(clrs_iter_info, {n}));' for n in fields_i]
+    src += ['  return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(c)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(out[0]), int(out[1])] == [C.sizeof(Options), C.sizeof(IterInfo)]
+    offs = [int(v) for v in out[2:]]
+    assert offs[:len(fields_o)] == [getattr(Options, n).offset for n in fields_o]
+    assert offs[len(fields_o):] == [getattr(IterInfo, n).offset for n in fields_i]
