@@ -345,6 +345,16 @@ class Solver:
         self._call("mp_cholesky", self.h, C.c_int32(n), A.ctypes.data_as(C.c_void_p), L.ctypes.data_as(C.c_void_p))
         return L
 
+    def mp_qr_pivot(self, A: np.ndarray):
+        """Column-pivoted QR (clrs_mp_qr_pivot): returns (R wire (min(m,n), n) in the pivoted column order, perm int32 (n,))."""
+        m, n = A.shape
+        R = wire.wire_zeros((min(m, n), n), self.prec)
+        perm = np.zeros(n, dtype=np.int32)
+        A = np.ascontiguousarray(A)
+        self._call("mp_qr_pivot", self.h, C.c_int32(m), C.c_int32(n), A.ctypes.data_as(C.c_void_p), R.ctypes.data_as(C.c_void_p),
+                   perm.ctypes.data_as(C.c_void_p))
+        return R, perm
+
 
 STATUS = ["Optimal", "NearOptimal", "Feasible", "PrimalFeasible", "DualFeasible", "NotConverged"]
 

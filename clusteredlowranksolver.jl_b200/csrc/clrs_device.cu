@@ -249,6 +249,7 @@ struct SolverBase {
   virtual int get_objectives(void* d, void* p, void* g) = 0;
   virtual int mp_gemm(int M, int N, int K, const void* A, const void* B, void* C, int path, double* ms) = 0;
   virtual int mp_cholesky(int n, const void* A, void* L) = 0;
+  virtual int mp_qr_pivot(int m, int n, const void* A, void* R, int32_t* perm) = 0;
   virtual int64_t debug_get(const char* what, int j, int l, void* out, int64_t cap) = 0;
   virtual void profile(int enable) = 0;
   virtual void profile_get(double* out) = 0;
@@ -1416,6 +1417,27 @@ template <int NL> struct Solver : SolverBase {
     CK(cudaGetLastError());
     download_wire(C, dC, (size_t)M * N_); return 0;
   }
+  // column-pivoted QR of an m x n matrix (modified Gram-Schmidt, pivot = largest remaining column norm): R is min(m,n) x n in the pivoted
+  // column order, perm[k] = original index of pivoted column k  (the core of preprocess!, src/pre_postprocessing.jl:36,56,104)
+  int mp_qr_pivot(int m, int n, const void* Aw, void* Rw, int32_t* permw) override {
+    if (m <= 0 || n <= 0) { err = "clrs_mp_qr_pivot: empty matrix"; return CLRS_ERR_ARG; }
+    Scratch tmp; const int kmax = std::min(m, n);
+    num* dA = talloc<num>(tmp, (size_t)m * n); num* dR = talloc<num>(tmp, (size_t)kmax * n); num* dq = talloc<num>(tmp, (size_t)m); num* dn = talloc<num>(tmp, (size_t)n);
+    int32_t* dperm = talloc<int32_t>(tmp, (size_t)n); int* dpiv = talloc<int>(tmp, 1);
+    wire_to_device(dA, Aw, (size_t)m * n);
+    { std::vector<int32_t> hp(n); for (int i = 0; i < n; i++) hp[i] = i; CK(cudaMemcpyAsync(dperm, hp.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+    nlaunch++, k_qr_colnorm2<NL><<<(n + 7) / 8, 256, 0, st>>>(m, n, dA, n, dn);
+    for (int k0 = 0; k0 < kmax; k0++) {
+      nlaunch++, k_qr_pivot<NL><<<1, 32, 0, st>>>(n, k0, dn, dpiv);
+      nlaunch++, k_qr_swap<NL><<<grid_for((int64_t)m + k0 + 1), 256, 0, st>>>(m, k0, dpiv, dA, n, dR, n, dn, dperm);
+      nlaunch++, k_qr_scale<NL><<<grid_for((int64_t)m, 256, 64), 256, 0, st>>>(m, k0, dA, n, dn, dR, n, dq);
+      if (k0 + 1 < n) nlaunch++, k_qr_project<NL><<<(n - k0 - 1 + 7) / 8, 256, 0, st>>>(m, n, k0, dA, n, dq, dR, n, dn);
+    }
+    CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+    download_wire(Rw, dR, (size_t)kmax * n);
+    CK(cudaMemcpyAsync(permw, dperm, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    return 0;
+  }
   int mp_cholesky(int n, const void* A, void* Lw) override {
     Scratch tmp; num* dA = talloc<num>(tmp, (size_t)n * n); num* dM = talloc<num>(tmp, (size_t)n * n);
     wire_to_device(dA, A, (size_t)n * n);
@@ -1552,6 +1574,7 @@ int clrs_plan_shards(int32_t J, const double* p3, const int32_t* nblocks, const 
 }
 int clrs_mp_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K, const void* A, const void* B, void* C, int32_t path, double* ms) { GUARD(h, return h->s->mp_gemm(M, N, K, A, B, C, path, ms);) }
 int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L) { GUARD(h, return h->s->mp_cholesky(n, A, L);) }
+int clrs_mp_qr_pivot(clrs_handle* h, int32_t m, int32_t n, const void* A, void* R, int32_t* perm) { GUARD(h, return h->s->mp_qr_pivot(m, n, A, R, perm);) }
 void clrs_profile(clrs_handle* h, int32_t enable) { h->s->profile(enable); }
 void clrs_profile_get(clrs_handle* h, double* out10) { h->s->profile_get(out10); }
 double clrs_last_iteration_ms(clrs_handle* h) { return h->s->last_iteration_ms(); }

@@ -827,6 +827,65 @@ template <int NL> __global__ void k_scatter_triplets(int nnz, const int32_t* row
 }
 
 // ---------------------------------------------------------------------------
+// Column-pivoted QR in multi-limb arithmetic (the numerical core of `preprocess!`,
+// src/pre_postprocessing.jl:36 `qr(mpsd, ColumnNorm())` — the reference does it in BigFloat on the host and warns that it
+// "can be slow", docs/src/solving.md:17).  Modified Gram-Schmidt with the pivot = largest remaining column norm; A (m x n, row-major) is
+// overwritten by the orthogonalised columns, R (kmax x n) receives the triangular factor in the PIVOTED column order, perm the order.
+// Per step: k_qr_pivot (arg max) -> k_qr_swap -> k_qr_scale (r_kk, q = a_k / r_kk) -> k_qr_project (r_kj = q . a_j, a_j -= r_kj q and the
+// new ||a_j||^2, one warp per column).
+// ---------------------------------------------------------------------------
+template <int NL> __global__ void __launch_bounds__(256) k_qr_colnorm2(int m, int n, const mpn<NL>* A, int lda, mpn<NL>* norms) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31; if (j >= n) return;
+  mpn<NL> acc; mp_zero(acc);
+  for (int i = lane; i < m; i += 32) { mpn<NL> v = A[(int64_t)i * lda + j]; mp_mul(v, v, v); mp_add(acc, acc, v); }
+  warp_reduce_add(acc);
+  if (lane == 0) norms[j] = acc;
+}
+// piv[0] = first index j >= k0 with the largest norms[j]
+template <int NL> __global__ void k_qr_pivot(int n, int k0, const mpn<NL>* norms, int* piv) {
+  __shared__ int best_i[32]; __shared__ mpn<NL> best_v[32];
+  const int lane = threadIdx.x; int bi = -1; mpn<NL> bv; mp_zero(bv);
+  for (int j = k0 + lane; j < n; j += 32) { const mpn<NL> v = norms[j]; if (bi < 0 || mp_cmp(v, bv) > 0) { bi = j; bv = v; } }
+  best_i[lane] = bi; best_v[lane] = bv; __syncwarp();
+  if (lane == 0) { int b = -1; mpn<NL> v; mp_zero(v);
+    for (int t = 0; t < 32; t++) { if (best_i[t] < 0) continue; const int c = b < 0 ? 1 : mp_cmp(best_v[t], v); if (c > 0 || (c == 0 && best_i[t] < b)) { b = best_i[t]; v = best_v[t]; } }
+    piv[0] = b < 0 ? k0 : b; }
+}
+// swap columns k0 and piv[0] of A (m rows), of the rows of R already computed (k0 of them), of norms and of perm
+template <int NL> __global__ void k_qr_swap(int m, int k0, const int* piv, mpn<NL>* A, int lda, mpn<NL>* R, int ldr, mpn<NL>* norms, int32_t* perm) {
+  const int p = piv[0]; if (p == k0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m + k0 + 1; i += gridDim.x * blockDim.x) {
+    if (i < m) { mpn<NL>* a = A + (int64_t)i * lda; const mpn<NL> t = a[k0]; a[k0] = a[p]; a[p] = t; }
+    else if (i < m + k0) { mpn<NL>* r = R + (int64_t)(i - m) * ldr; const mpn<NL> t = r[k0]; r[k0] = r[p]; r[p] = t; }
+    else { const mpn<NL> t = norms[k0]; norms[k0] = norms[p]; norms[p] = t; const int32_t q = perm[k0]; perm[k0] = perm[p]; perm[p] = q; }
+  }
+}
+// R[k0][k0] = ||a_k0||, q = a_k0 / ||a_k0|| (also written back into column k0 of A); a zero column gives r = 0, q = 0
+template <int NL> __global__ void __launch_bounds__(256) k_qr_scale(int m, int k0, mpn<NL>* A, int lda, const mpn<NL>* norms, mpn<NL>* R, int ldr, mpn<NL>* q) {
+  __shared__ mpn<NL> rinv;
+  if (threadIdx.x == 0) { const mpn<NL> n2 = norms[k0]; mpn<NL> r, ri; if (n2.sign > 0) mp_sqrt_rsqrt(r, ri, n2); else { mp_zero(r); mp_zero(ri); }
+    rinv = ri; if (blockIdx.x == 0) R[(int64_t)k0 * ldr + k0] = r; }
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) { mpn<NL> v = A[(int64_t)i * lda + k0]; mp_mul(v, v, rinv); A[(int64_t)i * lda + k0] = v; q[i] = v; }
+}
+// columns j > k0, one warp each: r = q . a_j -> R[k0][j];  a_j -= r q;  norms[j] = ||a_j||^2 of the updated column
+template <int NL> __global__ void __launch_bounds__(256) k_qr_project(int m, int n, int k0, mpn<NL>* A, int lda, const mpn<NL>* q, mpn<NL>* R, int ldr, mpn<NL>* norms) {
+  const int j = k0 + 1 + blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31; if (j >= n) return;
+  mpn<NL> acc; mp_zero(acc);
+  for (int i = lane; i < m; i += 32) { mpn<NL> v = A[(int64_t)i * lda + j]; mp_mul(v, v, q[i]); mp_add(acc, acc, v); }
+  warp_reduce_add(acc);
+  mpn<NL> r;                                                             // lane 0 holds the sum: broadcast it
+#pragma unroll
+  for (int t = 0; t < NL; t++) r.l[t] = __shfl_sync(0xffffffffu, acc.l[t], 0);
+  r.exp = __shfl_sync(0xffffffffu, acc.exp, 0); r.sign = __shfl_sync(0xffffffffu, acc.sign, 0);
+  if (lane == 0) R[(int64_t)k0 * ldr + j] = r;
+  mpn<NL> n2; mp_zero(n2);
+  for (int i = lane; i < m; i += 32) { mpn<NL> v = A[(int64_t)i * lda + j], t; mp_mul(t, r, q[i]); mp_sub(v, v, t); A[(int64_t)i * lda + j] = v; mp_mul(v, v, v); mp_add(n2, n2, v); }
+  warp_reduce_add(n2);
+  if (lane == 0) norms[j] = n2;
+}
+
+// ---------------------------------------------------------------------------
 // Float64 smallest eigenvalue per block (stands in for KrylovKit's Lanczos,
 // src/solver.jl:1659-1662): Lanczos with full reorthogonalisation, one CTA per
 // block, followed by Sturm bisection on the tridiagonal.  lam[b] receives the

@@ -220,6 +220,11 @@ int clrs_mp_gemm(clrs_handle* h, int32_t M, int32_t N, int32_t K,
 /* lower Cholesky factor of an n x n matrix; returns CLRS_ERR_CHOL_X on a
  * non-positive pivot (src/tools.jl:75-107) */
 int clrs_mp_cholesky(clrs_handle* h, int32_t n, const void* A, void* L);
+/* column-pivoted QR of an m x n matrix of wire numbers (modified Gram-Schmidt on the device, pivot = the largest remaining column
+ * norm, first index on ties): R (min(m,n) x n, row-major, caller-allocated) in the pivoted column order with a non-negative
+ * diagonal, perm[k] = original index of pivoted column k.  The numerical core of preprocess! (src/pre_postprocessing.jl:36:
+ * `qr(mpsd, ColumnNorm())` in BigFloat on the host); |R[i][i]| < tol marks the linearly dependent constraints. */
+int clrs_mp_qr_pivot(clrs_handle* h, int32_t m, int32_t n, const void* A, void* R, int32_t* perm);
 /* device self-test of the warp-cooperative arithmetic against the single-thread routines; returns the
  * number of mismatching samples (0 = pass), -1 on a CUDA error */
 int clrs_debug_selftest(clrs_handle* h);

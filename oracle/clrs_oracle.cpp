@@ -728,6 +728,26 @@ int clrs_oracle_mp_gemm(Oracle*, int32_t M, int32_t N, int32_t K, const void* A,
 int clrs_oracle_mp_cholesky(Oracle*, int32_t n, const void* A, void* L) {
   Mat a(n, n); mat_from_wire(a, A); int ok = cholesky(a); mat_to_wire(L, a); return ok ? 0 : 10;
 }
+// column-pivoted QR by modified Gram-Schmidt (pivot = largest remaining column norm, first index on ties): the checker of
+// clrs_mp_qr_pivot; the reference's preprocess! uses LinearAlgebra.qr(mpsd, ColumnNorm()) in BigFloat (src/pre_postprocessing.jl:36),
+// whose R agrees with this one up to the signs of its rows
+int clrs_oracle_mp_qr_pivot(Oracle*, int32_t m, int32_t n, const void* Aw, void* Rw, int32_t* perm) {
+  Mat A(m, n); mat_from_wire(A, Aw); const int kmax = m < n ? m : n; Mat R(kmax, n); std::vector<Num> norms(n); Num t, r, ri;
+  for (int j = 0; j < n; j++) { perm[j] = j; norms[j].v._exp = EXP_ZERO; norms[j].v._sign = 1; for (int i = 0; i < m; i++) { mpfr_mul(t.p(), A(i, j), A(i, j), RN); mpfr_add(norms[j].p(), norms[j].p(), t.p(), RN); } }
+  for (int k = 0; k < kmax; k++) {
+    int p = k; for (int j = k + 1; j < n; j++) if (cmp(norms[j].p(), norms[p].p()) > 0) p = j;
+    if (p != k) { for (int i = 0; i < m; i++) { set(t.p(), A(i, k)); set(A(i, k), A(i, p)); set(A(i, p), t.p()); }
+      for (int i = 0; i < k; i++) { set(t.p(), R(i, k)); set(R(i, k), R(i, p)); set(R(i, p), t.p()); }
+      set(t.p(), norms[k].p()); set(norms[k].p(), norms[p].p()); set(norms[p].p(), t.p()); std::swap(perm[k], perm[p]); }
+    if (sgn(norms[k].p()) > 0) { mpfr_sqrt(r.p(), norms[k].p(), RN); set(R(k, k), r.p()); for (int i = 0; i < m; i++) mpfr_div(A(i, k), A(i, k), r.p(), RN); }
+    else for (int i = 0; i < m; i++) { A(i, k)->_exp = EXP_ZERO; A(i, k)->_sign = 1; }
+    for (int j = k + 1; j < n; j++) {
+      r.v._exp = EXP_ZERO; r.v._sign = 1; for (int i = 0; i < m; i++) { mpfr_mul(t.p(), A(i, k), A(i, j), RN); mpfr_add(r.p(), r.p(), t.p(), RN); }
+      set(R(k, j), r.p()); norms[j].v._exp = EXP_ZERO; norms[j].v._sign = 1;
+      for (int i = 0; i < m; i++) { mpfr_mul(t.p(), r.p(), A(i, k), RN); mpfr_sub(A(i, j), A(i, j), t.p(), RN); mpfr_mul(t.p(), A(i, j), A(i, j), RN); mpfr_add(norms[j].p(), norms[j].p(), t.p(), RN); } }
+  }
+  mat_to_wire(Rw, R); return 0;
+}
 int64_t clrs_oracle_debug_get(Oracle* h, const char* what, int32_t j, int32_t l, void* out, int64_t cap) {
   std::string w(what); const Mat* m = nullptr;
   if (w == "S") m = &h->cl[j].S; else if (w == "LinvB") m = &h->cl[j].LinvB; else if (w == "Q") m = &h->Q;
