@@ -65,7 +65,7 @@ def test_preprocess_on_the_device_removes_the_same_constraints_as_on_the_oracle(
     blk.dense = {p: np.asarray(A) for p, A in blk.dense.items()}
     blk.dense[n] = wire.wire_eye_scaled(n, 1, PREC)
     sdp.clusters[0] = Cluster(B=wire.wire_zeros((n + 1, 0), PREC), c=w([1] * n + [n]), blocks=[blk])
-    new, cs = pp.preprocess(sdp, dev)
+    new, cs, _ = pp.preprocess(sdp, dev)
     assert len(cs) == 1 and new.clusters[0].P == n
     assert len(pp.preprocess(sdp, ora)[1]) == 1
     r = solvesdp(new, lib="device", duality_gap_threshold=1e-30)
