@@ -367,6 +367,20 @@ def main():
     S = Solver(sdp, lib="device", device=local_rank, gemm_path=args.gemm_path, comm=comm, duality_gap_threshold=GAP)
     reps = 1 if sharded else world
     W, K = max(args.warmup, 3), args.steps
+    comm_info = None
+    if sharded:                 # what the library's own plan gave every rank (stderr: one line per rank; JSON: the plan as rank 0 sees it)
+        try:
+            owners = [S.cluster_owner(j) for j in range(len(sdp.clusters))]
+            blocks = [[S.block_owner(j, l) for l in range(len(c.blocks))] for j, c in enumerate(sdp.clusters)]
+            mine_c = [j for j, o in enumerate(owners) if o == rank]
+            mine_b = sum(1 for bl in blocks for o in bl if o == rank)
+            print(f"[rank {rank}/{world}] cuda:{local_rank} leads clusters {mine_c}, holds {mine_b} of {sum(len(b) for b in blocks)} PSD blocks", file=sys.stderr, flush=True)
+            comm_info = {"nranks": world, "backend": "NCCL (ncclCommInitRank inside libclrs_b200, id broadcast with torch.distributed)",
+                         "clusters_led_per_rank": [sum(1 for o in owners if o == r) for r in range(world)],
+                         "blocks_held_per_rank": [sum(1 for bl in blocks for o in bl if o == r) for r in range(world)],
+                         "split_clusters": [j for j, bl in enumerate(blocks) if len(set(bl)) > 1]}
+        except Exception as e:      # reporting only
+            comm_info = {"nranks": world, "error": str(e)}
 
     def sync():
         torch.cuda.synchronize()
@@ -436,7 +450,7 @@ def main():
            "data": "synthetic", "config": config(args.n, world, kind, sdp), "wall_ms_per_step": 1e3 * wall / K,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes_all, "d2h_bytes_per_step": nbytes_all,
                    "path": "clrs_set_state + clrs_iterate + clrs_get_state with pinned host wire buffers"},
-           "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+           "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "comm": comm_info,
            "phase_ms": dict(zip(clrs_b200.PHASES, [round(v, 4) for v in last_info.phase_ms])),
            "solver": {"duality_gap_threshold": GAP, "snapshot_iteration": SNAP_ITER, "restore_every": RESTORE_EVERY,
                       "cuda_graph": os.environ.get("CLRS_GRAPH", "1") != "0"}}
